@@ -1,0 +1,56 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def h16(a: np.ndarray) -> torch.Tensor:
+    """uint16 bit pattern array -> fp16 CPU tensor (inverse of oracle/make_goldens.bits)."""
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.half)
+
+
+def bits16(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+
+
+def assert_bits_equal(a: torch.Tensor, b: torch.Tensor, what=""):
+    """Bit-exact fp16 equality (NaN payloads included)."""
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    x, y = bits16(a), bits16(b)
+    bad = int((x != y).sum())
+    assert bad == 0, f"{what}: {bad} of {x.size} fp16 values differ bitwise"
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.float().cpu(), b.float().cpu()
+    return float(torch.norm(a - b) / torch.norm(b).clamp_min(1e-30))
+
+
+@pytest.fixture(scope="session")
+def golden_codecs():
+    return np.load(os.path.join(GOLDEN, "codecs.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_slowpath():
+    return np.load(os.path.join(GOLDEN, "slowpath.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_state():
+    return np.load(os.path.join(GOLDEN, "state_machine.npz"))
+
+
+CODEC_CASES = ["rand_64x256", "rand_48x1152", "rand_130x64", "flux_k_96x512"]
