@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json: "compress+exchange GB/s and
+per-step latency, FLUX 1024^2 at 1/2/4/8 B200").
+
+Workload ("flux1024_patch_parallel", BASELINE.json configs[1]): one denoising step of
+FLUX.1-dev at 1024^2 = 57 attention layers x {K, V}, sequence 4096 image + 512 text tokens,
+C = 24 x 128 = 3072, fp16.  Each of the N ranks owns 4608/N tokens.  Per layer and step:
+residual-compress the local K and V shard against the cached base (1-bit sign codes +
+token x channel scales; `--codec int2` for the 2-bit preset), all-gather the compressed
+payloads over NCCL, reconstruct every origin's shard (error-feedback cache update) into the
+global K/V buffers attention reads.  Synthetic AR(1) activations with per-channel log-normal
+scales (no network: no real weights / prompts); step 0 is the reference's uncompressed
+WARMUP step and is not timed.
+
+  python bench.py [--gpus N --steps K --warmup W]            (torchrun for N > 1)
+  python bench.py --impl reference ...                        CPU arm (oracle port of the
+                                                              reference's eager torch path)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+LAYERS, SEQ, CH = 57, 4096 + 512, 3072
+METRIC = "compress+exchange GB/s (raw fp16 K/V bytes reconstructed per second, all ranks), FLUX 1024^2 patch parallel"
+UNIT = "GB/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--codec", default="binary", choices=["binary", "int2"])
+    p.add_argument("--layers", type=int, default=LAYERS)
+    p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample-layers", type=int, default=1)
+    return p.parse_args()
+
+
+def job_bytes(layers, world):
+    """Raw fp16 K/V bytes reconstructed per step, summed over ranks."""
+    return world * layers * 2 * SEQ * CH * 2
+
+
+def synth_activations(n_local, layers, versions, device, rank):
+    """AR(1) K/V per layer: x_{t+1} = rho x_t + sqrt(1-rho^2) sigma eps, rho = 0.97, per-channel
+    log-normal sigma (log-std 0.355, mean |x| ~ 0.92: the statistics of the reference's
+    activation dump)."""
+    rho = 0.97
+    out = []
+    for layer in range(layers):
+        per_kv = []
+        for j in range(2):
+            g = torch.Generator(device=device).manual_seed(1234 + 1000 * rank + 2 * layer + j)
+            sigma = torch.exp(0.355 * torch.randn(CH, generator=g, device=device)) * 1.15
+            x = torch.randn(n_local, CH, generator=g, device=device) * sigma
+            vers = [x.half()]
+            for _ in range(versions - 1):
+                x = rho * x + (1 - rho * rho) ** 0.5 * sigma * torch.randn(n_local, CH, generator=g, device=device)
+                vers.append(x.half())
+            per_kv.append(vers)
+        out.append(per_kv)
+    return out  # out[layer][kv][version]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(codec, n_local, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(f"apply_{codec}_n{n_local}_b{2 * world}")
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference's eager torch path
+# --------------------------------------------------------------------------------------------
+def cpu_rank_step_seconds(codec, world, sample_layers, reps=1):
+    """Time one rank's share of `sample_layers` layers on the host: compress own K and V shard
+    (no cache update) + decompress all `world` origins (cache update), main.py:390-420."""
+    from oracle.state import OracleCompact
+    n_local = SEQ // world
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    ranks = OracleCompact(residual=1, ef=True, fastpath=True)
+    xs0, xs1 = [], []
+    for i in range(sample_layers * 2):
+        x0 = torch.randn(n_local, CH, generator=g)
+        xs0.append(x0.half())
+        xs1.append((0.97 * x0 + 0.243 * torch.randn(n_local, CH, generator=g)).half())
+    # warm-up step: bases for every origin (all origins carry the same synthetic shard)
+    for i, x in enumerate(xs0):
+        for r in range(world):
+            ranks.decompress(f"{i}-{r}", x, "warmup", x.shape, update_cache=True)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for i, x in enumerate(xs1):
+            payload = ranks.compress(f"{i}-0", x, codec, update_cache=False)
+            for r in range(world):
+                ranks.decompress(f"{i}-{r}", payload, codec, x.shape, update_cache=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        xs0, xs1 = xs1, xs0
+    return best
+
+
+def cpu_baseline(codec, world, layers, sample_layers):
+    dt = cpu_rank_step_seconds(codec, world, sample_layers)
+    step_s = dt * layers / sample_layers * world  # all `world` ranks' work on this host's cores
+    return {"value": job_bytes(layers, world) / step_s / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle port (eager torch CPU, {torch.get_num_threads()} threads) of one rank's work for "
+                      f"{sample_layers} of {layers} layers (K and V: compress own {SEQ // world}x{CH} shard + decompress "
+                      f"{world} origins), {dt:.2f} s, extrapolated to all layers and all {world} ranks on this host"}
+
+
+def run_reference(args, world, rank):
+    if rank != 0:
+        return
+    per = []
+    for _ in range(args.warmup):
+        cpu_rank_step_seconds(args.codec, world, args.cpu_sample_layers)
+    for _ in range(args.steps):
+        per.append(cpu_rank_step_seconds(args.codec, world, args.cpu_sample_layers))
+    dt = sum(per) / len(per)
+    step_s = dt * args.layers / args.cpu_sample_layers * world
+    val = job_bytes(args.layers, world) / step_s / 1e9
+    sample = (f"each step = one rank's work for {args.cpu_sample_layers} of {args.layers} layers on the host "
+              f"({torch.get_num_threads()} threads), extrapolated to all layers and all {world} ranks")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": args.layers, "seq": SEQ,
+                   "channels": CH, "world": world},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, max(world, args.gpus), rank)
+        return
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun for N > 1"
+    assert SEQ % world == 0
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from compactfusion_b200.engine import PatchGatherEngine
+    from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+    ctype = T.BINARY if args.codec == "binary" else T.INT2
+    n_local, layers = SEQ // world, args.layers
+    eng = PatchGatherEngine(layers, n_local, CH, group=None, device=device)
+    versions = 2
+    acts = synth_activations(n_local, layers, versions, device, rank)
+    ks = [[acts[l][0][v] for l in range(layers)] for v in range(versions)]
+    vs = [[acts[l][1][v] for l in range(layers)] for v in range(versions)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # step 0: WARMUP (uncompressed), not timed
+    eng.step(ks[0], vs[0], T.WARMUP)
+    graphs = None
+    mode = "eager"
+    if not args.no_graph:
+        try:
+            graphs = [eng.capture_step(ks[v], vs[v], ctype) for v in range(versions)]
+            mode = "cuda_graph"
+        except Exception as e:  # capture can fail with NCCL inside: fall back to eager launches
+            graphs, mode = None, f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        v = (i + 1) % versions
+        if graphs is not None:
+            graphs[v].replay()
+        else:
+            eng.step(ks[v], vs[v], ctype)
+
+    for i in range(max(args.warmup, 3)):
+        run_step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    eng.kernel_launches = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        run_step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clock_info = clocks.stop() if rank == 0 else None
+    launches = (eng.launches_per_graph * args.steps) if graphs is not None else eng.kernel_launches
+    ms_per_step = ms / args.steps
+    value = job_bytes(layers, world) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (k_apply_codes: reconstruct all origins' K and V) ----
+    # one more full step, launched eagerly on the current stream with CUDA events around every
+    # decompress launch (inputs cycle through > 6 GB per step: cold in L2)
+    e_tensor = n_local * CH
+    per_byte = 8 if args.codec == "binary" else 4
+    algo_bytes = 2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor)
+    evs = []
+    vsel = args.steps % versions
+    barrier()
+    for layer in range(layers):
+        eng.compress(layer, ks[vsel][layer], vs[vsel][layer], ctype)
+        eng.gather(ctype)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.decompress(layer, ctype)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    k_ms = [a.elapsed_time(b) for a, b in evs]
+    n_launch_per_call = (2 * world + 15) // 16
+    k_avg = sum(k_ms) / len(k_ms)
+    peak, peak_src = measured_hbm_peak()
+    achieved = algo_bytes / (k_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.codec, n_local, world), "kernel": "k_apply_codes",
+                "algorithmic_bytes_per_launch": algo_bytes // n_launch_per_call,
+                "avg_launch_us": k_avg * 1e3 / n_launch_per_call, "share_of_step": k_avg * layers / ms_per_step,
+                "peak_source": peak_src}
+
+    # ---- e2e: pinned host activations -> H2D -> exchange -> D2H of the reconstructed K/V -------
+    e2e = None
+    if not args.no_e2e:
+        e2e_layers = layers
+        hk = [torch.empty((n_local, CH), dtype=torch.half).pin_memory() for _ in range(2)]
+        hv = [torch.empty((n_local, CH), dtype=torch.half).pin_memory() for _ in range(2)]
+        for b_ in hk + hv:
+            b_.copy_(acts[0][0][0].cpu())
+        out_k = torch.empty((world * n_local, CH), dtype=torch.half).pin_memory()
+        out_v = torch.empty((world * n_local, CH), dtype=torch.half).pin_memory()
+        dk = [torch.empty((n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
+        dv = [torch.empty((n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
+        copy_in, copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        main_s = torch.cuda.current_stream()
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            in_done = [None, None]
+            comp_done = None
+            for layer in range(e2e_layers):
+                s = layer & 1
+                with torch.cuda.stream(copy_in):
+                    dk[s].copy_(hk[s], non_blocking=True)
+                    dv[s].copy_(hv[s], non_blocking=True)
+                    in_done[s] = torch.cuda.Event()
+                    in_done[s].record(copy_in)
+                main_s.wait_event(in_done[s])
+                if comp_done is not None:
+                    pass
+                gk, gv = eng.exchange(layer, dk[s], dv[s], ctype)
+                done = torch.cuda.Event()
+                done.record(main_s)
+                with torch.cuda.stream(copy_out):
+                    copy_out.wait_event(done)
+                    out_k.copy_(gk, non_blocking=True)
+                    out_v.copy_(gv, non_blocking=True)
+                copy_in.wait_event(done)  # the staging buffer may be refilled only after its exchange
+            main_s.wait_stream(copy_out)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": job_bytes(layers, world) / e2e_s / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": world * layers * 2 * n_local * CH * 2,
+               "d2h_bytes_per_step": world * layers * 2 * world * n_local * CH * 2,
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "path": "pinned host K/V -> H2D -> PatchGatherEngine.exchange (C-ABI batched kernels + NCCL) -> "
+                       "D2H of reconstructed global K/V, double-buffered over 3 streams"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(args.codec, world, layers, args.cpu_sample_layers)
+        except Exception as e:
+            cpu = {"error": f"{type(e).__name__}: {e}"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": layers, "seq": SEQ,
+                       "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
+                       "l2": "inputs larger than L2 (each step streams > 6 GB of distinct K/V + cache)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,69 @@
+"""Attention block + LSE merge used by the ring / patch-parallel callers.
+
+Attention is the *consumer* of the hot path, not part of it (SURVEY.md section 8a rows
+a19/a20): it is a library call here -- flash-attn 2 when its extension imports and runs on
+this GPU, else torch SDPA-style math with an explicit log-sum-exp.  `update_out_and_lse`
+restates yunchang.ring.utils (third party, absent; `yunchang>=0.6.0` in the reference's
+setup.py:35): out <- out - sigmoid(lse_b - lse) * (out - out_b); lse <- lse - logsigmoid(lse - lse_b).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+_flash_fwd = None
+_flash_checked = False
+
+
+def _try_flash():
+    global _flash_fwd, _flash_checked
+    if not _flash_checked:
+        _flash_checked = True
+        try:
+            from flash_attn.flash_attn_interface import _flash_attn_forward
+            _flash_fwd = _flash_attn_forward
+        except Exception:
+            _flash_fwd = None
+    return _flash_fwd
+
+
+def torch_attn_forward(q, k, v, softmax_scale, causal=False):
+    """(b, s, h, d) layout.  Returns out (b, s_q, h, d) in q.dtype and lse (b, h, s_q) fp32."""
+    qf, kf, vf = (t.transpose(1, 2).float() for t in (q, k, v))
+    scores = torch.matmul(qf, kf.transpose(-1, -2)) * softmax_scale
+    if causal:
+        sq, sk = scores.shape[-2:]
+        mask = torch.ones(sq, sk, dtype=torch.bool, device=q.device).tril(diagonal=sk - sq)
+        scores = scores.masked_fill(~mask, float("-inf"))
+    lse = torch.logsumexp(scores, dim=-1)
+    out = torch.matmul(torch.exp(scores - lse.unsqueeze(-1)), vf)
+    return out.transpose(1, 2).to(q.dtype), lse
+
+
+def attn_forward(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1)):
+    """One attention block; returns (out (b,s,h,d), lse (b,h,s) fp32)."""
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** (-0.5)
+    fwd = _try_flash() if (q.is_cuda and q.dtype in (torch.half, torch.bfloat16)) else None
+    if fwd is not None:
+        try:
+            out, lse, _, _ = fwd(q, k, v, dropout_p, softmax_scale, causal=causal, window_size_left=window_size[0],
+                                 window_size_right=window_size[1], softcap=0.0, alibi_slopes=None,
+                                 return_softmax=False)
+            return out, lse
+        except Exception:
+            global _flash_fwd
+            _flash_fwd = None  # e.g. no kernel image for this GPU: use the torch path from now on
+    return torch_attn_forward(q, k, v, softmax_scale, causal)
+
+
+def update_out_and_lse(out, lse, block_out, block_lse):
+    """Online-softmax merge of two attention blocks in fp32 (restated from yunchang.ring.utils).
+    `block_lse` is (b, h, s); state `lse` is kept as (b, s, h, 1)."""
+    block_out = block_out.to(torch.float32)
+    block_lse = block_lse.transpose(-2, -1).unsqueeze(dim=-1)
+    if out is None:
+        return block_out, block_lse
+    out = out - torch.sigmoid(block_lse - lse) * (out - block_out)
+    lse = lse - F.logsigmoid(lse - block_lse)
+    return out, lse

@@ -1,0 +1,68 @@
+"""Low-rank projector (mirror of xfuser/compact/compress_lowrank.py)."""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nv
+from .prof import Profiler
+
+MAX_RANK = 64
+
+
+def svd(input_tensor: torch.Tensor, rank: int):
+    """Exact truncated SVD reference (library call, test helper).  compress_lowrank.py:5-12."""
+    u, s, vh = torch.linalg.svd(input_tensor.float(), full_matrices=False)
+    return (u[:, :rank] @ torch.diag(s[:rank])).to(input_tensor.dtype), vh[:rank, :].to(input_tensor.dtype)
+
+
+def _init_q(n: int, rank: int, device) -> torch.Tensor:
+    """The reference's random start: qr(randn(n, rank)) in fp32 from the global torch RNG
+    (compress_lowrank.py:40-42).  Data independent; drawn with torch, like the reference."""
+    q = torch.randn(n, rank, device=device, dtype=torch.float)
+    q, _ = torch.linalg.qr(q)
+    return q.contiguous()
+
+
+def lowrank_project(x: torch.Tensor, base: torch.Tensor | None, rank: int, num_iters: int,
+                    init_q: torch.Tensor | None = None, u_out=None, v_out=None, want_q=False):
+    """U (N,r), V (r,C) fp16 with A = x - base ~= U V, fused residual subtract."""
+    nv.require_cuda_half(x, "A")
+    assert x.dim() == 2
+    assert 1 <= rank <= MAX_RANK, f"rank must be in [1, {MAX_RANK}]"
+    x = x.contiguous()
+    n, c = x.shape
+    q0 = _init_q(c, rank, x.device) if init_q is None else init_q.float().contiguous()
+    assert q0.shape == (c, rank)
+    u = torch.empty((n, rank), dtype=torch.half, device=x.device) if u_out is None else u_out
+    v = torch.empty((rank, c), dtype=torch.half, device=x.device) if v_out is None else v_out
+    q = torch.empty((c, rank), dtype=torch.float, device=x.device) if want_q else None
+    ws_bytes = nv.workspace_bytes(nv.CODEC_LOWRANK, n, c, rank)
+    ws = nv.workspace(ws_bytes, x.device)
+    rc = nv.lib().cf_lowrank_project(nv.ptr(x), nv.ptr(base), nv.ptr(q0), nv.ptr(u), nv.ptr(v), nv.ptr(q), n, c, rank,
+                                     num_iters, nv.ptr(ws), ws.numel(), nv.stream_ptr())
+    nv.check(rc, "cf_lowrank_project")
+    return u, v, q
+
+
+@Profiler.prof_func("compact.subspace_iter")
+def subspace_iter(A: torch.Tensor, rank: int, num_iters: int = 10, init_q: torch.Tensor | None = None):
+    """A (m,n) ~= U (m,rank) @ V (rank,n); returns U, V, Q in A.dtype.  compress_lowrank.py:16-62.
+    fp16 input only (the reference's callers pass fp16 activations / residuals)."""
+    dtype = A.dtype
+    a16 = A if A.dtype == torch.half else A.half()
+    u, v, q = lowrank_project(a16, None, rank, num_iters, init_q=init_q, want_q=True)
+    return u.to(dtype), v.to(dtype), q.to(dtype)
+
+
+def lowrank_reconstruct(u: torch.Tensor, v: torch.Tensor, base: torch.Tensor | None = None,
+                        out: torch.Tensor | None = None) -> torch.Tensor:
+    """base + fp16(U V), fused (replaces torch.matmul(u, v) + add, slowpath.py:152-154)."""
+    n, r = u.shape
+    c = v.shape[1]
+    assert v.shape[0] == r
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.half, device=u.device)
+    rc = nv.lib().cf_lowrank_reconstruct(nv.ptr(u.contiguous()), nv.ptr(v.contiguous()), nv.ptr(base), nv.ptr(out), n, c,
+                                         r, nv.stream_ptr())
+    nv.check(rc, "cf_lowrank_reconstruct")
+    return out

@@ -1,0 +1,479 @@
+// INT4 and INT8 per-channel min/max affine codecs for sm_100a.
+//
+// Reference semantics (eager == the reference's ground truth):
+//   INT4  quantize_int4 / dequantize_int4 / sim_int4(dim=0)   compress_quantize.py:487-640
+//   INT8  quantize_int8 / dequantize_int8                     compress_quantize.py:428-484
+// The reference only *simulates* INT4 on residuals (slowpath.py:205-206) and uses INT8 for a
+// deprecated cache; here both are real wire codecs with the residual subtract and the
+// error-feedback update fused in.  min/max are exact, so scales and codes are bit-exact.
+//
+// Two streaming passes: (1) per-column min/max of delta = x - base, (2) encode (+ optional
+// new_base = base + dequant).  All fp16 arithmetic rounds once per reference op; the
+// divisions are IEEE fp32 divisions followed by one rounding to fp16 (what eager torch does).
+#include "cf_common.cuh"
+
+namespace cf {
+
+enum { MODE_INT4 = 0, MODE_INT8 = 1 };
+__host__ __device__ constexpr int mm_unroll_for(int G) { return G == 1 ? 4 : (G == 2 ? 2 : 1); }
+
+__device__ __forceinline__ __half hdiv_exact(__half a, __half b) {
+  return __float2half_rn(__fdiv_rn(__half2float(a), __half2float(b)));
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 1: per-CTA column min / max of delta.   grid (B), block (TX, TY)
+// partial layout: pmin[b][C], pmax[b][C] (fp16)
+// ---------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(512) k_minmax_stats(const __half* __restrict__ x,
+                                                      const __half* __restrict__ base,
+                                                      __half* __restrict__ pmin, __half* __restrict__ pmax,
+                                                      int N, int C, int rows_per_cta) {
+  extern __shared__ uint32_t sm_u32[];
+  constexpr int kMMUnroll = mm_unroll_for(G);
+  const int groups = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(N, r_begin + rows_per_cta);
+  const __half2 pinf = __half2half2(__ushort_as_half(0x7C00)), ninf = __half2half2(__ushort_as_half(0xFC00));
+  __half2 mn[G][4], mx[G][4];
+#pragma unroll
+  for (int j = 0; j < G; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mn[j][i] = pinf; mx[j][i] = ninf; }
+
+  for (int r = r_begin + ty; r < r_end; r += TY * kMMUnroll) {
+    uint4 xv[kMMUnroll][G], bv[kMMUnroll][G];
+#pragma unroll
+    for (int u = 0; u < kMMUnroll; ++u) {
+      const int rr = r + u * TY;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        xv[u][j] = make_uint4(0, 0, 0, 0);
+        bv[u][j] = make_uint4(0, 0, 0, 0);
+        if (rr < r_end && g < groups) {
+          const size_t off = static_cast<size_t>(rr) * C + 8 * g;
+          xv[u][j] = ldg_stream(x + off);
+          if (base != nullptr) bv[u][j] = ldg_stream(base + off);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kMMUnroll; ++u) {
+      const int rr = r + u * TY;
+      if (rr < r_end) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const H8 d = h8_sub(as_h8(xv[u][j]), as_h8(bv[u][j]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            mn[j][i] = __hmin2(mn[j][i], u2h2(d.w[i]));
+            mx[j][i] = __hmax2(mx[j][i], u2h2(d.w[i]));
+          }
+        }
+      }
+    }
+  }
+  // reduce over ty through smem: layout [ty][j][tx][8 words: 4 min, 4 max]
+  if (TY > 1) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      uint32_t* dst = sm_u32 + ((static_cast<size_t>(ty) * G + j) * TX + tx) * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { dst[i] = h22u(mn[j][i]); dst[4 + i] = h22u(mx[j][i]); }
+    }
+    __syncthreads();
+    if (ty == 0) {
+      for (int yy = 1; yy < TY; ++yy) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const uint32_t* src = sm_u32 + ((static_cast<size_t>(yy) * G + j) * TX + tx) * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            mn[j][i] = __hmin2(mn[j][i], u2h2(src[i]));
+            mx[j][i] = __hmax2(mx[j][i], u2h2(src[4 + i]));
+          }
+        }
+      }
+    }
+  }
+  if (ty == 0) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int g = tx + j * TX;
+      if (g < groups) {
+        const size_t off = static_cast<size_t>(blockIdx.x) * C + 8 * g;
+        *reinterpret_cast<uint4*>(pmin + off) = make_uint4(h22u(mn[j][0]), h22u(mn[j][1]), h22u(mn[j][2]), h22u(mn[j][3]));
+        *reinterpret_cast<uint4*>(pmax + off) = make_uint4(h22u(mx[j][0]), h22u(mx[j][1]), h22u(mx[j][2]), h22u(mx[j][3]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: min/max over partials -> scale, min (INT4) or scale, zero_point (INT8)
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_minmax_finalize(const __half* __restrict__ pmin,
+                                                         const __half* __restrict__ pmax, int B, int C,
+                                                         __half* __restrict__ scale_out,
+                                                         void* __restrict__ second_out,
+                                                         __half* __restrict__ min_ws) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  __half mn = pmin[c], mx = pmax[c];
+  for (int b = 1; b < B; ++b) {
+    mn = __hmin(mn, pmin[static_cast<size_t>(b) * C + c]);
+    mx = __hmax(mx, pmax[static_cast<size_t>(b) * C + c]);
+  }
+  const __half diff = __hsub_rn(mx, mn);  // (max_val - min_val) in fp16
+  if (MODE == MODE_INT4) {
+    // scale = (max - min) / (15 + 1e-6): fp16 tensor / python scalar = fp32 divide by float(15.000001)
+    const __half s = __float2half_rn(__fdiv_rn(__half2float(diff), 15.000001f));  // compress_quantize.py:556
+    scale_out[c] = s;
+    static_cast<__half*>(second_out)[c] = mn;
+  } else {
+    const __half s = __float2half_rn(__fdiv_rn(__half2float(diff), 255.000001f));  // compress_quantize.py:455
+    scale_out[c] = s;
+    // zero_point = clamp(qmin - round(min / scale), qmin, qmax).to(int16)   (:460-463)
+    const float t1 = __half2float(hdiv_exact(mn, s));
+    const float t2 = __half2float(__float2half_rn(rintf(t1)));
+    float zp = __half2float(__float2half_rn(-128.f - t2));
+    zp = fminf(fmaxf(zp, -128.f), 127.f);  // NaN -> -128 by fmaxf; reference NaN cast is undefined
+    if (t1 != t1) zp = 0.f;                // define NaN -> 0
+    static_cast<int16_t*>(second_out)[c] = static_cast<int16_t>(zp);
+    min_ws[c] = mn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// INT4 pass 2 / decode.  A thread handles the row pair (2i, 2i+1) of its column groups.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t int4_code(__half d, __half mn, __half s) {
+  const __half a = __hsub_rn(d, mn);                     // (input - min_val)          :561
+  const float q = rintf(__half2float(hdiv_exact(a, s))); // round(. / scale), half-even :561
+  return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), 15.f));  // clamp; NaN -> 0         :564
+}
+__device__ __forceinline__ __half int4_value(uint32_t q, __half mn, __half s) {
+  return __hadd_rn(__hmul_rn(__ushort2half_rn(static_cast<unsigned short>(q)), s), mn);  // q*scale + min :636
+}
+
+template <int G, bool ENCODE>
+__global__ void __launch_bounds__(512) k_int4_codec(const __half* __restrict__ x, const __half* __restrict__ base,
+                                                    const __half* __restrict__ scale, const __half* __restrict__ minv,
+                                                    uint8_t* __restrict__ packed, __half* __restrict__ out,
+                                                    int N, int C) {
+  // ENCODE: x, base -> packed (+ out = base + deq if out != null)
+  // !ENCODE: packed, base -> out = base + deq
+  const int groups = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  __half sfrag[G][8], mfrag[G][8];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int g = tx + j * TX;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sfrag[j][e] = (g < groups) ? scale[8 * g + e] : __float2half_rn(1.f);
+      mfrag[j][e] = (g < groups) ? minv[8 * g + e] : __float2half_rn(0.f);
+    }
+  }
+  const int pairs = N >> 1;
+  const int pair_stride = gridDim.x * TY;
+  for (int pi = blockIdx.x * TY + ty; pi < pairs; pi += pair_stride) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int g = tx + j * TX;
+      if (g >= groups) continue;
+      const size_t off0 = static_cast<size_t>(2 * pi) * C + 8 * g, off1 = off0 + C;
+      uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+      if (base != nullptr) { b0 = ldg_stream(base + off0); b1 = ldg_stream(base + off1); }
+      const __half* b0h = reinterpret_cast<const __half*>(&b0);
+      const __half* b1h = reinterpret_cast<const __half*>(&b1);
+      uint32_t q0[8], q1[8];
+      uint8_t* pk = packed + static_cast<size_t>(pi) * C + 8 * g;
+      if (ENCODE) {
+        const uint4 x0 = ldg_stream(x + off0), x1 = ldg_stream(x + off1);
+        const H8 d0 = h8_sub(as_h8(x0), as_h8(b0)), d1 = h8_sub(as_h8(x1), as_h8(b1));
+        const __half* d0h = reinterpret_cast<const __half*>(&d0);
+        const __half* d1h = reinterpret_cast<const __half*>(&d1);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          q0[e] = int4_code(d0h[e], mfrag[j][e], sfrag[j][e]);
+          q1[e] = int4_code(d1h[e], mfrag[j][e], sfrag[j][e]);
+          const uint32_t byte = q0[e] | (q1[e] << 4);  // low nibble = even row  :573
+          if (e < 4) lo |= byte << (8 * e); else hi |= byte << (8 * (e - 4));
+        }
+        *reinterpret_cast<uint2*>(pk) = make_uint2(lo, hi);
+      } else {
+        const uint2 pv = *reinterpret_cast<const uint2*>(pk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t byte = ((e < 4 ? pv.x : pv.y) >> (8 * (e & 3))) & 0xFFu;
+          q0[e] = byte & 0xFu;
+          q1[e] = byte >> 4;
+        }
+      }
+      if (out != nullptr) {
+        __align__(16) __half o0[8], o1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __half v0 = int4_value(q0[e], mfrag[j][e], sfrag[j][e]);
+          const __half v1 = int4_value(q1[e], mfrag[j][e], sfrag[j][e]);
+          o0[e] = (base != nullptr) ? __hadd_rn(b0h[e], v0) : v0;
+          o1[e] = (base != nullptr) ? __hadd_rn(b1h[e], v1) : v1;
+        }
+        stg_stream(out + off0, *reinterpret_cast<uint4*>(o0));
+        stg_stream(out + off1, *reinterpret_cast<uint4*>(o1));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// INT8 pass 2 / decode
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int int8_code(__half d, __half s, __half zp_h) {
+  // q = clamp(round(x / scale + zero_point), -128, 127)     compress_quantize.py:465-467
+  const __half t = __hadd_rn(hdiv_exact(d, s), zp_h);
+  const float q = rintf(__half2float(t));
+  if (q != q) return 0;
+  return static_cast<int>(fminf(fmaxf(q, -128.f), 127.f));
+}
+__device__ __forceinline__ __half int8_value(int q, __half s, __half zp_h) {
+  // (q.half() - zero_point.half()) * scale                  compress_quantize.py:482
+  return __hmul_rn(__hsub_rn(__short2half_rn(static_cast<short>(q)), zp_h), s);
+}
+
+template <int G, bool ENCODE>
+__global__ void __launch_bounds__(512) k_int8_codec(const __half* __restrict__ x, const __half* __restrict__ base,
+                                                    const __half* __restrict__ scale,
+                                                    const int16_t* __restrict__ zpv, int8_t* __restrict__ qout,
+                                                    __half* __restrict__ out, int N, int C) {
+  const int groups = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  __half sfrag[G][8], zfrag[G][8];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int g = tx + j * TX;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sfrag[j][e] = (g < groups) ? scale[8 * g + e] : __float2half_rn(1.f);
+      zfrag[j][e] = (g < groups) ? __short2half_rn(zpv[8 * g + e]) : __float2half_rn(0.f);
+    }
+  }
+  const int row_stride = gridDim.x * TY;
+  for (int r = blockIdx.x * TY + ty; r < N; r += row_stride) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int g = tx + j * TX;
+      if (g >= groups) continue;
+      const size_t off = static_cast<size_t>(r) * C + 8 * g;
+      uint4 b = make_uint4(0, 0, 0, 0);
+      if (base != nullptr) b = ldg_stream(base + off);
+      const __half* bh = reinterpret_cast<const __half*>(&b);
+      int q[8];
+      int8_t* qp = qout + off;
+      if (ENCODE) {
+        const uint4 xv = ldg_stream(x + off);
+        const H8 d = h8_sub(as_h8(xv), as_h8(b));
+        const __half* dh = reinterpret_cast<const __half*>(&d);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          q[e] = int8_code(dh[e], sfrag[j][e], zfrag[j][e]);
+          const uint32_t byte = static_cast<uint32_t>(q[e]) & 0xFFu;
+          if (e < 4) lo |= byte << (8 * e); else hi |= byte << (8 * (e - 4));
+        }
+        *reinterpret_cast<uint2*>(qp) = make_uint2(lo, hi);
+      } else {
+        const uint2 pv = *reinterpret_cast<const uint2*>(qp);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          q[e] = static_cast<int8_t>(((e < 4 ? pv.x : pv.y) >> (8 * (e & 3))) & 0xFFu);
+      }
+      if (out != nullptr) {
+        __align__(16) __half o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const __half v = int8_value(q[e], sfrag[j][e], zfrag[j][e]);
+          o[e] = (base != nullptr) ? __hadd_rn(bh[e], v) : v;
+        }
+        stg_stream(out + off, *reinterpret_cast<uint4*>(o));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct MinMaxPlan {
+  RowGeom geom;
+  int B, rows_per_cta;
+  size_t part_bytes, total_bytes, smem_bytes;
+};
+static MinMaxPlan make_minmax_plan(int64_t N, int64_t C) {
+  MinMaxPlan pl;
+  pl.geom = make_row_geom(C);
+  const int threads = pl.geom.TX * pl.geom.TY;
+  const int ctas_per_sm = threads >= 512 ? 2 : (1024 / threads);
+  int B = sm_count() * ctas_per_sm;
+  const int64_t max_b = (N + pl.geom.TY - 1) / pl.geom.TY;
+  if (B > max_b) B = static_cast<int>(max_b);
+  pl.rows_per_cta = static_cast<int>((N + B - 1) / B);
+  pl.B = static_cast<int>((N + pl.rows_per_cta - 1) / pl.rows_per_cta);
+  pl.part_bytes = round_up(static_cast<size_t>(pl.B) * C * 2, 256);
+  pl.total_bytes = 2 * pl.part_bytes + round_up(static_cast<size_t>(C) * 2, 256);
+  pl.smem_bytes = pl.geom.TY > 1 ? static_cast<size_t>(pl.geom.TY) * pl.geom.G * pl.geom.TX * 32 : 0;
+  return pl;
+}
+size_t minmax_codec_workspace_bytes(int64_t N, int64_t C) { return make_minmax_plan(N, C).total_bytes; }
+
+static int grid_rows(const RowGeom& g, int64_t rows) {
+  const int threads = g.TX * g.TY;
+  const int ctas_per_sm = threads >= 512 ? 2 : (1024 / threads);
+  int64_t bx = static_cast<int64_t>(sm_count()) * ctas_per_sm * 2;
+  const int64_t max_b = (rows + g.TY - 1) / g.TY;
+  if (bx > max_b) bx = max_b;
+  if (bx < 1) bx = 1;
+  return static_cast<int>(bx);
+}
+
+static int check_mm_shape(int64_t N, int64_t C, bool need_even) {
+  CF_CHECK_ARG(N >= 1 && N < (int64_t(1) << 31), "N=%lld out of range", (long long)N);
+  CF_CHECK_ARG(!need_even || N % 2 == 0, "INT4 needs an even N, got %lld", (long long)N);
+  CF_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 32768, "C=%lld must be a multiple of 8 in [8, 32768]", (long long)C);
+  return CF_OK;
+}
+
+template <int MODE>
+static int minmax_compress(const void* x, const void* base, void* new_base, void* codes, void* scale,
+                           void* second, int64_t N, int64_t C, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st) {
+  if (int rc = check_mm_shape(N, C, MODE == MODE_INT4)) return rc;
+  CF_CHECK_ARG(x && codes && scale && second, "null pointer");
+  CF_CHECK_ARG(aligned16(x) && (!base || aligned16(base)) && (!new_base || aligned16(new_base)),
+               "x/base/new_base must be 16-byte aligned");
+  CF_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 7u) == 0, "codes must be 8-byte aligned");
+  CF_CHECK_ARG(aligned2(scale) && aligned2(second), "scale vectors must be 2-byte aligned");
+  MinMaxPlan pl = make_minmax_plan(N, C);
+  CF_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+               "workspace must be non-null and 256-byte aligned");
+  if (pl.total_bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", pl.total_bytes, workspace_bytes);
+    return CF_ERR_WORKSPACE;
+  }
+  __half* pmin = static_cast<__half*>(workspace);
+  __half* pmax = reinterpret_cast<__half*>(static_cast<char*>(workspace) + pl.part_bytes);
+  __half* min_ws = reinterpret_cast<__half*>(static_cast<char*>(workspace) + 2 * pl.part_bytes);
+  const __half* xh = static_cast<const __half*>(x);
+  const __half* bh = static_cast<const __half*>(base);
+  const int n = static_cast<int>(N), c = static_cast<int>(C);
+  dim3 block(pl.geom.TX, pl.geom.TY);
+#define CF_MM_STATS(GG)                                                                         \
+  case GG:                                                                                      \
+    if (pl.smem_bytes > 48 * 1024)                                                              \
+      CF_CHECK_CUDA(cudaFuncSetAttribute(k_minmax_stats<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         static_cast<int>(pl.smem_bytes)));                     \
+    k_minmax_stats<GG><<<pl.B, block, pl.smem_bytes, st>>>(xh, bh, pmin, pmax, n, c, pl.rows_per_cta); \
+    break;
+  switch (pl.geom.G) {
+    CF_MM_STATS(1) CF_MM_STATS(2) CF_MM_STATS(4) CF_MM_STATS(8)
+    default: set_error("unsupported geometry"); return CF_ERR_UNSUPPORTED;
+  }
+#undef CF_MM_STATS
+  CF_CHECK_LAUNCH();
+  k_minmax_finalize<MODE><<<(c + 255) / 256, 256, 0, st>>>(pmin, pmax, pl.B, c, static_cast<__half*>(scale), second, min_ws);
+  CF_CHECK_LAUNCH();
+  if (MODE == MODE_INT4) {
+    dim3 grid(grid_rows(pl.geom, N / 2));
+#define CF_I4(GG)                                                                               \
+  case GG:                                                                                      \
+    k_int4_codec<GG, true><<<grid, block, 0, st>>>(xh, bh, static_cast<const __half*>(scale),   \
+                                                   static_cast<const __half*>(second),          \
+                                                   static_cast<uint8_t*>(codes),                \
+                                                   static_cast<__half*>(new_base), n, c);       \
+    break;
+    switch (pl.geom.G) { CF_I4(1) CF_I4(2) CF_I4(4) CF_I4(8) }
+#undef CF_I4
+  } else {
+    dim3 grid(grid_rows(pl.geom, N));
+#define CF_I8(GG)                                                                               \
+  case GG:                                                                                      \
+    k_int8_codec<GG, true><<<grid, block, 0, st>>>(xh, bh, static_cast<const __half*>(scale),   \
+                                                   static_cast<const int16_t*>(second),         \
+                                                   static_cast<int8_t*>(codes),                 \
+                                                   static_cast<__half*>(new_base), n, c);       \
+    break;
+    switch (pl.geom.G) { CF_I8(1) CF_I8(2) CF_I8(4) CF_I8(8) }
+#undef CF_I8
+  }
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
+template <int MODE>
+static int minmax_decompress(const void* codes, const void* scale, const void* second, const void* base,
+                             void* recon, int64_t N, int64_t C, cudaStream_t st) {
+  if (int rc = check_mm_shape(N, C, MODE == MODE_INT4)) return rc;
+  CF_CHECK_ARG(codes && scale && second && recon, "null pointer");
+  CF_CHECK_ARG(aligned16(recon) && (!base || aligned16(base)), "base/recon must be 16-byte aligned");
+  CF_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 7u) == 0, "codes must be 8-byte aligned");
+  const RowGeom g = make_row_geom(C);
+  dim3 block(g.TX, g.TY);
+  const int n = static_cast<int>(N), c = static_cast<int>(C);
+  const __half* bh = static_cast<const __half*>(base);
+  if (MODE == MODE_INT4) {
+    dim3 grid(grid_rows(g, N / 2));
+#define CF_I4D(GG)                                                                              \
+  case GG:                                                                                      \
+    k_int4_codec<GG, false><<<grid, block, 0, st>>>(nullptr, bh, static_cast<const __half*>(scale), \
+                                                    static_cast<const __half*>(second),         \
+                                                    const_cast<uint8_t*>(static_cast<const uint8_t*>(codes)), \
+                                                    static_cast<__half*>(recon), n, c);         \
+    break;
+    switch (g.G) { CF_I4D(1) CF_I4D(2) CF_I4D(4) CF_I4D(8) }
+#undef CF_I4D
+  } else {
+    dim3 grid(grid_rows(g, N));
+#define CF_I8D(GG)                                                                              \
+  case GG:                                                                                      \
+    k_int8_codec<GG, false><<<grid, block, 0, st>>>(nullptr, bh, static_cast<const __half*>(scale), \
+                                                    static_cast<const int16_t*>(second),        \
+                                                    const_cast<int8_t*>(static_cast<const int8_t*>(codes)), \
+                                                    static_cast<__half*>(recon), n, c);         \
+    break;
+    switch (g.G) { CF_I8D(1) CF_I8D(2) CF_I8D(4) CF_I8D(8) }
+#undef CF_I8D
+  }
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
+}  // namespace cf
+
+extern "C" {
+int cf_int4_compress(const void* x, const void* base, void* new_base, void* packed, void* scale, void* minv,
+                     int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  return cf::minmax_compress<cf::MODE_INT4>(x, base, new_base, packed, scale, minv, N, C, workspace,
+                                            workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int cf_int4_decompress(const void* packed, const void* scale, const void* minv, const void* base, void* recon,
+                       int64_t N, int64_t C, cf_stream_t stream) {
+  return cf::minmax_decompress<cf::MODE_INT4>(packed, scale, minv, base, recon, N, C,
+                                              static_cast<cudaStream_t>(stream));
+}
+int cf_int8_compress(const void* x, const void* base, void* new_base, void* q, void* scale, void* zero_point,
+                     int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  return cf::minmax_compress<cf::MODE_INT8>(x, base, new_base, q, scale, zero_point, N, C, workspace,
+                                            workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int cf_int8_decompress(const void* q, const void* scale, const void* zero_point, const void* base, void* recon,
+                       int64_t N, int64_t C, cf_stream_t stream) {
+  return cf::minmax_decompress<cf::MODE_INT8>(q, scale, zero_point, base, recon, N, C,
+                                              static_cast<cudaStream_t>(stream));
+}
+}

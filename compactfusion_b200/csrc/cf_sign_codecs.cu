@@ -1,0 +1,779 @@
+// BINARY (1-bit) and INT2 residual codecs for sm_100a.
+//
+// Reference semantics: xfuser/compact/fastpath.py (binary_quant_fastpath :124-228,
+// _binary_quant_fastpath :13-120, _binary_dequant_fastpath :277-367, int2_quant_fastpath
+// :584-669, _int2_quant_fastpath :486-580, _int2_dequant_fastpath :672-741).  The reference
+// spends 5-6 eager passes on the scales before its Triton kernel; here one pass over x/base
+// produces delta statistics (and, for BINARY, the packed sign bits), a tiny finalize kernel
+// turns the partial sums into the fp16 scale vectors, and one streaming pass applies the
+// codes to the base (the *same* kernel on sender and receiver, so caches stay bit-identical).
+//
+// HBM-bound byte work: 128-bit loads, per-thread column ownership (scale fragments and
+// column accumulators stay in registers), warp-shuffle row reductions, fixed-order two-level
+// fp32 sums (deterministic, no atomics).
+#include "cf_common.cuh"
+
+namespace cf {
+
+enum { MODE_BINARY = 0, MODE_INT2 = 1 };
+
+constexpr int kRowChunk = 128;  // rows whose per-warp partial sums are staged in smem at once
+// rows in flight per thread: 4 x 128-bit loads per operand when a thread owns one column
+// group; fewer when it owns several (keeps the kernels under 128 registers, no spills)
+__host__ __device__ constexpr int unroll_for(int G) { return G == 1 ? 4 : (G == 2 ? 2 : 1); }
+
+struct StatsParams {
+  const __half* x[CF_MAX_BATCH];
+  const __half* base[CF_MAX_BATCH];  // may be null (base = 0)
+  uint8_t* packed[CF_MAX_BATCH];     // BINARY only
+  __half* rowmean[CF_MAX_BATCH];     // (N) fp16 mean_c |delta|
+  float* tokpart[CF_MAX_BATCH];      // (B) partial sums of rowmean
+  float* colpart[CF_MAX_BATCH];      // (B, C) partial column sums of |delta|
+  int N, C, rows_per_cta;
+};
+
+// ---------------------------------------------------------------------------------------
+// pass 1: delta statistics (+ sign packing for BINARY)
+// grid (B, batch), block (TX, TY)
+// ---------------------------------------------------------------------------------------
+template <int MODE, int G>
+__global__ void __launch_bounds__(512) k_delta_stats(const StatsParams p) {
+  extern __shared__ float smem[];
+  const int t = blockIdx.y;
+  const __half* __restrict__ x = p.x[t];
+  const __half* __restrict__ base = p.base[t];
+  uint8_t* __restrict__ packed = p.packed[t];
+  const int N = p.N, C = p.C;
+  const int groups = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int NWX = TX >> 5, warp_x = tx >> 5, lane = tx & 31;
+  const int tid = ty * TX + tx, nthreads = TX * TY;
+  const int r_begin = blockIdx.x * p.rows_per_cta;
+  const int r_end = min(N, r_begin + p.rows_per_cta);
+
+  constexpr int kUnroll = unroll_for(G);
+  float colacc[G][8];
+#pragma unroll
+  for (int j = 0; j < G; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) colacc[j][e] = 0.f;
+  float tokacc = 0.f;
+  const float inv_c_den = static_cast<float>(C);
+
+  for (int chunk = r_begin; chunk < r_end; chunk += kRowChunk) {
+    const int cend = min(r_end, chunk + kRowChunk);
+    for (int r = chunk + ty; r < cend; r += TY * kUnroll) {
+      uint4 xv[kUnroll][G], bv[kUnroll][G];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int rr = r + u * TY;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const int g = tx + j * TX;
+          xv[u][j] = make_uint4(0, 0, 0, 0);
+          bv[u][j] = make_uint4(0, 0, 0, 0);
+          if (rr < cend && g < groups) {
+            const size_t off = static_cast<size_t>(rr) * C + 8 * g;
+            xv[u][j] = ldg_stream(x + off);
+            if (base != nullptr) bv[u][j] = ldg_stream(base + off);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int rr = r + u * TY;
+        if (rr < cend) {  // warp-uniform: a warp lies inside one ty
+          float rs = 0.f;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int g = tx + j * TX;
+            const H8 d = h8_sub(as_h8(xv[u][j]), as_h8(bv[u][j]));
+            if (g < groups) {
+              rs += h8_abs_accumulate(d, colacc[j]);
+              if (MODE == MODE_BINARY)
+                packed[static_cast<size_t>(rr) * groups + g] = static_cast<uint8_t>(h8_ge0_bits(d));
+            }
+          }
+          rs = warp_sum(rs);
+          if (lane == 0) smem[(rr - chunk) * NWX + warp_x] = rs;
+        }
+      }
+    }
+    __syncthreads();
+    // row means of this chunk: fixed-order sum over the row's warps, one rounding to fp16
+    for (int i = tid; i < cend - chunk; i += nthreads) {
+      float s = 0.f;
+      for (int w = 0; w < NWX; ++w) s += smem[i * NWX + w];
+      const __half h = __float2half_rn(s / inv_c_den);
+      p.rowmean[t][chunk + i] = h;
+      tokacc += __half2float(h);
+    }
+    __syncthreads();
+  }
+
+  // ---- CTA partial of sum_n rowmean[n] (fixed order: thread-strided, then warp tree) ----
+  {
+    float v = warp_sum(tokacc);
+    const int wid = tid >> 5, nw = nthreads >> 5;
+    if ((tid & 31) == 0) smem[wid] = v;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += smem[w];
+      p.tokpart[t][blockIdx.x] = s;
+    }
+    __syncthreads();
+  }
+
+  // ---- CTA partial column sums: reduce over ty in order, then one store per column ----
+  float* __restrict__ colout = p.colpart[t] + static_cast<size_t>(blockIdx.x) * C;
+  if (TY > 1) {
+    // smem layout [ty][j][tx][8]
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      float4* dst = reinterpret_cast<float4*>(smem + ((static_cast<size_t>(ty) * G + j) * TX + tx) * 8);
+      dst[0] = make_float4(colacc[j][0], colacc[j][1], colacc[j][2], colacc[j][3]);
+      dst[1] = make_float4(colacc[j][4], colacc[j][5], colacc[j][6], colacc[j][7]);
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        if (g < groups) {
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          for (int yy = 0; yy < TY; ++yy) {
+            const float* src = smem + ((static_cast<size_t>(yy) * G + j) * TX + tx) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += src[e];
+          }
+          float4* o = reinterpret_cast<float4*>(colout + 8 * g);
+          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int g = tx + j * TX;
+      if (g < groups) {
+        float4* o = reinterpret_cast<float4*>(colout + 8 * g);
+        o[0] = make_float4(colacc[j][0], colacc[j][1], colacc[j][2], colacc[j][3]);
+        o[1] = make_float4(colacc[j][4], colacc[j][5], colacc[j][6], colacc[j][7]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: partial sums -> fp16 scale vectors written straight into the payload
+//   V[c]  = fp16( sum_b colpart[b][c] / N )                       (fastpath.py:160 / :618)
+//   tm    = fp16( sum_n rowmean[n] / N )
+//   BINARY: U[n] = fp16( rowmean[n] / tm )                        (fastpath.py:164-165)
+//   INT2:   U[n] = fp16( rowmean[n] / fp16(tm + 1e-6) )           (fastpath.py:621-622)
+// grid (F, batch), block 256 = 32 columns x 8 partial lanes
+// ---------------------------------------------------------------------------------------
+struct FinalizeParams {
+  const __half* rowmean[CF_MAX_BATCH];
+  const float* tokpart[CF_MAX_BATCH];
+  const float* colpart[CF_MAX_BATCH];
+  __half* scale_u[CF_MAX_BATCH];
+  __half* scale_v[CF_MAX_BATCH];
+  int N, C, B;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_finalize_scales(const FinalizeParams p) {
+  __shared__ float red[8][33];
+  __shared__ float denom_s;
+  const int t = blockIdx.y;
+  const int N = p.N, C = p.C, B = p.B;
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const float n_f = static_cast<float>(N);
+
+  // token-mean denominator (every CTA recomputes it in the same order -> identical value)
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 32) s += p.tokpart[t][b];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+      const __half tm = __float2half_rn(s / n_f);
+      float d = __half2float(tm);
+      if (MODE == MODE_INT2) d = __half2float(__float2half_rn(d + 1e-6f));
+      denom_s = d;
+    }
+  }
+
+  // column means
+  for (int c0 = blockIdx.x * 32; c0 < C; c0 += gridDim.x * 32) {
+    const int c = c0 + cx;
+    float s = 0.f;
+    if (c < C)
+      for (int b = py; b < B; b += 8) s += p.colpart[t][static_cast<size_t>(b) * C + c];
+    red[py][cx] = s;
+    __syncthreads();
+    if (py == 0 && c < C) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += red[k][cx];
+      p.scale_v[t][c] = __float2half_rn(tot / n_f);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const float denom = denom_s;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
+    p.scale_u[t][n] = __float2half_rn(__half2float(p.rowmean[t][n]) / denom);
+}
+
+// ---------------------------------------------------------------------------------------
+// apply: recon = base + dequant(codes, U, V)           grid (B, batch), block (TX, TY)
+// also used by the sender for its error-feedback cache update.
+// ---------------------------------------------------------------------------------------
+struct ApplyParams {
+  const uint8_t* packed[CF_MAX_BATCH];
+  const __half* scale_u[CF_MAX_BATCH];
+  const __half* scale_v[CF_MAX_BATCH];
+  const __half* base[CF_MAX_BATCH];  // may be null
+  __half* recon[CF_MAX_BATCH];
+  int N, C, K;
+};
+
+__device__ __forceinline__ uint32_t load_v_pair(const __half* v, int c) {
+  // scale_v may be only 2-byte aligned (it lives inside the wire payload)
+  return static_cast<uint32_t>(__half_as_ushort(v[c])) |
+         (static_cast<uint32_t>(__half_as_ushort(v[c + 1])) << 16);
+}
+
+// BINARY: 8 elements from one code byte
+__device__ __forceinline__ H8 binary_apply8(const H8& b, uint32_t bits, __half2 u2, const uint32_t* vfrag) {
+  H8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t scale = h22u(__hmul2_rn(u2, u2h2(vfrag[i])));  // fp16(U[n] V[c]), fastpath.py:109
+    // (2 bit - 1) * scale: flip the sign where the bit is 0 (exact)
+    const uint32_t b0 = (bits >> (2 * i)) & 1u, b1 = (bits >> (2 * i + 1)) & 1u;
+    const uint32_t flip = ((b0 ^ 1u) << 15) | ((b1 ^ 1u) << 31);
+    r.w[i] = h22u(__hadd2_rn(u2h2(b.w[i]), u2h2(scale ^ flip)));  // fastpath.py:116 / :363
+  }
+  return r;
+}
+
+// INT2: 8 elements from two code bytes (element e at bits 2e..2e+1 of the 16-bit word)
+__device__ __forceinline__ H8 int2_apply8(const H8& b, uint32_t codes, __half2 u2, const uint32_t* vfrag) {
+  H8 r;
+  const __half2 half2_05 = __float2half2_rn(0.5f), half2_2 = __float2half2_rn(2.0f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 thr = __hmul2_rn(u2h2(vfrag[i]), u2);  // fp16(chan tok), fastpath.py:714
+    const uint32_t small = h22u(__hmul2_rn(half2_05, thr));
+    const uint32_t large = h22u(__hmul2_rn(half2_2, thr));
+    const uint32_t c0 = (codes >> (4 * i)) & 3u, c1 = (codes >> (4 * i + 2)) & 3u;
+    uint32_t lo = ((c0 & 1u) ? large : small) & 0xFFFFu;
+    uint32_t hi = ((c1 & 1u) ? large : small) & 0xFFFF0000u;
+    uint32_t lvl = lo | hi;
+    lvl ^= (((c0 >> 1) ^ 1u) << 15) | (((c1 >> 1) ^ 1u) << 31);  // sign bit 0 -> negative
+    r.w[i] = h22u(__hadd2_rn(u2h2(b.w[i]), u2h2(lvl)));
+  }
+  return r;
+}
+
+template <int MODE, int G>
+__global__ void __launch_bounds__(512) k_apply_codes(const ApplyParams p) {
+  const int t = blockIdx.y;
+  const uint8_t* __restrict__ packed = p.packed[t];
+  const __half* __restrict__ su = p.scale_u[t];
+  const __half* __restrict__ sv = p.scale_v[t];
+  const __half* __restrict__ base = p.base[t];
+  __half* __restrict__ recon = p.recon[t];
+  const int N = p.N, C = p.C;
+  const int groups = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+
+  constexpr int kUnroll = unroll_for(G);
+  uint32_t vfrag[G][4];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int g = tx + j * TX;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vfrag[j][i] = (g < groups) ? load_v_pair(sv, 8 * g + 2 * i) : 0u;
+  }
+
+  const int row_stride = gridDim.x * TY;
+  for (int r = blockIdx.x * TY + ty; r < N; r += row_stride * kUnroll) {
+    uint4 bv[kUnroll][G];
+    uint32_t code[kUnroll][G];
+    __half uu[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int rr = r + u * row_stride;
+      uu[u] = __float2half_rn(0.f);
+      if (rr < N) uu[u] = su[rr];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        bv[u][j] = make_uint4(0, 0, 0, 0);
+        code[u][j] = 0;
+        if (rr < N && g < groups) {
+          if (base != nullptr) bv[u][j] = ldg_stream(base + static_cast<size_t>(rr) * C + 8 * g);
+          if (MODE == MODE_BINARY) {
+            code[u][j] = packed[static_cast<size_t>(rr) * groups + g];
+          } else {
+            const uint8_t* q = packed + (static_cast<size_t>(rr) * groups + g) * 2;
+            code[u][j] = static_cast<uint32_t>(q[0]) | (static_cast<uint32_t>(q[1]) << 8);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int rr = r + u * row_stride;
+      if (rr < N) {
+        const __half2 u2 = __half2half2(uu[u]);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const int g = tx + j * TX;
+          if (g < groups) {
+            H8 out;
+            if (MODE == MODE_BINARY)
+              out = binary_apply8(as_h8(bv[u][j]), code[u][j], u2, vfrag[j]);
+            else
+              out = int2_apply8(as_h8(bv[u][j]), code[u][j], u2, vfrag[j]);
+            stg_stream(recon + static_cast<size_t>(rr) * C + 8 * g, as_u4(out));
+          }
+        }
+      }
+    }
+  }
+}
+
+// BINARY with rank-K scales, K > 1 (deprecated in the reference, main.py:188-189): the scale
+// sum_k U[n,k] V[c,k] is accumulated in fp32 in k order and rounded once.
+__global__ void __launch_bounds__(256) k_binary_apply_rank_k(const uint8_t* __restrict__ packed,
+                                                            const __half* __restrict__ su,
+                                                            const __half* __restrict__ sv,
+                                                            const __half* __restrict__ base,
+                                                            __half* __restrict__ recon, int N, int C,
+                                                            int K) {
+  const int groups = C >> 3;
+  const size_t total = static_cast<size_t>(N) * groups;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / groups), g = static_cast<int>(i % groups);
+    const uint32_t bits = packed[i];
+    uint4 bvec = make_uint4(0, 0, 0, 0);
+    if (base != nullptr) bvec = ldg_stream(base + static_cast<size_t>(n) * C + 8 * g);
+    const __half* bh = reinterpret_cast<const __half*>(&bvec);
+    __align__(16) __half out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = 8 * g + e;
+      float s = 0.f;
+      for (int k = 0; k < K; ++k)
+        s += __half2float(su[static_cast<size_t>(n) * K + k]) * __half2float(sv[static_cast<size_t>(c) * K + k]);
+      __half sc = __float2half_rn(s);
+      if (((bits >> e) & 1u) == 0) sc = __hneg(sc);
+      out[e] = __hadd_rn(bh[e], sc);
+    }
+    stg_stream(recon + static_cast<size_t>(n) * C + 8 * g, *reinterpret_cast<uint4*>(out));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// INT2 encode: codes (and optional error-feedback base) from x, base and final scales
+// ---------------------------------------------------------------------------------------
+struct Int2EncodeParams {
+  const __half* x[CF_MAX_BATCH];
+  const __half* base[CF_MAX_BATCH];
+  const __half* scale_u[CF_MAX_BATCH];
+  const __half* scale_v[CF_MAX_BATCH];
+  uint8_t* packed[CF_MAX_BATCH];
+  __half* new_base[CF_MAX_BATCH];  // may be null
+  int N, C;
+};
+
+template <int G>
+__global__ void __launch_bounds__(512) k_int2_encode(const Int2EncodeParams p) {
+  const int t = blockIdx.y;
+  const __half* __restrict__ x = p.x[t];
+  const __half* __restrict__ base = p.base[t];
+  const __half* __restrict__ su = p.scale_u[t];
+  const __half* __restrict__ sv = p.scale_v[t];
+  uint8_t* __restrict__ packed = p.packed[t];
+  __half* __restrict__ new_base = p.new_base[t];
+  const int N = p.N, C = p.C;
+  const int groups = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+
+  constexpr int kUnroll = unroll_for(G);
+  uint32_t vfrag[G][4];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int g = tx + j * TX;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vfrag[j][i] = (g < groups) ? load_v_pair(sv, 8 * g + 2 * i) : 0u;
+  }
+  const __half2 zero2 = __float2half2_rn(0.f);
+  const int row_stride = gridDim.x * TY;
+  for (int r = blockIdx.x * TY + ty; r < N; r += row_stride * kUnroll) {
+    uint4 xv[kUnroll][G], bv[kUnroll][G];
+    __half uu[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int rr = r + u * row_stride;
+      uu[u] = __float2half_rn(0.f);
+      if (rr < N) uu[u] = su[rr];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        xv[u][j] = make_uint4(0, 0, 0, 0);
+        bv[u][j] = make_uint4(0, 0, 0, 0);
+        if (rr < N && g < groups) {
+          const size_t off = static_cast<size_t>(rr) * C + 8 * g;
+          xv[u][j] = ldg_stream(x + off);
+          if (base != nullptr) bv[u][j] = ldg_stream(base + off);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int rr = r + u * row_stride;
+      if (rr < N) {
+        const __half2 u2 = __half2half2(uu[u]);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const int g = tx + j * TX;
+          if (g < groups) {
+            const H8 b = as_h8(bv[u][j]);
+            const H8 d = h8_sub(as_h8(xv[u][j]), b);
+            uint32_t codes = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __half2 thr = __hmul2_rn(u2h2(vfrag[j][i]), u2);            // fastpath.py:536
+              const uint32_t sgn = __hge2_mask(u2h2(d.w[i]), zero2);             // fastpath.py:539
+              const uint32_t mag = __hgt2_mask(__habs2(u2h2(d.w[i])), thr);      // fastpath.py:540
+              const uint32_t c0 = ((sgn & 1u) << 1) | (mag & 1u);
+              const uint32_t c1 = (((sgn >> 16) & 1u) << 1) | ((mag >> 16) & 1u);
+              codes |= (c0 | (c1 << 2)) << (4 * i);
+            }
+            uint8_t* q = packed + (static_cast<size_t>(rr) * groups + g) * 2;
+            q[0] = static_cast<uint8_t>(codes & 0xFFu);
+            q[1] = static_cast<uint8_t>(codes >> 8);
+            if (new_base != nullptr) {
+              const H8 nb = int2_apply8(b, codes, u2, vfrag[j]);
+              stg_stream(new_base + static_cast<size_t>(rr) * C + 8 * g, as_u4(nb));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side launch logic
+// ---------------------------------------------------------------------------------------
+struct StatsPlan {
+  RowGeom geom;
+  int B;             // row blocks per tensor
+  int rows_per_cta;
+  size_t rowmean_bytes, tokpart_bytes, colpart_bytes, per_tensor_bytes;
+  size_t smem_bytes;
+};
+
+static StatsPlan make_stats_plan(int64_t N, int64_t C, int batch) {
+  StatsPlan pl;
+  pl.geom = make_row_geom(C);
+  const int threads = pl.geom.TX * pl.geom.TY;
+  const int ctas_per_sm = threads >= 512 ? 2 : (1024 / threads);
+  const int total = sm_count() * ctas_per_sm;
+  int B = total / (batch > 0 ? batch : 1);
+  if (B < 1) B = 1;
+  const int64_t max_b = (N + pl.geom.TY - 1) / pl.geom.TY;
+  if (B > max_b) B = static_cast<int>(max_b);
+  pl.rows_per_cta = static_cast<int>((N + B - 1) / B);
+  pl.B = static_cast<int>((N + pl.rows_per_cta - 1) / pl.rows_per_cta);
+  pl.rowmean_bytes = round_up(static_cast<size_t>(N) * 2, 256);
+  pl.tokpart_bytes = round_up(static_cast<size_t>(pl.B) * 4, 256);
+  pl.colpart_bytes = round_up(static_cast<size_t>(pl.B) * C * 4, 256);
+  pl.per_tensor_bytes = pl.rowmean_bytes + pl.tokpart_bytes + pl.colpart_bytes;
+  const int NWX = pl.geom.TX / 32;
+  size_t s1 = static_cast<size_t>(kRowChunk) * NWX * 4;
+  size_t s2 = pl.geom.TY > 1 ? static_cast<size_t>(pl.geom.TY) * pl.geom.G * pl.geom.TX * 32 : 0;
+  size_t s3 = 64 * 4;
+  pl.smem_bytes = s1 > s2 ? s1 : s2;
+  if (pl.smem_bytes < s3) pl.smem_bytes = s3;
+  return pl;
+}
+
+size_t sign_codec_workspace_bytes(int64_t N, int64_t C, int batch) {
+  // upper bound independent of the batch split: B never exceeds the batch=1 value
+  StatsPlan pl = make_stats_plan(N, C, 1);
+  return pl.per_tensor_bytes * static_cast<size_t>(batch > 0 ? batch : 1);
+}
+
+template <int MODE>
+static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st) {
+  dim3 grid(pl.B, batch), block(pl.geom.TX, pl.geom.TY);
+#define CF_LAUNCH_STATS(GG)                                                                    \
+  case GG: {                                                                                   \
+    if (pl.smem_bytes > 48 * 1024)                                                             \
+      CF_CHECK_CUDA(cudaFuncSetAttribute(k_delta_stats<MODE, GG>,                              \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                         static_cast<int>(pl.smem_bytes)));                    \
+    k_delta_stats<MODE, GG><<<grid, block, pl.smem_bytes, st>>>(sp);                           \
+  } break;
+  switch (pl.geom.G) {
+    CF_LAUNCH_STATS(1)
+    CF_LAUNCH_STATS(2)
+    CF_LAUNCH_STATS(4)
+    CF_LAUNCH_STATS(8)
+    default:
+      set_error("unsupported column geometry G=%d", pl.geom.G);
+      return CF_ERR_UNSUPPORTED;
+  }
+#undef CF_LAUNCH_STATS
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
+static int apply_grid_x(const RowGeom& g, int64_t N, int batch) {
+  const int threads = g.TX * g.TY;
+  const int ctas_per_sm = threads >= 512 ? 2 : (1024 / threads);
+  int64_t bx = static_cast<int64_t>(sm_count()) * ctas_per_sm / (batch > 0 ? batch : 1);
+  const int64_t per = static_cast<int64_t>(g.TY) * unroll_for(g.G);
+  const int64_t max_b = (N + per - 1) / per;
+  if (bx > max_b) bx = max_b;
+  if (bx < 1) bx = 1;
+  return static_cast<int>(bx);
+}
+
+template <int MODE>
+static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
+  const RowGeom g = make_row_geom(ap.C);
+  dim3 grid(apply_grid_x(g, ap.N, batch), batch), block(g.TX, g.TY);
+  switch (g.G) {
+    case 1: k_apply_codes<MODE, 1><<<grid, block, 0, st>>>(ap); break;
+    case 2: k_apply_codes<MODE, 2><<<grid, block, 0, st>>>(ap); break;
+    case 4: k_apply_codes<MODE, 4><<<grid, block, 0, st>>>(ap); break;
+    case 8: k_apply_codes<MODE, 8><<<grid, block, 0, st>>>(ap); break;
+    default:
+      set_error("unsupported column geometry G=%d", g.G);
+      return CF_ERR_UNSUPPORTED;
+  }
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
+static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_t st) {
+  const RowGeom g = make_row_geom(ep.C);
+  dim3 grid(apply_grid_x(g, ep.N, batch), batch), block(g.TX, g.TY);
+  switch (g.G) {
+    case 1: k_int2_encode<1><<<grid, block, 0, st>>>(ep); break;
+    case 2: k_int2_encode<2><<<grid, block, 0, st>>>(ep); break;
+    case 4: k_int2_encode<4><<<grid, block, 0, st>>>(ep); break;
+    case 8: k_int2_encode<8><<<grid, block, 0, st>>>(ep); break;
+    default:
+      set_error("unsupported column geometry G=%d", g.G);
+      return CF_ERR_UNSUPPORTED;
+  }
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
+static int check_shape(int64_t N, int64_t C, int batch) {
+  CF_CHECK_ARG(batch >= 1 && batch <= CF_MAX_BATCH, "batch %d out of range [1,%d]", batch, CF_MAX_BATCH);
+  CF_CHECK_ARG(N >= 1 && N < (int64_t(1) << 31), "N=%lld out of range", (long long)N);
+  CF_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 32768, "C=%lld must be a multiple of 8 in [8, 32768]", (long long)C);
+  CF_CHECK_ARG(N * C < (int64_t(1) << 40), "tensor too large");
+  return CF_OK;
+}
+
+template <int MODE>
+static int sign_compress(int batch, const void* const* x, const void* const* base, void* const* new_base,
+                         void* const* packed, void* const* scale_u, void* const* scale_v, int64_t N,
+                         int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  if (int rc = check_shape(N, C, batch)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StatsPlan pl = make_stats_plan(N, C, batch);
+  CF_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+               "workspace must be non-null and 256-byte aligned");
+  if (pl.per_tensor_bytes * batch > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", pl.per_tensor_bytes * batch, workspace_bytes);
+    return CF_ERR_WORKSPACE;
+  }
+  StatsParams sp{};
+  FinalizeParams fp{};
+  sp.N = fp.N = static_cast<int>(N);
+  sp.C = fp.C = static_cast<int>(C);
+  sp.rows_per_cta = pl.rows_per_cta;
+  fp.B = pl.B;
+  bool any_update = false;
+  for (int t = 0; t < batch; ++t) {
+    CF_CHECK_ARG(x[t] && packed[t] && scale_u[t] && scale_v[t], "null pointer in tensor %d", t);
+    CF_CHECK_ARG(aligned16(x[t]) && (!base || !base[t] || aligned16(base[t])) &&
+                     (!new_base || !new_base[t] || aligned16(new_base[t])),
+                 "x/base/new_base must be 16-byte aligned (tensor %d)", t);
+    CF_CHECK_ARG(aligned2(scale_u[t]) && aligned2(scale_v[t]), "scales must be 2-byte aligned");
+    char* ws = static_cast<char*>(workspace) + pl.per_tensor_bytes * t;
+    sp.x[t] = static_cast<const __half*>(x[t]);
+    sp.base[t] = base ? static_cast<const __half*>(base[t]) : nullptr;
+    sp.packed[t] = static_cast<uint8_t*>(packed[t]);
+    sp.rowmean[t] = reinterpret_cast<__half*>(ws);
+    sp.tokpart[t] = reinterpret_cast<float*>(ws + pl.rowmean_bytes);
+    sp.colpart[t] = reinterpret_cast<float*>(ws + pl.rowmean_bytes + pl.tokpart_bytes);
+    fp.rowmean[t] = sp.rowmean[t];
+    fp.tokpart[t] = sp.tokpart[t];
+    fp.colpart[t] = sp.colpart[t];
+    fp.scale_u[t] = static_cast<__half*>(scale_u[t]);
+    fp.scale_v[t] = static_cast<__half*>(scale_v[t]);
+    if (new_base && new_base[t]) any_update = true;
+  }
+  if (int rc = launch_stats<MODE>(pl, sp, batch, st)) return rc;
+  {
+    int F = static_cast<int>((C + 31) / 32);
+    const int cap = 2 * sm_count();
+    if (F > cap) F = cap;
+    dim3 grid(F, batch);
+    k_finalize_scales<MODE><<<grid, 256, 0, st>>>(fp);
+    CF_CHECK_LAUNCH();
+  }
+  if (MODE == MODE_BINARY) {
+    if (any_update) {
+      ApplyParams ap{};
+      ap.N = sp.N; ap.C = sp.C; ap.K = 1;
+      for (int t = 0; t < batch; ++t) {
+        CF_CHECK_ARG(new_base[t] != nullptr, "batched compress: new_base must be set for all tensors or none");
+        ap.packed[t] = sp.packed[t];
+        ap.scale_u[t] = fp.scale_u[t];
+        ap.scale_v[t] = fp.scale_v[t];
+        ap.base[t] = sp.base[t];
+        ap.recon[t] = static_cast<__half*>(new_base[t]);
+      }
+      if (int rc = launch_apply<MODE_BINARY>(ap, batch, st)) return rc;
+    }
+  } else {
+    Int2EncodeParams ep{};
+    ep.N = sp.N; ep.C = sp.C;
+    for (int t = 0; t < batch; ++t) {
+      CF_CHECK_ARG(!any_update || new_base[t] != nullptr,
+                   "batched compress: new_base must be set for all tensors or none");
+      ep.x[t] = sp.x[t];
+      ep.base[t] = sp.base[t];
+      ep.scale_u[t] = fp.scale_u[t];
+      ep.scale_v[t] = fp.scale_v[t];
+      ep.packed[t] = sp.packed[t];
+      ep.new_base[t] = any_update ? static_cast<__half*>(new_base[t]) : nullptr;
+    }
+    if (int rc = launch_int2_encode(ep, batch, st)) return rc;
+  }
+  return CF_OK;
+}
+
+template <int MODE>
+static int sign_decompress(int batch, const void* const* packed, const void* const* scale_u,
+                           const void* const* scale_v, int K, const void* const* base, void* const* recon,
+                           int64_t N, int64_t C, cf_stream_t stream) {
+  if (int rc = check_shape(N, C, batch)) return rc;
+  CF_CHECK_ARG(K >= 1, "K must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ApplyParams ap{};
+  ap.N = static_cast<int>(N); ap.C = static_cast<int>(C); ap.K = K;
+  for (int t = 0; t < batch; ++t) {
+    CF_CHECK_ARG(packed[t] && scale_u[t] && scale_v[t] && recon[t], "null pointer in tensor %d", t);
+    CF_CHECK_ARG(aligned16(recon[t]) && (!base || !base[t] || aligned16(base[t])),
+                 "base/recon must be 16-byte aligned (tensor %d)", t);
+    CF_CHECK_ARG(aligned2(scale_u[t]) && aligned2(scale_v[t]), "scales must be 2-byte aligned");
+    ap.packed[t] = static_cast<const uint8_t*>(packed[t]);
+    ap.scale_u[t] = static_cast<const __half*>(scale_u[t]);
+    ap.scale_v[t] = static_cast<const __half*>(scale_v[t]);
+    ap.base[t] = base ? static_cast<const __half*>(base[t]) : nullptr;
+    ap.recon[t] = static_cast<__half*>(recon[t]);
+  }
+  if (K > 1) {
+    CF_CHECK_ARG(MODE == MODE_BINARY, "rank-K scales are only defined for BINARY");
+    for (int t = 0; t < batch; ++t) {
+      const size_t total = static_cast<size_t>(N) * (C / 8);
+      int blocks = static_cast<int>((total + 255) / 256);
+      const int cap = sm_count() * 8;
+      if (blocks > cap) blocks = cap;
+      k_binary_apply_rank_k<<<blocks, 256, 0, st>>>(ap.packed[t], ap.scale_u[t], ap.scale_v[t], ap.base[t],
+                                                    ap.recon[t], ap.N, ap.C, K);
+      CF_CHECK_LAUNCH();
+    }
+    return CF_OK;
+  }
+  return launch_apply<MODE>(ap, batch, st);
+}
+
+}  // namespace cf
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int cf_binary_compress_batched(int batch, const void* const* x, const void* const* base, void* const* new_base,
+                               void* const* packed, void* const* scale_u, void* const* scale_v, int64_t N,
+                               int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  return cf::sign_compress<cf::MODE_BINARY>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
+                                            workspace_bytes, stream);
+}
+int cf_binary_compress(const void* x, const void* base, void* new_base, void* packed, void* scale_u,
+                       void* scale_v, int64_t N, int64_t C, void* workspace, size_t workspace_bytes,
+                       cf_stream_t stream) {
+  return cf_binary_compress_batched(1, &x, &base, &new_base, &packed, &scale_u, &scale_v, N, C, workspace,
+                                    workspace_bytes, stream);
+}
+int cf_binary_decompress_batched(int batch, const void* const* packed, const void* const* scale_u,
+                                 const void* const* scale_v, const void* const* base, void* const* recon,
+                                 int64_t N, int64_t C, cf_stream_t stream) {
+  return cf::sign_decompress<cf::MODE_BINARY>(batch, packed, scale_u, scale_v, 1, base, recon, N, C, stream);
+}
+int cf_binary_decompress(const void* packed, const void* scale_u, const void* scale_v, int K, const void* base,
+                         void* recon, int64_t N, int64_t C, cf_stream_t stream) {
+  return cf::sign_decompress<cf::MODE_BINARY>(1, &packed, &scale_u, &scale_v, K, &base, &recon, N, C, stream);
+}
+
+int cf_int2_compress_batched(int batch, const void* const* x, const void* const* base, void* const* new_base,
+                             void* const* packed, void* const* scale_u, void* const* scale_v, int64_t N,
+                             int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  return cf::sign_compress<cf::MODE_INT2>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
+                                          workspace_bytes, stream);
+}
+int cf_int2_compress(const void* x, const void* base, void* new_base, void* packed, void* scale_u, void* scale_v,
+                     int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  return cf_int2_compress_batched(1, &x, &base, &new_base, &packed, &scale_u, &scale_v, N, C, workspace,
+                                  workspace_bytes, stream);
+}
+int cf_int2_decompress_batched(int batch, const void* const* packed, const void* const* scale_u,
+                               const void* const* scale_v, const void* const* base, void* const* recon, int64_t N,
+                               int64_t C, cf_stream_t stream) {
+  return cf::sign_decompress<cf::MODE_INT2>(batch, packed, scale_u, scale_v, 1, base, recon, N, C, stream);
+}
+int cf_int2_decompress(const void* packed, const void* scale_u, const void* scale_v, const void* base,
+                       void* recon, int64_t N, int64_t C, cf_stream_t stream) {
+  return cf::sign_decompress<cf::MODE_INT2>(1, &packed, &scale_u, &scale_v, 1, &base, &recon, N, C, stream);
+}
+int cf_int2_encode_with_scales(const void* x, const void* base, const void* scale_u, const void* scale_v,
+                               void* new_base, void* packed, int64_t N, int64_t C, cf_stream_t stream) {
+  if (int rc = cf::check_shape(N, C, 1)) return rc;
+  CF_CHECK_ARG(x && scale_u && scale_v && packed, "null pointer");
+  CF_CHECK_ARG(cf::aligned16(x) && (!base || cf::aligned16(base)) && (!new_base || cf::aligned16(new_base)),
+               "x/base/new_base must be 16-byte aligned");
+  cf::Int2EncodeParams ep{};
+  ep.N = static_cast<int>(N); ep.C = static_cast<int>(C);
+  ep.x[0] = static_cast<const __half*>(x);
+  ep.base[0] = static_cast<const __half*>(base);
+  ep.scale_u[0] = static_cast<const __half*>(scale_u);
+  ep.scale_v[0] = static_cast<const __half*>(scale_v);
+  ep.packed[0] = static_cast<uint8_t*>(packed);
+  ep.new_base[0] = static_cast<__half*>(new_base);
+  return cf::launch_int2_encode(ep, 1, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

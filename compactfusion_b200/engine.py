@@ -1,0 +1,181 @@
+"""Persistent-buffer, batched, CUDA-graph-capturable runtime for the compressed K/V exchange.
+
+`compact_all_gather` / `_compact_ring_fwd` (main.py, ring.py) are the drop-in API: they
+allocate per call and launch per tensor, like the reference.  This module is the B200-first
+way to drive the same kernels for a whole denoising step (SURVEY.md section 7 hard part 4):
+
+  * one compress launch pair for K *and* V of a layer (batched C-ABI entry points),
+  * K and V payloads travel as ONE message per collective,
+  * one decompress launch reconstructs K and V of all W origins, writing straight into the
+    layer's global-sequence K/V buffers -- which double as the error-feedback cache and as
+    the attention input (no torch.cat, no per-call allocation),
+  * every buffer is allocated once, so a whole step (all layers) can be captured in a CUDA
+    graph and replayed with a single launch.
+
+Results are the ones `compact_all_gather` produces (same kernels, same wire format); only
+the 1-ulp freedom of the mean-scale reductions applies (batched launches split rows over a
+different number of CTAs).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _native as nv
+from .utils import COMPACT_COMPRESS_TYPE as T
+
+_CODEC = {T.BINARY: nv.CODEC_BINARY, T.INT2: nv.CODEC_INT2}
+
+
+class PatchGatherEngine:
+    """Compressed patch-parallel K/V all-gather for `layers` attention layers (bs = 1).
+
+    global_k[l], global_v[l]: (W * n_local, C) fp16 -- rows [r*n_local, (r+1)*n_local) hold
+    origin r's shard.  After `exchange(l, k, v, ...)` they contain what every rank feeds to
+    attention (identical on all ranks) and are the bases of the next step.
+    """
+
+    def __init__(self, layers: int, n_local: int, c: int, group=None, device=None):
+        self.layers, self.n, self.c = layers, n_local, c
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        W, n = self.world, n_local
+        self.global_k = [torch.zeros((W * n, c), dtype=torch.half, device=self.device) for _ in range(layers)]
+        self.global_v = [torch.zeros((W * n, c), dtype=torch.half, device=self.device) for _ in range(layers)]
+        self._payload_numel = {}
+        self._send = {}
+        self._recv = {}
+        self._ptr_cache = {}
+        self.kernel_launches = 0  # launches of our kernels since the last reset
+        nv.lib()  # fail loudly now if the extension is missing
+
+    # -- buffers ---------------------------------------------------------------------------
+    def _numel(self, ctype):
+        per_byte = 8 if ctype == T.BINARY else 4
+        return self.n * (self.c // per_byte) // 2 + self.n + self.c
+
+    def _buffers(self, ctype):
+        if ctype not in self._send:
+            pn = self._numel(ctype)
+            self._payload_numel[ctype] = pn
+            self._send[ctype] = torch.empty((2, pn), dtype=torch.half, device=self.device)
+            self._recv[ctype] = (self._send[ctype].view(1, 2, pn) if self.world == 1 else
+                                 torch.empty((self.world, 2, pn), dtype=torch.half, device=self.device))
+        return self._send[ctype], self._recv[ctype]
+
+    def _views(self, flat, ctype):
+        per_byte = 8 if ctype == T.BINARY else 4
+        qh = self.n * (self.c // per_byte) // 2
+        return flat[:qh], flat[qh:qh + self.n], flat[qh + self.n:]
+
+    def _shard(self, buf, r):
+        return buf[r * self.n:(r + 1) * self.n]
+
+    # -- one layer -------------------------------------------------------------------------
+    def warmup(self, layer: int, k: torch.Tensor, v: torch.Tensor):
+        """Uncompressed step (COMPACT_COMPRESS_TYPE.WARMUP): raw shards are gathered straight
+        into the global buffers, which become the first bases (main.py:195-209, :351-366)."""
+        k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
+        if self.world == 1:
+            self.global_k[layer].copy_(k2)
+            self.global_v[layer].copy_(v2)
+        else:
+            dist.all_gather_into_tensor(self.global_k[layer], k2, group=self.group)
+            dist.all_gather_into_tensor(self.global_v[layer], v2, group=self.group)
+        return self.global_k[layer], self.global_v[layer]
+
+    def _compress_args(self, layer, k2, v2, ctype):
+        key = ("c", layer, k2.data_ptr(), v2.data_ptr(), ctype)
+        args = self._ptr_cache.get(key)
+        if args is None:
+            send, _ = self._buffers(ctype)
+            pk, uk, vk = self._views(send[0], ctype)
+            pv, uv, vv = self._views(send[1], ctype)
+            bases = [self._shard(self.global_k[layer], self.rank), self._shard(self.global_v[layer], self.rank)]
+            ws_bytes = nv.workspace_bytes(_CODEC[ctype], self.n, self.c, 0, 2)
+            ws = nv.workspace(ws_bytes, self.device)
+            args = (nv.ptr_array([k2, v2]), nv.ptr_array(bases), nv.ptr_array([None, None]), nv.ptr_array([pk, pv]),
+                    nv.ptr_array([uk, uv]), nv.ptr_array([vk, vv]), ws)
+            self._ptr_cache[key] = args
+        return args
+
+    def _decompress_args(self, layer, ctype):
+        key = ("d", layer, ctype)
+        args = self._ptr_cache.get(key)
+        if args is None:
+            _, recv = self._buffers(ctype)
+            packed, us, vs, bases = [], [], [], []
+            for r in range(self.world):
+                for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
+                    p, u, v = self._views(recv[r, j], ctype)
+                    packed.append(p)
+                    us.append(u)
+                    vs.append(v)
+                    bases.append(self._shard(glob, r))
+            chunks = []
+            for s in range(0, len(packed), nv.CF_MAX_BATCH):
+                e = min(len(packed), s + nv.CF_MAX_BATCH)
+                b = nv.ptr_array(bases[s:e])
+                chunks.append((e - s, nv.ptr_array(packed[s:e]), nv.ptr_array(us[s:e]), nv.ptr_array(vs[s:e]), b, b))
+            args = chunks
+            self._ptr_cache[key] = args
+        return args
+
+    def compress(self, layer, k, v, ctype):
+        """K and V of this rank -> the send buffer (no cache update: the sender's own shard is
+        updated by the decompress below, like every other origin; main.py:400-405)."""
+        k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
+        xs, bases, nones, pk, us, vs, ws = self._compress_args(layer, k2, v2, ctype)
+        fn = nv.lib().cf_binary_compress_batched if ctype == T.BINARY else nv.lib().cf_int2_compress_batched
+        rc = fn(2, xs, bases, nones, pk, us, vs, self.n, self.c, ws.data_ptr(), ws.numel(), nv.stream_ptr())
+        nv.check(rc, "compress_batched")
+        self.kernel_launches += 2 if ctype == T.BINARY else 3
+
+    def gather(self, ctype):
+        send, recv = self._buffers(ctype)
+        if self.world > 1:
+            dist.all_gather_into_tensor(recv.view(self.world, -1), send.view(-1), group=self.group)
+
+    def decompress(self, layer, ctype):
+        """All W origins x {K, V}: recon = base + dequant, in place in the global buffers."""
+        fn = nv.lib().cf_binary_decompress_batched if ctype == T.BINARY else nv.lib().cf_int2_decompress_batched
+        for cnt, pk, us, vs, bases, recon in self._decompress_args(layer, ctype):
+            rc = fn(cnt, pk, us, vs, bases, recon, self.n, self.c, nv.stream_ptr())
+            nv.check(rc, "decompress_batched")
+            self.kernel_launches += 1
+
+    def exchange(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
+        """One layer of one step; returns (global_k, global_v) ready for attention."""
+        if ctype == T.WARMUP:
+            return self.warmup(layer, k, v)
+        assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
+        self.compress(layer, k, v, ctype)
+        self.gather(ctype)
+        self.decompress(layer, ctype)
+        return self.global_k[layer], self.global_v[layer]
+
+    # -- whole step ------------------------------------------------------------------------
+    def step(self, ks, vs, ctype):
+        for layer in range(self.layers):
+            self.exchange(layer, ks[layer], vs[layer], ctype)
+
+    def capture_step(self, ks, vs, ctype, warmup_iters: int = 1):
+        """Capture `step` (all layers, fixed input buffers) into a CUDA graph; returns the graph.
+        The caller replays it after refreshing ks / vs contents in place."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup_iters):
+                self.step(ks, vs, ctype)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._ptr_cache.clear()  # workspaces are keyed by stream: rebuild inside the capture
+        g = torch.cuda.CUDAGraph()
+        before = self.kernel_launches
+        with torch.cuda.graph(g):
+            self.step(ks, vs, ctype)
+        self.launches_per_graph = self.kernel_launches - before
+        self._ptr_cache.clear()
+        return g

@@ -1,0 +1,189 @@
+/*
+ * compactb200.h -- C ABI of libcompactb200.so, the B200 (sm_100a) implementation of the
+ * CompactFusion residual-compression hot path.
+ *
+ * The reference has no FFI of its own: its boundary is the Python module API
+ * `xfuser.compact.*`.  Each entry point below replaces the tensor
+ * work of one reference function (cited as file:line under /root/reference); the Python
+ * mirror `compactfusion_b200/*.py` keeps the reference's names and signatures and binds
+ * these symbols with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Unless a function says "host", every
+ *     data pointer is a DEVICE pointer on the current CUDA device.
+ *   - activations are (N, C) row-major fp16 (IEEE binary16), C % 8 == 0, 16-byte aligned.
+ *     Code / scale outputs may be arbitrarily (2-byte) aligned so they can point straight
+ *     into the flat fp16 wire payload -- no torch.cat needed.
+ *   - `stream` is a cudaStream_t (0 = legacy default stream).  Functions only enqueue work:
+ *     no allocation, no synchronisation, CUDA-graph capturable.
+ *   - `workspace` is caller-owned scratch of at least cf_workspace_bytes(...) bytes,
+ *     256-byte aligned; contents need not be preserved between calls.
+ *   - return value: 0 on success, negative cf_status on error; cf_last_error() gives text.
+ *   - batched calls process `batch` (<= CF_MAX_BATCH) same-shape tensors in ONE launch per
+ *     pass (K and V, or all peers of an all-gather); argument arrays are HOST arrays of
+ *     device pointers, copied into kernel parameters.
+ */
+#ifndef COMPACTB200_H_
+#define COMPACTB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CF_API __attribute__((visibility("default")))
+#else
+#define CF_API
+#endif
+
+#define CF_ABI_VERSION 1
+#define CF_MAX_BATCH 16
+
+typedef void* cf_stream_t; /* cudaStream_t */
+
+enum cf_status {
+  CF_OK = 0,
+  CF_ERR_ARG = -1,       /* bad shape / alignment / null pointer */
+  CF_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  CF_ERR_WORKSPACE = -3, /* workspace too small */
+  CF_ERR_UNSUPPORTED = -4
+};
+
+enum cf_codec {
+  CF_CODEC_BINARY = 1, /* COMPACT_COMPRESS_TYPE.BINARY  (utils.py:21) */
+  CF_CODEC_INT2 = 2,   /* COMPACT_COMPRESS_TYPE.INT2    (utils.py:22) */
+  CF_CODEC_INT4 = 4,   /* COMPACT_COMPRESS_TYPE.INT4    (utils.py:24) */
+  CF_CODEC_INT8 = 8,   /* quantize_int8 (compress_quantize.py:428) */
+  CF_CODEC_TOPK = 16,  /* COMPACT_COMPRESS_TYPE.SPARSE  (utils.py:20) */
+  CF_CODEC_LOWRANK = 32 /* COMPACT_COMPRESS_TYPE.LOW_RANK / LOW_RANK_Q (utils.py:26-27) */
+};
+
+CF_API int cf_abi_version(void);
+CF_API const char* cf_last_error(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+CF_API int cf_sm_count(void);
+
+/* Scratch bytes needed by the compress entry points of `codec` for `batch` tensors of
+ * shape (N, C); `rank` only matters for CF_CODEC_LOWRANK. */
+CF_API size_t cf_workspace_bytes(int codec, int64_t N, int64_t C, int rank, int batch);
+
+/* ---- BINARY: 1-bit sign + rank-1 (token x channel) mean-|delta| scale ------------------
+ * replaces binary_quant_fastpath + _binary_quant_fastpath (fastpath.py:124-228, :13-120)
+ * with rank = -1:   delta = x - base;  V[c] = mean_n |delta|;  u[n] = mean_c |delta|;
+ * U[n] = u[n] / mean_n u[n];  bit = (delta >= 0) packed LSB-first along C;
+ * if new_base != NULL:  new_base = base + (2 bit - 1) * fp16(U[n] V[c])   (error feedback).
+ * base == NULL means base = 0 (quantize_1bit, compress_quantize.py:7-90).
+ * new_base may alias base (in-place cache update).
+ * outputs: packed (N, C/8) u8, scale_u (N,1) fp16, scale_v (C,1) fp16. */
+CF_API int cf_binary_compress(const void* x, const void* base, void* new_base, void* packed,
+                       void* scale_u, void* scale_v, int64_t N, int64_t C, void* workspace,
+                       size_t workspace_bytes, cf_stream_t stream);
+CF_API int cf_binary_compress_batched(int batch, const void* const* x, const void* const* base,
+                               void* const* new_base, void* const* packed,
+                               void* const* scale_u, void* const* scale_v, int64_t N,
+                               int64_t C, void* workspace, size_t workspace_bytes,
+                               cf_stream_t stream);
+/* replaces binary_dequant_fastpath + kernel (fastpath.py:371-438, :277-367):
+ * recon = base + (2 bit - 1) * fp16(sum_k U[n,k] V[c,k]);  base == NULL gives the bare
+ * dequantised delta (dequantize_1bit, compress_quantize.py:154-225).  K = 1 is bit-exact;
+ * K > 1 (deprecated in the reference, main.py:188-189) accumulates in fp32.
+ * recon may alias base.  scale_v is (C, K). */
+CF_API int cf_binary_decompress(const void* packed, const void* scale_u, const void* scale_v, int K,
+                         const void* base, void* recon, int64_t N, int64_t C,
+                         cf_stream_t stream);
+CF_API int cf_binary_decompress_batched(int batch, const void* const* packed,
+                                 const void* const* scale_u, const void* const* scale_v,
+                                 const void* const* base, void* const* recon, int64_t N,
+                                 int64_t C, cf_stream_t stream);
+
+/* ---- INT2: sign + magnitude bit, levels +-0.5 thr / +-2 thr, thr = fp16(chan[c] tok[n]) --
+ * replaces int2_quant_fastpath + kernel (fastpath.py:584-669, :486-580) and
+ * int2_dequant_fastpath + kernel (fastpath.py:745-811, :672-741).
+ * outputs: packed (N, C/4) u8, scale_u = tok (N,1), scale_v = chan (C,1). */
+CF_API int cf_int2_compress(const void* x, const void* base, void* new_base, void* packed,
+                     void* scale_u, void* scale_v, int64_t N, int64_t C, void* workspace,
+                     size_t workspace_bytes, cf_stream_t stream);
+CF_API int cf_int2_compress_batched(int batch, const void* const* x, const void* const* base,
+                             void* const* new_base, void* const* packed,
+                             void* const* scale_u, void* const* scale_v, int64_t N, int64_t C,
+                             void* workspace, size_t workspace_bytes, cf_stream_t stream);
+CF_API int cf_int2_decompress(const void* packed, const void* scale_u, const void* scale_v,
+                       const void* base, void* recon, int64_t N, int64_t C,
+                       cf_stream_t stream);
+CF_API int cf_int2_decompress_batched(int batch, const void* const* packed,
+                               const void* const* scale_u, const void* const* scale_v,
+                               const void* const* base, void* const* recon, int64_t N,
+                               int64_t C, cf_stream_t stream);
+/* Elementwise stage only, with caller-supplied scales (parity tests: codes are bit-exact
+ * given identical scale tensors; SURVEY.md section 7 hard part 2). */
+CF_API int cf_int2_encode_with_scales(const void* x, const void* base, const void* scale_u,
+                               const void* scale_v, void* new_base, void* packed, int64_t N,
+                               int64_t C, cf_stream_t stream);
+
+/* ---- INT4 / INT8: per-channel (over N) min/max affine codes ----------------------------
+ * INT4 replaces quantize_int4 / dequantize_int4 / sim_int4(dim=0) (compress_quantize.py:
+ * 487-640): scale = fp16((max-min)/(15+1e-6)), q = clamp(rne((v-min)/scale),0,15), rows
+ * (2i,2i+1) share byte (i,c), low nibble = even row; N even.  v = x - base (base may be
+ * NULL).  If new_base != NULL: new_base = base + (q*scale + min)  (or the bare
+ * reconstruction when base == NULL: that is sim_int4).  NaN codes (zero scale) -> 0.
+ * outputs: packed (N/2, C) u8, scale (1,C) fp16, minv (1,C) fp16. */
+CF_API int cf_int4_compress(const void* x, const void* base, void* new_base, void* packed,
+                     void* scale, void* minv, int64_t N, int64_t C, void* workspace,
+                     size_t workspace_bytes, cf_stream_t stream);
+CF_API int cf_int4_decompress(const void* packed, const void* scale, const void* minv,
+                       const void* base, void* recon, int64_t N, int64_t C,
+                       cf_stream_t stream);
+/* INT8 replaces quantize_int8 / dequantize_int8 (compress_quantize.py:428-484):
+ * outputs: q (N,C) i8, scale (1,C) fp16, zero_point (1,C) i16. */
+CF_API int cf_int8_compress(const void* x, const void* base, void* new_base, void* q, void* scale,
+                     void* zero_point, int64_t N, int64_t C, void* workspace,
+                     size_t workspace_bytes, cf_stream_t stream);
+CF_API int cf_int8_decompress(const void* q, const void* scale, const void* zero_point,
+                       const void* base, void* recon, int64_t N, int64_t C,
+                       cf_stream_t stream);
+
+/* ---- SPARSE 1:m ("top-k"): per m-block argmax |v|, lowest index wins ties ---------------
+ * replaces topk_compress / topk_decompress / topk_sparsify (compress_topk.py:11-219).
+ * v = x - base viewed as rows of 1024; m in {2,4,8,16}; numel % 1024 == 0.
+ * outputs: val (numel/m) fp16, idx (numel/(2m)) u8 = idx_block1 << 4 | idx_block2. */
+CF_API int cf_topk_compress(const void* x, const void* base, void* new_base, void* val, void* idx,
+                     int64_t numel, int m, cf_stream_t stream);
+CF_API int cf_topk_decompress(const void* val, const void* idx, const void* base, void* recon,
+                       int64_t numel, int m, cf_stream_t stream);
+
+/* ---- LOW_RANK: randomised subspace iteration projector ---------------------------------
+ * replaces subspace_iter (compress_lowrank.py:16-62) on A = x - base (fp32 arithmetic):
+ * Q <- q0 (C, r) fp32 (the caller draws / orthonormalises it, like the reference's randn+qr);
+ * iters x { Z = A^T (A Q); Q = orth(Z) };  U = orth(A Q) (N, r);  V = U^T A (r, C).
+ * orth() is CholeskyQR2 with an fp64 Gram matrix: it spans the same subspace as the
+ * reference's Householder QR, so U V (the only comparable quantity)
+ * matches to fp16 rounding.  outputs U (N,r) fp16, V (r,C) fp16. */
+CF_API int cf_lowrank_project(const void* x, const void* base, const float* q0, void* U, void* V,
+                       float* q_out /* (C, r) fp32 final Q, may be NULL */, int64_t N, int64_t C,
+                       int rank, int iters, void* workspace, size_t workspace_bytes,
+                       cf_stream_t stream);
+/* replaces torch.matmul(u, v) of slowpath_decompress (slowpath.py:152-154) fused with the
+ * residual add: recon = base + fp16(U V) (base may be NULL). */
+CF_API int cf_lowrank_reconstruct(const void* U, const void* V, const void* base, void* recon,
+                           int64_t N, int64_t C, int rank, cf_stream_t stream);
+
+/* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside the call) ---------
+ * x_host/base_host/recon_host are HOST (ideally pinned) buffers; payload_host receives /
+ * supplies the flat fp16 wire payload [codes | U | V] (main.py:149-152).  dev_scratch is a
+ * caller-owned DEVICE buffer of cf_host_scratch_bytes(codec, N, C) bytes.  The calls
+ * synchronise `stream` before returning. */
+CF_API size_t cf_host_scratch_bytes(int codec, int64_t N, int64_t C);
+CF_API int cf_host_compress(int codec, const void* x_host, const void* base_host, void* new_base_host,
+                     void* payload_host, int64_t N, int64_t C, void* dev_scratch,
+                     size_t dev_scratch_bytes, cf_stream_t stream);
+CF_API int cf_host_decompress(int codec, const void* payload_host, const void* base_host,
+                       void* recon_host, int64_t N, int64_t C, void* dev_scratch,
+                       size_t dev_scratch_bytes, cf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMPACTB200_H_ */
