@@ -51,7 +51,7 @@ def parse():
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-sample-layers", type=int, default=1)
+    p.add_argument("--cpu-sample-layers", type=int, default=2)
     return p.parse_args()
 
 
@@ -183,13 +183,19 @@ def cpu_rank_step_seconds(codec, world, sample_layers, reps=1):
     return best
 
 
-def cpu_baseline(codec, world, layers, sample_layers):
-    dt = cpu_rank_step_seconds(codec, world, sample_layers)
+def cpu_baseline(codec, world, layers, sample_layers, budget_s=12.0):
+    """Bounded sample: repeat the sampled layers until ~budget_s of CPU work, keep the mean."""
+    cpu_rank_step_seconds(codec, world, sample_layers)  # page-in / thread-pool warm-up
+    t_all, times = time.perf_counter(), []
+    while time.perf_counter() - t_all < budget_s and len(times) < 200:
+        times.append(cpu_rank_step_seconds(codec, world, sample_layers))
+    dt = sum(times) / len(times)
     step_s = dt * layers / sample_layers * world  # all `world` ranks' work on this host's cores
     return {"value": job_bytes(layers, world) / step_s / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
             "sample": f"oracle port (eager torch CPU, {torch.get_num_threads()} threads) of one rank's work for "
                       f"{sample_layers} of {layers} layers (K and V: compress own {SEQ // world}x{CH} shard + decompress "
-                      f"{world} origins), {dt:.2f} s, extrapolated to all layers and all {world} ranks on this host"}
+                      f"{world} origins), mean of {len(times)} repeats ({sum(times):.1f} s of CPU work), extrapolated "
+                      f"to all layers and all {world} ranks on this host"}
 
 
 def run_reference(args, world, rank):

@@ -62,7 +62,10 @@ def lowrank_reconstruct(u: torch.Tensor, v: torch.Tensor, base: torch.Tensor | N
     assert v.shape[0] == r
     if out is None:
         out = torch.empty((n, c), dtype=torch.half, device=u.device)
-    rc = nv.lib().cf_lowrank_reconstruct(nv.ptr(u.contiguous()), nv.ptr(v.contiguous()), nv.ptr(base), nv.ptr(out), n, c,
+    v = v.contiguous()
+    if v.data_ptr() % 16:  # a view into a wire payload may be only 2-byte aligned
+        v = v.clone()
+    rc = nv.lib().cf_lowrank_reconstruct(nv.ptr(u.contiguous()), nv.ptr(v), nv.ptr(base), nv.ptr(out), n, c,
                                          r, nv.stream_ptr())
     nv.check(rc, "cf_lowrank_reconstruct")
     return out

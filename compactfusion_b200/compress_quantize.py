@@ -21,6 +21,7 @@ def _check2d(t: torch.Tensor, name="input_tensor"):
 def _sign_compress(codec, x, base, update_cache, packed=None, u=None, v=None, new_base=None):
     """Fused residual compress for BINARY / INT2.  Output tensors may be supplied (views into
     a wire payload); returns (packed, U (N,1), V (C,1), new_base|None)."""
+    nv.require_cuda_half(x, "x")
     n, c = x.shape
     per_byte = 8 if codec == nv.CODEC_BINARY else 4
     assert c % 8 == 0, "C must be divisible by 8"
@@ -119,6 +120,7 @@ def sim_int2(input_tensor: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------ INT4 / INT8
 def _minmax_compress(codec, x, base, want_codes=True, want_recon=False):
+    nv.require_cuda_half(x, "x")
     n, c = x.shape
     dev = x.device
     if codec == nv.CODEC_INT4:

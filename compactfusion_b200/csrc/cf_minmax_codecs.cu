@@ -116,18 +116,8 @@ __global__ void __launch_bounds__(512) k_minmax_stats(const __half* __restrict__
 // finalize: min/max over partials -> scale, min (INT4) or scale, zero_point (INT8)
 // ---------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) k_minmax_finalize(const __half* __restrict__ pmin,
-                                                         const __half* __restrict__ pmax, int B, int C,
-                                                         __half* __restrict__ scale_out,
-                                                         void* __restrict__ second_out,
-                                                         __half* __restrict__ min_ws) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  __half mn = pmin[c], mx = pmax[c];
-  for (int b = 1; b < B; ++b) {
-    mn = __hmin(mn, pmin[static_cast<size_t>(b) * C + c]);
-    mx = __hmax(mx, pmax[static_cast<size_t>(b) * C + c]);
-  }
+__device__ __forceinline__ void finalize_column(__half mn, __half mx, int c, __half* __restrict__ scale_out,
+                                                void* __restrict__ second_out, __half* __restrict__ min_ws) {
   const __half diff = __hsub_rn(mx, mn);  // (max_val - min_val) in fp16
   if (MODE == MODE_INT4) {
     // scale = (max - min) / (15 + 1e-6): fp16 tensor / python scalar = fp32 divide by float(15.000001)
@@ -141,11 +131,52 @@ __global__ void __launch_bounds__(256) k_minmax_finalize(const __half* __restric
     const float t1 = __half2float(hdiv_exact(mn, s));
     const float t2 = __half2float(__float2half_rn(rintf(t1)));
     float zp = __half2float(__float2half_rn(-128.f - t2));
-    zp = fminf(fmaxf(zp, -128.f), 127.f);  // NaN -> -128 by fmaxf; reference NaN cast is undefined
-    if (t1 != t1) zp = 0.f;                // define NaN -> 0
+    zp = fminf(fmaxf(zp, -128.f), 127.f);
+    if (t1 != t1) zp = 0.f;  // NaN (zero scale): the reference's cast is undefined, we define 0
     static_cast<int16_t*>(second_out)[c] = static_cast<int16_t>(zp);
-    min_ws[c] = mn;
+    if (min_ws) min_ws[c] = mn;
   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_minmax_finalize(const __half* __restrict__ pmin,
+                                                         const __half* __restrict__ pmax, int B, int C,
+                                                         __half* __restrict__ scale_out,
+                                                         void* __restrict__ second_out,
+                                                         __half* __restrict__ min_ws) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  __half mn = pmin[c], mx = pmax[c];
+  for (int b = 1; b < B; ++b) {
+    mn = __hmin(mn, pmin[static_cast<size_t>(b) * C + c]);
+    mx = __hmax(mx, pmax[static_cast<size_t>(b) * C + c]);
+  }
+  finalize_column<MODE>(mn, mx, c, scale_out, second_out, min_ws);
+}
+
+// ---- generic path for C % 8 != 0 (tall-skinny low-rank factors, LOW_RANK_Q: slowpath.py:69-70) ----
+// one CTA per column: block min/max over the N rows, then the same finalize arithmetic
+template <int MODE>
+__global__ void __launch_bounds__(256) k_minmax_column_generic(const __half* __restrict__ x,
+                                                               const __half* __restrict__ base, int N, int C,
+                                                               __half* __restrict__ scale_out,
+                                                               void* __restrict__ second_out) {
+  __shared__ __half smn[256], smx[256];
+  const int c = blockIdx.x, t = threadIdx.x;
+  __half mn = __ushort_as_half(0x7C00), mx = __ushort_as_half(0xFC00);
+  for (int n = t; n < N; n += 256) {
+    const size_t i = static_cast<size_t>(n) * C + c;
+    const __half d = base ? __hsub_rn(x[i], base[i]) : x[i];
+    mn = __hmin(mn, d);
+    mx = __hmax(mx, d);
+  }
+  smn[t] = mn; smx[t] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) { smn[t] = __hmin(smn[t], smn[t + o]); smx[t] = __hmax(smx[t], smx[t + o]); }
+    __syncthreads();
+  }
+  if (t == 0) finalize_column<MODE>(smn[0], smx[0], c, scale_out, second_out, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -307,6 +338,62 @@ __global__ void __launch_bounds__(512) k_int8_codec(const __half* __restrict__ x
   }
 }
 
+// ---- generic element-per-thread codecs for C % 8 != 0 --------------------------------------
+template <bool ENCODE>
+__global__ void __launch_bounds__(256) k_int4_codec_generic(const __half* __restrict__ x, const __half* __restrict__ base,
+                                                            const __half* __restrict__ scale, const __half* __restrict__ minv,
+                                                            uint8_t* __restrict__ packed, __half* __restrict__ out,
+                                                            int N, int C) {
+  const size_t total = static_cast<size_t>(N / 2) * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pi = static_cast<int>(i / C), c = static_cast<int>(i % C);
+    const size_t o0 = static_cast<size_t>(2 * pi) * C + c, o1 = o0 + C;
+    const __half s = scale[c], mn = minv[c];
+    const __half zero = __float2half_rn(0.f);
+    const __half b0 = base ? base[o0] : zero, b1 = base ? base[o1] : zero;
+    uint32_t q0, q1;
+    if (ENCODE) {
+      q0 = int4_code(base ? __hsub_rn(x[o0], b0) : x[o0], mn, s);
+      q1 = int4_code(base ? __hsub_rn(x[o1], b1) : x[o1], mn, s);
+      packed[i] = static_cast<uint8_t>(q0 | (q1 << 4));
+    } else {
+      const uint32_t byte = packed[i];
+      q0 = byte & 0xFu;
+      q1 = byte >> 4;
+    }
+    if (out != nullptr) {
+      const __half v0 = int4_value(q0, mn, s), v1 = int4_value(q1, mn, s);
+      out[o0] = base ? __hadd_rn(b0, v0) : v0;
+      out[o1] = base ? __hadd_rn(b1, v1) : v1;
+    }
+  }
+}
+
+template <bool ENCODE>
+__global__ void __launch_bounds__(256) k_int8_codec_generic(const __half* __restrict__ x, const __half* __restrict__ base,
+                                                            const __half* __restrict__ scale, const int16_t* __restrict__ zpv,
+                                                            int8_t* __restrict__ qout, __half* __restrict__ out, int N, int C) {
+  const size_t total = static_cast<size_t>(N) * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const __half s = scale[c], zp = __short2half_rn(zpv[c]);
+    const __half b = base ? base[i] : __float2half_rn(0.f);
+    int q;
+    if (ENCODE) {
+      q = int8_code(base ? __hsub_rn(x[i], b) : x[i], s, zp);
+      qout[i] = static_cast<int8_t>(q);
+    } else {
+      q = qout[i];
+    }
+    if (out != nullptr) {
+      const __half v = int8_value(q, s, zp);
+      out[i] = base ? __hadd_rn(b, v) : v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -345,7 +432,32 @@ static int grid_rows(const RowGeom& g, int64_t rows) {
 static int check_mm_shape(int64_t N, int64_t C, bool need_even) {
   CF_CHECK_ARG(N >= 1 && N < (int64_t(1) << 31), "N=%lld out of range", (long long)N);
   CF_CHECK_ARG(!need_even || N % 2 == 0, "INT4 needs an even N, got %lld", (long long)N);
-  CF_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 32768, "C=%lld must be a multiple of 8 in [8, 32768]", (long long)C);
+  CF_CHECK_ARG(C >= 1 && C <= 32768, "C=%lld out of range [1, 32768]", (long long)C);
+  return CF_OK;
+}
+
+static int generic_grid(size_t total) {
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = static_cast<size_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+template <int MODE>
+static int minmax_compress_generic(const __half* xh, const __half* bh, void* new_base, void* codes, void* scale,
+                                   void* second, int n, int c, cudaStream_t st) {
+  k_minmax_column_generic<MODE><<<c, 256, 0, st>>>(xh, bh, n, c, static_cast<__half*>(scale), second);
+  CF_CHECK_LAUNCH();
+  if (MODE == MODE_INT4)
+    k_int4_codec_generic<true><<<generic_grid(static_cast<size_t>(n / 2) * c), 256, 0, st>>>(
+        xh, bh, static_cast<const __half*>(scale), static_cast<const __half*>(second), static_cast<uint8_t*>(codes),
+        static_cast<__half*>(new_base), n, c);
+  else
+    k_int8_codec_generic<true><<<generic_grid(static_cast<size_t>(n) * c), 256, 0, st>>>(
+        xh, bh, static_cast<const __half*>(scale), static_cast<const int16_t*>(second), static_cast<int8_t*>(codes),
+        static_cast<__half*>(new_base), n, c);
+  CF_CHECK_LAUNCH();
   return CF_OK;
 }
 
@@ -355,10 +467,13 @@ static int minmax_compress(const void* x, const void* base, void* new_base, void
                            cudaStream_t st) {
   if (int rc = check_mm_shape(N, C, MODE == MODE_INT4)) return rc;
   CF_CHECK_ARG(x && codes && scale && second, "null pointer");
+  CF_CHECK_ARG(aligned2(scale) && aligned2(second), "scale vectors must be 2-byte aligned");
+  if (C % 8 != 0)
+    return minmax_compress_generic<MODE>(static_cast<const __half*>(x), static_cast<const __half*>(base), new_base,
+                                         codes, scale, second, static_cast<int>(N), static_cast<int>(C), st);
   CF_CHECK_ARG(aligned16(x) && (!base || aligned16(base)) && (!new_base || aligned16(new_base)),
                "x/base/new_base must be 16-byte aligned");
   CF_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 7u) == 0, "codes must be 8-byte aligned");
-  CF_CHECK_ARG(aligned2(scale) && aligned2(second), "scale vectors must be 2-byte aligned");
   MinMaxPlan pl = make_minmax_plan(N, C);
   CF_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                "workspace must be non-null and 256-byte aligned");
@@ -420,8 +535,22 @@ static int minmax_decompress(const void* codes, const void* scale, const void* s
                              void* recon, int64_t N, int64_t C, cudaStream_t st) {
   if (int rc = check_mm_shape(N, C, MODE == MODE_INT4)) return rc;
   CF_CHECK_ARG(codes && scale && second && recon, "null pointer");
+  if (C % 8 != 0 || (reinterpret_cast<uintptr_t>(codes) & 7u) != 0) {
+    const int n = static_cast<int>(N), c = static_cast<int>(C);
+    if (MODE == MODE_INT4)
+      k_int4_codec_generic<false><<<generic_grid(static_cast<size_t>(n / 2) * c), 256, 0, st>>>(
+          nullptr, static_cast<const __half*>(base), static_cast<const __half*>(scale),
+          static_cast<const __half*>(second), const_cast<uint8_t*>(static_cast<const uint8_t*>(codes)),
+          static_cast<__half*>(recon), n, c);
+    else
+      k_int8_codec_generic<false><<<generic_grid(static_cast<size_t>(n) * c), 256, 0, st>>>(
+          nullptr, static_cast<const __half*>(base), static_cast<const __half*>(scale),
+          static_cast<const int16_t*>(second), const_cast<int8_t*>(static_cast<const int8_t*>(codes)),
+          static_cast<__half*>(recon), n, c);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+  }
   CF_CHECK_ARG(aligned16(recon) && (!base || aligned16(base)), "base/recon must be 16-byte aligned");
-  CF_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 7u) == 0, "codes must be 8-byte aligned");
   const RowGeom g = make_row_geom(C);
   dim3 block(g.TX, g.TY);
   const int n = static_cast<int>(N), c = static_cast<int>(C);

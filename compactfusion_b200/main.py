@@ -370,7 +370,7 @@ def compact_all_gather(tag, x: torch.Tensor, comp_type: COMPACT_COMPRESS_TYPE, g
     flat = to_send.reshape(-1)
     gathered = torch.empty((world_size, flat.numel()), dtype=flat.dtype, device=flat.device)
     with Profiler.scope("compact.all_gather"):
-        dist.all_gather_into_tensor(gathered, flat, group=group)
+        dist.all_gather_into_tensor(gathered.view(-1), flat, group=group)
     bufs = [gathered[i] for i in range(world_size)]
     tags = [f"{tag}-{i}" for i in range(world_size)]
     if _config.fastpath and comp_type in (T.BINARY, T.INT2) and _config.comp_rank == -1:

@@ -1,0 +1,226 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header
+declares, shapes / payload sizes / config rules match the reference, the product fails loudly
+without CUDA, and the host-side exchange logic (all-gather, ring) runs under gloo with
+world_size 2 (codec calls replaced by the oracle IN THE TEST ONLY)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from compactfusion_b200 import build as cf_build
+    return cf_build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from compactfusion_b200 import _native as nv
+    hdr = open(os.path.join(ROOT, "include", "compactb200.h")).read()
+    declared = set(re.findall(r"CF_API\s+[\w\s\*]+?\b(cf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no CF_API declarations parsed"
+    assert declared == set(nv.SYMBOLS), (declared ^ set(nv.SYMBOLS))
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (cf_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    lib = nv.lib()  # binds every symbol with its prototype
+    assert lib.cf_abi_version() == 1
+
+
+def test_workspace_sizes_without_gpu(built_lib):
+    from compactfusion_b200 import _native as nv
+    for codec in (nv.CODEC_BINARY, nv.CODEC_INT2, nv.CODEC_INT4, nv.CODEC_INT8):
+        b = nv.workspace_bytes(codec, 4096, 3072)
+        assert 0 < b < 64 << 20
+    assert nv.workspace_bytes(nv.CODEC_BINARY, 4096, 3072, 0, 4) == 4 * nv.workspace_bytes(nv.CODEC_BINARY, 4096, 3072)
+    assert nv.workspace_bytes(nv.CODEC_LOWRANK, 4096, 3072, 32) > 4096 * 32 * 4
+
+
+def test_product_fails_loudly_on_cpu_tensors(built_lib):
+    import compactfusion_b200 as cf
+    from compactfusion_b200 import _native as nv
+    from compactfusion_b200.compress_quantize import quantize_int4, sim_binary
+    x = torch.randn(8, 64).half()
+    for fn in (lambda: sim_binary(x, rank=-1), lambda: quantize_int4(x)):
+        with pytest.raises(nv.NativeError):
+            fn()
+    T = cf.COMPACT_COMPRESS_TYPE
+    cf.compact_init(cf.CompactConfig(enabled=True, compress_func=lambda l, s: T.BINARY, comp_rank=-1, residual=1,
+                                     ef=True, fastpath=True))
+    cf.compact_compress("0-0-k", x, T.WARMUP, update_cache=True)
+    with pytest.raises(nv.NativeError):
+        cf.compact_compress("0-0-k", x, T.BINARY, update_cache=True)
+
+
+def test_missing_library_raises(monkeypatch, built_lib):
+    from compactfusion_b200 import _native as nv
+    monkeypatch.setattr(nv, "_lib", None)
+    monkeypatch.setattr(nv, "LIB_PATH", "/nonexistent/libcompactb200.so")
+    with pytest.raises(nv.NativeError):
+        nv.lib()
+
+
+def test_payload_sizes_match_reference_wire_formats():
+    """SURVEY.md App-A / BASELINE.md section 2 byte counts for (4096, 3072)."""
+    from compactfusion_b200.main import fastpath_payload_numel
+    from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+    assert fastpath_payload_numel(4096, 3072, T.BINARY) * 2 == 1_587_200
+    assert fastpath_payload_numel(4096, 3072, T.INT2) * 2 == 3_160_064
+    from oracle import codecs as oc
+    x = torch.randn(64, 256).half()
+    p, u, v, _ = oc.binary_quant(x, torch.zeros_like(x), False)
+    assert oc.fastpath_payload(p, u, v).numel() == fastpath_payload_numel(64, 256, T.BINARY)
+
+
+def test_config_rules_match_reference():
+    import compactfusion_b200 as cf
+    T = cf.COMPACT_COMPRESS_TYPE
+    assert T("low-rank-int4") is T.LOW_RANK_Q and T.BINARY.value == "binary"
+    with pytest.raises(AssertionError):
+        cf.CompactConfig(enabled=True, residual=0, ef=True)
+    with pytest.raises(AssertionError):
+        cf.CompactConfig(enabled=True, residual=2, ef=False)
+    with pytest.raises(AssertionError):
+        cf.CompactConfig(enabled=True, residual=1, ef=True, simulate=True, fastpath=True)
+    with pytest.raises(AssertionError):
+        cf.CompactConfig(enabled=True, residual=1, ef=True, patch_gather_fwd_config=cf.PatchConfig(True, False, 1))
+    with pytest.raises(AssertionError):
+        cf.PatchConfig(use_compact=True, async_comm=True, async_warmup=1)
+    cfg = cf.CompactConfig(enabled=True, override_with_patch_gather_fwd=True,
+                           patch_gather_fwd_config=cf.PatchConfig(True, False, 1),
+                           compress_func=lambda l, s: T.INT2 if s >= 1 else T.WARMUP, comp_rank=-1, residual=1, ef=True,
+                           fastpath=True)
+    assert cfg.get_compress_type() == "INT2"
+    assert cf.CompactConfig().get_compress_type() == "NO_COMPACT"
+
+
+def test_warmup_and_shape_rules_on_cpu():
+    """WARMUP needs no kernel: passthrough + cache of the caller's tensor (main.py:195-209)."""
+    import compactfusion_b200 as cf
+    from compactfusion_b200.main import _to_2d_shape
+    T = cf.COMPACT_COMPRESS_TYPE
+    assert _to_2d_shape((2, 5, 4, 8)) == (10, 32) and _to_2d_shape((2, 5, 32)) == (10, 32)
+    cf.compact_init(cf.CompactConfig(enabled=True, compress_func=lambda l, s: T.WARMUP, comp_rank=-1, residual=1,
+                                     ef=True, fastpath=True))
+    cf.compact_set_step(0)
+    assert cf.compact_get_step() == 0
+    x = torch.randn(1, 6, 2, 8).half()
+    out = cf.compact_compress("3-0-k", x, T.WARMUP, update_cache=True)
+    assert out.data_ptr() == x.data_ptr() and out.shape == x.shape
+    assert cf.compact_cache().get_base("3-0-k").shape == (6, 16)
+    rec = cf.compact_decompress("3-1-k", out, T.WARMUP, x.shape, update_cache=True)
+    assert torch.equal(rec, x)
+    cf.compact_reset()
+    assert cf.compact_cache().get_base("3-0-k") is None and cf.compact_get_step() is None
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch
+import torch.distributed as dist
+import compactfusion_b200 as cf
+from compactfusion_b200 import main as cm, ring as cr, compress_quantize as cq, fastpath as fp
+from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+from oracle import codecs as oc
+from oracle.state import OracleCompact, all_gather_step, ring_step
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+
+# ---- TEST-ONLY stand-ins for the CUDA codec calls (the product has no CPU path) ----
+def sign_compress(codec, x, base, update_cache, packed=None, u=None, v=None, new_base=None):
+    fn = oc.binary_quant if codec == 1 else oc.int2_quant
+    p, uu, vv, nb = fn(x, base if base is not None else torch.zeros_like(x), update_cache)
+    packed.copy_(torch.from_numpy(p)); u.copy_(uu); v.copy_(vv)
+    if update_cache:
+        new_base.copy_(nb)
+    return packed, u, v, (new_base if update_cache else None)
+def peers(tags, payloads, ctype, shape2d):
+    n, c = shape2d
+    outs = []
+    for t, p in zip(tags, payloads):
+        pk, u, v = cm._payload_views(p, n, c, ctype)
+        fn = oc.binary_dequant if ctype == T.BINARY else oc.int2_dequant
+        o = fn(pk.numpy(), u, v, cm._cache.get_base(t))
+        cm._put(t, o)
+        outs.append(o)
+    return outs
+cm._sign_compress = sign_compress
+cm._decompress_peers_batched = peers
+
+n, c, steps = 16, 64, 4
+shape = (1, n, 2, 32)
+g = torch.Generator().manual_seed(7)
+x0 = [torch.randn(n, c, generator=g) for _ in range(world)]
+xs = [[(x0[r] + 0.1 * t * torch.randn(n, c, generator=g)).half().view(shape) for r in range(world)] for t in range(steps)]
+
+for codec in (T.BINARY, T.INT2):
+    # ---------------- compressed all-gather (patch parallel) ----------------
+    cfg = cf.CompactConfig(enabled=True, override_with_patch_gather_fwd=True,
+                           patch_gather_fwd_config=cf.PatchConfig(True, False, 1),
+                           compress_func=lambda l, s: codec if s >= 1 else T.WARMUP, comp_rank=-1, residual=1,
+                           ef=True, fastpath=True)
+    cf.compact_init(cfg)
+    oracle_ranks = [OracleCompact(residual=1, ef=True, fastpath=True) for _ in range(world)]
+    for t in range(steps):
+        ct = cfg.compress_func(0, t)
+        got = cf.compact_all_gather("5-k", xs[t][rank], ct)
+        want, _ = all_gather_step(oracle_ranks, "5-k", xs[t], ct.value)
+        assert len(got) == world
+        for i in range(world):
+            assert torch.equal(got[i], want[rank][i]), (codec, t, i)
+    # ---------------- compressed ring ----------------
+    cfg = cf.CompactConfig(enabled=True, compress_func=lambda l, s: codec if s >= 1 else T.WARMUP, comp_rank=-1,
+                           residual=1, ef=True, fastpath=True, check_consist=True)
+    cf.compact_init(cfg)
+    seen = []
+    real_attn = cr.attn_forward
+    def spy(q, k, v, *a, **kw):
+        seen.append((k.clone(), v.clone()))
+        return real_attn(q, k, v, *a, **kw)
+    cr.attn_forward = spy
+    ok_ranks = [OracleCompact(residual=1, ef=True, fastpath=True) for _ in range(world)]
+    ov_ranks = [OracleCompact(residual=1, ef=True, fastpath=True) for _ in range(world)]
+    for t in range(steps):
+        seen.clear()
+        q = xs[t][rank].float()
+        out, lse, _ = cf.compact_fwd(q.half(), xs[t][rank], xs[t][rank].flip(1).contiguous(), causal=False,
+                                     mod_idx=2, current_iter=t)
+        ks = ring_step(ok_ranks, 2, xs[t], cfg.compress_func(2, t).value, "k")
+        vs = ring_step(ov_ranks, 2, [x.flip(1).contiguous() for x in xs[t]], cfg.compress_func(2, t).value, "v")
+        assert len(seen) == world
+        for s in range(world):
+            assert torch.equal(seen[s][0], ks[rank][s]) and torch.equal(seen[s][1], vs[rank][s]), (codec, t, s)
+        # blockwise LSE merge == attention over the concatenated sequence
+        kcat = torch.cat([b for b in ks[rank]], dim=1)
+        vcat = torch.cat([b for b in vs[rank]], dim=1)
+        ref, ref_lse = real_attn(q.half(), kcat, vcat, 0.0, None, False)
+        assert torch.allclose(out.float(), ref.float(), atol=2e-3), float((out.float() - ref.float()).abs().max())
+        assert torch.allclose(lse, ref_lse, atol=1e-3)
+    cr.attn_forward = real_attn
+    assert cf.compact_cache().passed_count == steps
+dist.destroy_process_group()
+print("WORKER_OK", rank)
+'''
+
+
+def test_exchange_host_logic_gloo_world2(tmp_path, built_lib):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", OMP_NUM_THREADS="2")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-3000:]

@@ -106,10 +106,10 @@ def test_fastpath_state_machine_vs_oracle(codec):
             nb = n * c // per_byte
             mism = float((comp.view(torch.uint8)[:nb].cpu() != o_comp.view(torch.uint8)[:nb]).float().mean())
             assert mism <= (0 if codec == "binary" else 1e-3)
-            assert rel_l2(rec, o_rec) < 1e-3 if codec == "binary" else 2e-2
-        assert rel_l2(rec, o_rec) < 5e-2
+            assert rel_l2(rec, o_rec.reshape(-1)) < (1e-3 if codec == "binary" else 2e-2)
+        assert rel_l2(rec, o_rec.reshape(-1)) < 5e-2
         # compression error stays bounded under error feedback
-        assert rel_l2(rec, xs[t]) < 0.5
+        assert rel_l2(rec, xs[t].reshape(-1)) < 0.5
 
 
 def test_inplace_cache_mode_is_equivalent():
@@ -128,6 +128,7 @@ def test_inplace_cache_mode_is_equivalent():
     finally:
         cf.compact_set_inplace(False)
     for (c0, r0, _, _), (c1, r1, _, _) in zip(ref, got):
-        assert torch.equal(c0, c1) and torch.equal(r0, r1)
+        # payloads hold code bytes viewed as fp16 (NaN patterns): compare bit patterns
+        assert torch.equal(c0.view(torch.int16), c1.view(torch.int16)) and torch.equal(r0, r1)
     for x, k in zip(xs, keep):  # no caller tensor (incl. the warm-up one cached as base) was overwritten
         assert torch.equal(x, k)
