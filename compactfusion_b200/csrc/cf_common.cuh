@@ -53,6 +53,7 @@ static inline RowGeom make_row_geom(int64_t C, int target_threads = 512) {
   while ((groups + G - 1) / G > target_threads && G < 8) G *= 2;
   int per = (groups + G - 1) / G;
   g.TX = (per + 31) / 32 * 32;
+  if (g.TX < 32) g.TX = 32;
   g.G = G;
   g.TY = target_threads / g.TX;
   if (g.TY < 1) g.TY = 1;

@@ -417,7 +417,10 @@ static MinMaxPlan make_minmax_plan(int64_t N, int64_t C) {
   pl.smem_bytes = pl.geom.TY > 1 ? static_cast<size_t>(pl.geom.TY) * pl.geom.G * pl.geom.TX * 32 : 0;
   return pl;
 }
-size_t minmax_codec_workspace_bytes(int64_t N, int64_t C) { return make_minmax_plan(N, C).total_bytes; }
+size_t minmax_codec_workspace_bytes(int64_t N, int64_t C) {
+  if (C % 8 != 0) return 256;  // generic path: no scratch
+  return make_minmax_plan(N, C).total_bytes;
+}
 
 static int grid_rows(const RowGeom& g, int64_t rows) {
   const int threads = g.TX * g.TY;
@@ -468,6 +471,7 @@ static int minmax_compress(const void* x, const void* base, void* new_base, void
   if (int rc = check_mm_shape(N, C, MODE == MODE_INT4)) return rc;
   CF_CHECK_ARG(x && codes && scale && second, "null pointer");
   CF_CHECK_ARG(aligned2(scale) && aligned2(second), "scale vectors must be 2-byte aligned");
+  if (int rc0 = check_mm_shape(N, C, MODE == MODE_INT4)) return rc0;
   if (C % 8 != 0)
     return minmax_compress_generic<MODE>(static_cast<const __half*>(x), static_cast<const __half*>(base), new_base,
                                          codes, scale, second, static_cast<int>(N), static_cast<int>(C), st);

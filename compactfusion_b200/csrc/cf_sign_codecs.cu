@@ -187,44 +187,44 @@ struct FinalizeParams {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_finalize_scales(const FinalizeParams p) {
-  __shared__ float red[8][33];
+__global__ void __launch_bounds__(1024) k_finalize_scales(const FinalizeParams p) {
+  // block = 32 columns x 32 partial lanes: every thread issues ceil(B/32) independent loads
+  __shared__ float red[32][33];
   __shared__ float denom_s;
   const int t = blockIdx.y;
   const int N = p.N, C = p.C, B = p.B;
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
   const float n_f = static_cast<float>(N);
+  const float* __restrict__ colpart = p.colpart[t];
+
+  // column means (issued first: the long-latency part)
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int b = py; b < B; b += 32) s += colpart[static_cast<size_t>(b) * C + c];
+  }
+  red[py][cx] = s;
 
   // token-mean denominator (every CTA recomputes it in the same order -> identical value)
-  if (threadIdx.x < 32) {
-    float s = 0.f;
-    for (int b = threadIdx.x; b < B; b += 32) s += p.tokpart[t][b];
-    s = warp_sum(s);
-    if (threadIdx.x == 0) {
-      const __half tm = __float2half_rn(s / n_f);
+  if (py == 0) {
+    float ts = 0.f;
+    for (int b = cx; b < B; b += 32) ts += p.tokpart[t][b];
+    ts = warp_sum(ts);
+    if (cx == 0) {
+      const __half tm = __float2half_rn(ts / n_f);
       float d = __half2float(tm);
       if (MODE == MODE_INT2) d = __half2float(__float2half_rn(d + 1e-6f));
       denom_s = d;
     }
   }
-
-  // column means
-  for (int c0 = blockIdx.x * 32; c0 < C; c0 += gridDim.x * 32) {
-    const int c = c0 + cx;
-    float s = 0.f;
-    if (c < C)
-      for (int b = py; b < B; b += 8) s += p.colpart[t][static_cast<size_t>(b) * C + c];
-    red[py][cx] = s;
-    __syncthreads();
-    if (py == 0 && c < C) {
-      float tot = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tot += red[k][cx];
-      p.scale_v[t][c] = __float2half_rn(tot / n_f);
-    }
-    __syncthreads();
-  }
   __syncthreads();
+  if (py == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) tot += red[k][cx];
+    p.scale_v[t][c] = __float2half_rn(tot / n_f);
+  }
   const float denom = denom_s;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
     p.scale_u[t][n] = __float2half_rn(__half2float(p.rowmean[t][n]) / denom);
@@ -635,11 +635,8 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
   }
   if (int rc = launch_stats<MODE>(pl, sp, batch, st)) return rc;
   {
-    int F = static_cast<int>((C + 31) / 32);
-    const int cap = 2 * sm_count();
-    if (F > cap) F = cap;
-    dim3 grid(F, batch);
-    k_finalize_scales<MODE><<<grid, 256, 0, st>>>(fp);
+    dim3 grid(static_cast<unsigned>((C + 31) / 32), batch);  // one CTA per 32 columns
+    k_finalize_scales<MODE><<<grid, 1024, 0, st>>>(fp);
     CF_CHECK_LAUNCH();
   }
   if (MODE == MODE_BINARY) {
