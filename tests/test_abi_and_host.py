@@ -224,3 +224,38 @@ def test_exchange_host_logic_gloo_world2(tmp_path, built_lib):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-3000:]
+
+
+def test_shim_installs_under_reference_module_path():
+    """Every name xDiT and the reference's tests import from xfuser.compact.* 
+    resolves to this package after shim.install()."""
+    import importlib
+    import compactfusion_b200.shim as shim
+    shim.install()
+    try:
+        wanted = {
+            "xfuser.compact.main": ["compact_config", "compact_get_step", "compact_set_step", "CompactConfig",
+                                    "compact_init", "compact_reset", "compact_hello", "compact_cache",
+                                    "compact_compress", "compact_decompress", "compact_all_gather", "allgather_cache"],
+            "xfuser.compact.ring": ["compact_fwd"],
+            "xfuser.compact.utils": ["CompactConfig", "CompactCache", "COMPACT_COMPRESS_TYPE", "ALLOW_DEPRECATED"],
+            "xfuser.compact.patchpara.df_utils": ["PatchConfig"],
+            "xfuser.compact.stats": ["stats_verbose", "stats_verbose_steps", "plot_eigenvalues", "save_eigenvalues",
+                                     "dump_err_vs_steps"],
+            "xfuser.compact.fastpath": ["binary_quant_fastpath", "binary_dequant_fastpath", "int2_quant_fastpath",
+                                        "int2_dequant_fastpath"],
+            "xfuser.compact.compress_quantize": ["quantize_1bit", "dequantize_1bit", "quantize_int2", "dequantize_int2",
+                                                 "sim_int2", "sim_binary", "quantize_int4", "dequantize_int4",
+                                                 "sim_int4", "quantize_int8", "dequantize_int8"],
+            "xfuser.compact.compress_topk": ["topk_compress", "topk_decompress", "sim_topk"],
+            "xfuser.compact.compress_lowrank": ["subspace_iter", "svd"],
+            "xfuser.compact.slowpath": ["slowpath_compress", "slowpath_decompress", "sim_compress"],
+        }
+        for mod, names in wanted.items():
+            m = importlib.import_module(mod)
+            assert m.__name__.startswith("compactfusion_b200"), mod
+            for n in names:
+                assert hasattr(m, n), f"{mod}.{n}"
+    finally:
+        shim.uninstall()
+    assert "xfuser.compact.main" not in sys.modules
