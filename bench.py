@@ -140,12 +140,13 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(codec, n_local, world):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+def ncu_traffic(kernel, codec, n_local, world):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full`
+    summary (profiles/traffic.json), or None if that shape was not captured."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get(f"apply_{codec}_n{n_local}_b{2 * world}")
+            return json.load(f).get(f"{kernel}|{codec}|n{n_local}|w{world}")
     except Exception:
         return None
 
@@ -299,37 +300,77 @@ def main():
     ms_per_step = ms / args.steps
     value = job_bytes(layers, world) / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (k_apply_codes: reconstruct all origins' K and V) ----
-    # one more full step, launched eagerly on the current stream with CUDA events around every
-    # decompress launch (inputs cycle through > 6 GB per step: cold in L2)
+    # ---- per-kernel durations and the roofline of the dominant one ---------------------------
+    # Every kernel of the step is timed on its own: a CUDA graph holding that kernel's launch for
+    # ALL layers (distinct buffers per layer: `layers` x tens of MB >> 126 MB L2, so every launch
+    # is cold) is replayed between two CUDA events on the launching stream.  No per-launch events
+    # (they add a front-end round trip of several us to a 10-20 us kernel).
+    from compactfusion_b200 import _native as nv
     e_tensor = n_local * CH
     per_byte = 8 if args.codec == "binary" else 4
-    algo_bytes = 2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor)
-    evs = []
     vsel = args.steps % versions
-    barrier()
-    # keep the GPU busy while the CPU enqueues the whole step, so the events bracket back-to-back
-    # kernel execution and not CPU submission gaps
-    torch.cuda._sleep(int(60e6))
-    for layer in range(layers):
-        eng.compress(layer, ks[vsel][layer], vs[vsel][layer], ctype)
-        eng.gather(ctype)
+    part_b = 148 // 2  # column/token partials written by pass 1 (one row block per CTA)
+    kernels = []
+
+    def time_kernel(name, fn, algo_bytes, reps=3):
+        barrier()
+        for layer in range(layers):
+            fn(layer)
+        torch.cuda.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for layer in range(layers):
+                    fn(layer)
+            run = g.replay
+        except Exception:
+            torch.cuda.synchronize()
+
+            def run():
+                for layer in range(layers):
+                    fn(layer)
+        run()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.decompress(layer, ctype)
+        for _ in range(reps):
+            run()
         b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    k_ms = [a.elapsed_time(b) for a, b in evs]
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / (reps * layers)
+        kernels.append({"kernel": name, "avg_launch_us": us, "algorithmic_bytes_per_launch": algo_bytes,
+                        "achieved": algo_bytes / us / 1e3})
+
+    stats_name = "k_delta_stats_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_delta_stats"
+    apply_name = "k_apply_codes_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_apply_codes"
+    # pass 1 over K and V of this rank: read x and base, write sign bits (BINARY) + partial sums
+    time_kernel(stats_name, lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
+                2 * (4 * e_tensor + (e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
+    time_kernel("k_finalize_scales", lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
+                2 * (4 * part_b * CH + 4 * n_local + 2 * CH))
+    if args.codec == "int2":
+        time_kernel("k_int2_encode_tma", lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
+                    2 * (4 * e_tensor + e_tensor // 4 + 2 * (n_local + CH)))
+    # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
     n_launch_per_call = (2 * world + 15) // 16
-    k_avg = sum(k_ms) / len(k_ms)
+    time_kernel(apply_name, lambda l: eng.decompress(l, ctype),
+                2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
+    kernels[-1]["avg_launch_us"] /= n_launch_per_call
+    kernels[-1]["algorithmic_bytes_per_launch"] //= n_launch_per_call
     peak, peak_src = measured_hbm_peak()
-    achieved = algo_bytes / (k_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.codec, n_local, world), "kernel": "k_apply_codes",
-                "algorithmic_bytes_per_launch": algo_bytes // n_launch_per_call,
-                "avg_launch_us": k_avg * 1e3 / n_launch_per_call, "share_of_step": k_avg * layers / ms_per_step,
-                "peak_source": peak_src}
+    k_total = sum(k["avg_launch_us"] * (n_launch_per_call if k["kernel"] == apply_name else 1) for k in kernels)
+    for k in kernels:
+        mult = n_launch_per_call if k["kernel"] == apply_name else 1
+        k["frac"] = k["achieved"] / peak
+        k["share_of_kernel_time"] = k["avg_launch_us"] * mult / k_total
+    dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
+    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": ncu_traffic(dom["kernel"], args.codec, n_local, world), "kernel": dom["kernel"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_kernel_time"],
+                "peak_source": peak_src, "kernels": kernels,
+                "method": "each kernel alone: one CUDA graph with its launch for all layers (cold buffers), "
+                          "replayed 3x between two CUDA events"}
 
     # ---- e2e: pinned host activations -> H2D -> exchange -> D2H of the reconstructed K/V -------
     e2e = None

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libcompactb200.so")
 
 CF_MAX_BATCH = 16
 CODEC_BINARY, CODEC_INT2, CODEC_INT4, CODEC_INT8, CODEC_TOPK, CODEC_LOWRANK = 1, 2, 4, 8, 16, 32
+PASS_STATS, PASS_FINALIZE, PASS_ENCODE, PASS_ALL = 1, 2, 4, 7
 
 # every symbol include/compactb200.h declares: (restype, argtypes)
 _VPP = POINTER(c_void_p)
@@ -34,6 +35,7 @@ SYMBOLS = {
     "cf_int2_decompress": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_void_p]),
     "cf_int2_decompress_batched": (c_int, [c_int] + [_VPP] * 5 + [c_int64, c_int64, c_void_p]),
     "cf_int2_encode_with_scales": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p]),
+    "cf_sign_compress_passes": (c_int, [c_int, c_int, c_int] + [_VPP] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "cf_int4_compress": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "cf_int4_decompress": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_void_p]),
     "cf_int8_compress": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),

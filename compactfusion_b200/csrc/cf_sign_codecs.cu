@@ -11,7 +11,10 @@
 // HBM-bound byte work: 128-bit loads, per-thread column ownership (scale fragments and
 // column accumulators stay in registers), warp-shuffle row reductions, fixed-order two-level
 // fp32 sums (deterministic, no atomics).
+#include <stdlib.h>
+
 #include "cf_common.cuh"
+#include "cf_pipe.cuh"
 
 namespace cf {
 
@@ -196,6 +199,8 @@ __global__ void __launch_bounds__(1024) k_finalize_scales(const FinalizeParams p
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
   const float n_f = static_cast<float>(N);
   const float* __restrict__ colpart = p.colpart[t];
+  pdl_wait();  // launched as a programmatic dependent of the stats kernel: its partials must be complete
+  pdl_launch_dependents();
 
   // column means (issued first: the long-latency part)
   const int c = blockIdx.x * 32 + cx;
@@ -474,20 +479,98 @@ __global__ void __launch_bounds__(512) k_int2_encode(const Int2EncodeParams p) {
   }
 }
 
+}  // namespace cf
+
+#include "cf_sign_tma.cuh"
+
+namespace cf {
+
 // ---------------------------------------------------------------------------------------
 // host-side launch logic
 // ---------------------------------------------------------------------------------------
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr || e[0] == 0) return dflt;
+  return e[0] != '0';
+}
+// CF_LEGACY_KERNELS=1 forces the register-staged kernels (parity tests exercise both paths)
+static bool legacy_forced() { return env_flag("CF_LEGACY_KERNELS", false); }
+// CF_PDL=0 disables programmatic dependent launch between our own back-to-back kernels
+static bool pdl_enabled() { return env_flag("CF_PDL", true); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                             Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static PipeArgs pipe_args(const PipeGeom& g, int rows_per_cta) {
+  PipeArgs a{};
+  a.TX = g.TX; a.TY = g.TY; a.R = g.R; a.stages = g.stages; a.chunk_rows = g.chunk_rows;
+  a.tile_bytes = g.tile_bytes; a.stage_bytes = g.stage_bytes; a.rows_per_cta = rows_per_cta;
+  return a;
+}
+
+static TileSched make_tile_sched(const PipeGeom& g, int64_t N, int batch, int* n_cta) {
+  TileSched ts{};
+  ts.tiles_per_tensor = static_cast<int>((N + g.R - 1) / g.R);
+  ts.total_tiles = ts.tiles_per_tensor * batch;
+  int ctas = sm_count();
+  if (ctas > ts.total_tiles) ctas = ts.total_tiles;
+  ts.tiles_per_cta = (ts.total_tiles + ctas - 1) / ctas;
+  const int cap = kPipeMaxRowsPerCta / g.R;
+  if (ts.tiles_per_cta > cap) ts.tiles_per_cta = cap;
+  *n_cta = (ts.total_tiles + ts.tiles_per_cta - 1) / ts.tiles_per_cta;
+  return ts;
+}
+
 struct StatsPlan {
   RowGeom geom;
+  bool tma;          // bulk-async pipelined kernel (cf_sign_tma.cuh) instead of the register-staged one
+  PipeGeom pipe;
   int B;             // row blocks per tensor
   int rows_per_cta;
   size_t rowmean_bytes, tokpart_bytes, colpart_bytes, per_tensor_bytes;
   size_t smem_bytes;
 };
 
-static StatsPlan make_stats_plan(int64_t N, int64_t C, int batch) {
+static StatsPlan make_stats_plan(int64_t N, int64_t C, int batch, bool allow_tma = false) {
   StatsPlan pl;
   pl.geom = make_row_geom(C);
+  pl.tma = false;
+  if (allow_tma && !legacy_forced()) {
+    pl.pipe = make_pipe_geom(C, 2, 0);
+    if (pl.pipe.ok) {
+      int B = sm_count() / (batch > 0 ? batch : 1);
+      if (B < 1) B = 1;
+      int64_t rpc = (N + B - 1) / B;
+      rpc = (rpc + pl.pipe.R - 1) / pl.pipe.R * pl.pipe.R;  // tile starts stay stage-aligned
+      pl.tma = true;
+      pl.rows_per_cta = static_cast<int>(rpc);
+      pl.B = static_cast<int>((N + rpc - 1) / rpc);
+      pl.rowmean_bytes = round_up(static_cast<size_t>(N) * 2, 256);
+      pl.tokpart_bytes = round_up(static_cast<size_t>(pl.B) * 4, 256);
+      pl.colpart_bytes = round_up(static_cast<size_t>(pl.B) * C * 4, 256);
+      pl.per_tensor_bytes = pl.rowmean_bytes + pl.tokpart_bytes + pl.colpart_bytes;
+      pl.smem_bytes = pl.pipe.smem_bytes;
+      return pl;
+    }
+  }
   const int threads = pl.geom.TX * pl.geom.TY;
   const int ctas_per_sm = threads >= 512 ? 2 : (1024 / threads);
   const int total = sm_count() * ctas_per_sm;
@@ -518,6 +601,15 @@ size_t sign_codec_workspace_bytes(int64_t N, int64_t C, int batch) {
 
 template <int MODE>
 static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st) {
+  if (pl.tma) {
+    const PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta);
+    dim3 grid(pl.B, batch), block(pl.pipe.TX * pl.pipe.TY + 32);
+    if (pl.pipe.G == 1)
+      CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 1>, grid, block, pl.pipe.smem_bytes, st, true, sp, a));
+    else
+      CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 2>, grid, block, pl.pipe.smem_bytes, st, true, sp, a));
+    return CF_OK;
+  }
   dim3 grid(pl.B, batch), block(pl.geom.TX, pl.geom.TY);
 #define CF_LAUNCH_STATS(GG)                                                                    \
   case GG: {                                                                                   \
@@ -554,6 +646,24 @@ static int apply_grid_x(const RowGeom& g, int64_t N, int batch) {
 
 template <int MODE>
 static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
+  const int code_row = (MODE == MODE_BINARY) ? ap.C / 8 : ap.C / 4;
+  bool tma = !legacy_forced() && code_row % 16 == 0;
+  for (int t = 0; t < batch && tma; ++t)
+    tma = ap.base[t] != nullptr && aligned16(ap.base[t]) && aligned16(ap.packed[t]);
+  if (tma) {
+    const PipeGeom pg = make_pipe_geom(ap.C, 1, code_row);
+    if (pg.ok) {
+      int n_cta = 1;
+      const TileSched ts = make_tile_sched(pg, ap.N, batch, &n_cta);
+      const PipeArgs a = pipe_args(pg, 0);
+      dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
+      if (pg.G == 1)
+        CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 1>, grid, block, pg.smem_bytes, st, true, ap, a, ts));
+      else
+        CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 2>, grid, block, pg.smem_bytes, st, true, ap, a, ts));
+      return CF_OK;
+    }
+  }
   const RowGeom g = make_row_geom(ap.C);
   dim3 grid(apply_grid_x(g, ap.N, batch), batch), block(g.TX, g.TY);
   switch (g.G) {
@@ -570,6 +680,23 @@ static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
 }
 
 static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_t st) {
+  bool tma = !legacy_forced();
+  for (int t = 0; t < batch && tma; ++t)
+    tma = ep.base[t] != nullptr && aligned16(ep.base[t]) && aligned16(ep.x[t]) && aligned2(ep.packed[t]);
+  if (tma) {
+    const PipeGeom pg = make_pipe_geom(ep.C, 2, 0);
+    if (pg.ok) {
+      int n_cta = 1;
+      const TileSched ts = make_tile_sched(pg, ep.N, batch, &n_cta);
+      const PipeArgs a = pipe_args(pg, 0);
+      dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
+      if (pg.G == 1)
+        CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<1>, grid, block, pg.smem_bytes, st, true, ep, a, ts));
+      else
+        CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<2>, grid, block, pg.smem_bytes, st, true, ep, a, ts));
+      return CF_OK;
+    }
+  }
   const RowGeom g = make_row_geom(ep.C);
   dim3 grid(apply_grid_x(g, ep.N, batch), batch), block(g.TX, g.TY);
   switch (g.G) {
@@ -596,10 +723,13 @@ static int check_shape(int64_t N, int64_t C, int batch) {
 template <int MODE>
 static int sign_compress(int batch, const void* const* x, const void* const* base, void* const* new_base,
                          void* const* packed, void* const* scale_u, void* const* scale_v, int64_t N,
-                         int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+                         int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream,
+                         int passes = CF_PASS_ALL) {
   if (int rc = check_shape(N, C, batch)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  StatsPlan pl = make_stats_plan(N, C, batch);
+  bool all_base = base != nullptr;
+  for (int t = 0; t < batch && all_base; ++t) all_base = base[t] != nullptr;
+  StatsPlan pl = make_stats_plan(N, C, batch, all_base);
   CF_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                "workspace must be non-null and 256-byte aligned");
   if (pl.per_tensor_bytes * batch > workspace_bytes) {
@@ -633,12 +763,13 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
     fp.scale_v[t] = static_cast<__half*>(scale_v[t]);
     if (new_base && new_base[t]) any_update = true;
   }
-  if (int rc = launch_stats<MODE>(pl, sp, batch, st)) return rc;
-  {
+  if (passes & CF_PASS_STATS)
+    if (int rc = launch_stats<MODE>(pl, sp, batch, st)) return rc;
+  if (passes & CF_PASS_FINALIZE) {
     dim3 grid(static_cast<unsigned>((C + 31) / 32), batch);  // one CTA per 32 columns
-    k_finalize_scales<MODE><<<grid, 1024, 0, st>>>(fp);
-    CF_CHECK_LAUNCH();
+    CF_CHECK_CUDA(launch_ex(k_finalize_scales<MODE>, grid, dim3(1024), 0, st, true, fp));
   }
+  if (!(passes & CF_PASS_ENCODE)) return CF_OK;
   if (MODE == MODE_BINARY) {
     if (any_update) {
       ApplyParams ap{};
@@ -755,6 +886,17 @@ int cf_int2_decompress_batched(int batch, const void* const* packed, const void*
 int cf_int2_decompress(const void* packed, const void* scale_u, const void* scale_v, const void* base,
                        void* recon, int64_t N, int64_t C, cf_stream_t stream) {
   return cf::sign_decompress<cf::MODE_INT2>(1, &packed, &scale_u, &scale_v, 1, &base, &recon, N, C, stream);
+}
+int cf_sign_compress_passes(int codec, int passes, int batch, const void* const* x, const void* const* base,
+                            void* const* new_base, void* const* packed, void* const* scale_u, void* const* scale_v,
+                            int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  CF_CHECK_ARG(codec == CF_CODEC_BINARY || codec == CF_CODEC_INT2, "codec must be CF_CODEC_BINARY or CF_CODEC_INT2");
+  CF_CHECK_ARG(passes > 0 && (passes & ~CF_PASS_ALL) == 0, "bad pass mask %d", passes);
+  if (codec == CF_CODEC_BINARY)
+    return cf::sign_compress<cf::MODE_BINARY>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
+                                              workspace_bytes, stream, passes);
+  return cf::sign_compress<cf::MODE_INT2>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
+                                          workspace_bytes, stream, passes);
 }
 int cf_int2_encode_with_scales(const void* x, const void* base, const void* scale_u, const void* scale_v,
                                void* new_base, void* packed, int64_t N, int64_t C, cf_stream_t stream) {

@@ -1,0 +1,531 @@
+// Bulk-async (TMA) pipelined versions of the BINARY / INT2 streaming kernels.
+// Included by cf_sign_codecs.cu after StatsParams / ApplyParams / Int2EncodeParams.
+//
+// One CTA per SM: TX*TY compute threads + one producer warp.  The producer lane streams
+// row tiles (R rows = one contiguous span per operand) into a `stages`-deep shared-memory
+// ring with cp.async.bulk + mbarrier; compute warps read 16 bytes per thread per row from
+// shared memory (conflict-free), keep their per-column state in registers and release each
+// stage through an "empty" mbarrier.  Arithmetic is identical to the legacy kernels (same
+// fp16 roundings; fp32 sums in a fixed order), so all parity properties carry over.
+#pragma once
+
+#include "cf_pipe.cuh"
+
+namespace cf {
+
+constexpr int kPipeMaxThreads = 512 + 32;
+constexpr int kPipeMaxRowsPerCta = 8192;   // rows whose U scale is staged in smem (apply / encode)
+constexpr size_t kPipeSmemBudget = 216 * 1024;
+
+struct PipeGeom {
+  int TX, TY, G, NWX;
+  int R;            // rows per stage (multiple of 4 * TY)
+  int stages;
+  int chunk_rows;   // stats: rows between row-mean flushes (multiple of R, <= 128 + R)
+  uint32_t tile_bytes;   // R * C * 2
+  uint32_t code_tile;    // R * code_row_bytes rounded up to 128 (apply only)
+  uint32_t stage_bytes;
+  size_t smem_bytes;
+  bool ok;
+};
+
+// nfull = number of full-size fp16 operands per stage (2: x + base, 1: base), code_row_bytes = bytes of
+// code per row staged alongside (0 if none)
+static int pipe_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
+static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes) {
+  PipeGeom g{};
+  g.ok = false;
+  // tunables (measured on B200, profiles/r1_tuning.md: 512 threads / 64 KB stages is the plateau)
+  int target_threads = pipe_env_int("CF_PIPE_THREADS", 512);
+  if (target_threads > 512) target_threads = 512;
+  if (target_threads < 32) target_threads = 32;
+  const size_t stage_target = static_cast<size_t>(pipe_env_int("CF_PIPE_STAGE_KB", 64)) * 1024;
+  const int max_stages = pipe_env_int("CF_PIPE_STAGES", 4);
+  if (C % 8 != 0 || C < 64) return g;
+  const int groups = static_cast<int>(C / 8);
+  g.G = groups > 512 ? 2 : 1;
+  if (groups > 1024) return g;
+  const int per = (groups + g.G - 1) / g.G;
+  g.TX = (per + 31) / 32 * 32;
+  g.NWX = g.TX / 32;
+  g.TY = target_threads / g.TX;
+  if (g.TY < 1) g.TY = 1;
+  if (g.TY > 8) g.TY = 8;
+  int qpt = 1;  // quads per thread per stage
+  const size_t row_bytes = static_cast<size_t>(C) * 2 * nfull + code_row_bytes;
+  while (static_cast<size_t>(4 * g.TY * qpt) * row_bytes < stage_target && qpt < 4) qpt *= 2;
+  g.R = 4 * g.TY * qpt;
+  g.tile_bytes = static_cast<uint32_t>(static_cast<size_t>(g.R) * C * 2);
+  g.code_tile = static_cast<uint32_t>((static_cast<size_t>(g.R) * code_row_bytes + 127) / 128 * 128);
+  g.stage_bytes = g.tile_bytes * nfull + g.code_tile;
+  g.chunk_rows = g.R * (128 / g.R > 0 ? 128 / g.R : 1);
+  const size_t fixed = 256 /*barriers*/ + static_cast<size_t>(g.chunk_rows) * g.NWX * 4 + 256 /*warp sums*/ +
+                       static_cast<size_t>(kPipeMaxRowsPerCta) * 2;
+  int stages = static_cast<int>((kPipeSmemBudget - fixed) / g.stage_bytes);
+  if (stages > max_stages) stages = max_stages;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return g;
+  g.stages = stages;
+  g.smem_bytes = static_cast<size_t>(stages) * g.stage_bytes + fixed;
+  g.ok = true;
+  return g;
+}
+
+struct PipeArgs {
+  int TX, TY, R, stages, chunk_rows;
+  uint32_t tile_bytes, stage_bytes;
+  int rows_per_cta;
+};
+
+// ---- shared-memory carve-up --------------------------------------------------------------
+struct PipeSmem {
+  unsigned char* stage0;
+  uint64_t* full;
+  uint64_t* empty;
+  float* rowpart;   // [chunk_rows][NWX]
+  float* wsum;      // [64]
+  __half* u_s;      // [kPipeMaxRowsPerCta]
+};
+__device__ __forceinline__ PipeSmem carve_smem(unsigned char* raw, const PipeArgs& a, int NWX) {
+  PipeSmem s;
+  s.stage0 = raw;
+  unsigned char* p = raw + static_cast<size_t>(a.stages) * a.stage_bytes;
+  s.full = reinterpret_cast<uint64_t*>(p);
+  s.empty = s.full + 8;
+  p += 256;
+  s.rowpart = reinterpret_cast<float*>(p);
+  p += static_cast<size_t>(a.chunk_rows) * NWX * 4;
+  s.wsum = reinterpret_cast<float*>(p);
+  p += 256;
+  s.u_s = reinterpret_cast<__half*>(p);
+  return s;
+}
+
+__device__ __forceinline__ void pipe_init(const PipeSmem& s, const PipeArgs& a, int ncompute) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.stages; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], ncompute / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+// producer lane: stream [r_begin, r_end) in tiles of R rows; operand o has `row_bytes[o]` bytes per
+// row and lands at stage offset `off[o]`
+template <int NOPS>
+__device__ __forceinline__ void pipe_produce(const PipeSmem& s, const PipeArgs& a, const unsigned char* const* src,
+                                             const uint32_t* row_bytes, const uint32_t* off, int r_begin, int r_end) {
+  int it = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += a.R, ++it) {
+    const int st = it % a.stages, k = it / a.stages;
+    if (k > 0) mbar_wait(&s.empty[st], (k - 1) & 1);
+    const int rows = min(a.R, r_end - r0);
+    uint32_t total = 0;
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) total += static_cast<uint32_t>(rows) * row_bytes[o];
+    mbar_arrive_expect_tx(&s.full[st], total);
+    unsigned char* dst = s.stage0 + static_cast<size_t>(st) * a.stage_bytes;
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o)
+      bulk_g2s(dst + off[o], src[o] + static_cast<size_t>(r0) * row_bytes[o], static_cast<uint32_t>(rows) * row_bytes[o],
+               &s.full[st]);
+  }
+}
+
+// Bit e (e = 0..7) = (v[e] >= 0); NaN -> 0, -0 -> 1.  4 HSET2 + 4 LOP3 + 2 ALU.
+__device__ __forceinline__ uint32_t h8_ge0_bits_fast(const H8& v) {
+  const __half2 z = __float2half2_rn(0.f);
+  uint32_t acc = __hge2_mask(u2h2(v.w[0]), z) & 0x00020001u;
+  acc |= __hge2_mask(u2h2(v.w[1]), z) & 0x00080004u;
+  acc |= __hge2_mask(u2h2(v.w[2]), z) & 0x00200010u;
+  acc |= __hge2_mask(u2h2(v.w[3]), z) & 0x00800040u;
+  return (acc | (acc >> 16)) & 0xFFu;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass 1: delta statistics (+ sign packing for BINARY)           grid (B, batch)
+// ---------------------------------------------------------------------------------------
+template <int MODE, int G>
+__global__ void __launch_bounds__(kPipeMaxThreads, 1) k_delta_stats_tma(const StatsParams p, const PipeArgs a) {
+  extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
+  const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
+  const int ncompute = TX * TY;
+  const PipeSmem sm = carve_smem(pipe_smem_raw, a, NWX);
+  const int tid = threadIdx.x;
+  const int t = blockIdx.y;
+  const int N = p.N, C = p.C, groups = C >> 3;
+  const int r_begin = blockIdx.x * a.rows_per_cta;
+  const int r_end = min(N, r_begin + a.rows_per_cta);
+  pipe_init(sm, a, ncompute);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (tid >= ncompute) {  // producer warp
+    if (tid == ncompute) {
+      const unsigned char* src[2] = {reinterpret_cast<const unsigned char*>(p.x[t]),
+                                     reinterpret_cast<const unsigned char*>(p.base[t])};
+      const uint32_t rb[2] = {static_cast<uint32_t>(C) * 2u, static_cast<uint32_t>(C) * 2u};
+      const uint32_t off[2] = {0u, a.tile_bytes};
+      pipe_produce<2>(sm, a, src, rb, off, r_begin, r_end);
+    }
+    return;
+  }
+
+  uint8_t* __restrict__ packed = p.packed[t];
+  const int tx = tid % TX, ty = tid / TX;
+  const int lane = tid & 31, warp_x = tx >> 5;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
+  float2 colacc[G][4];
+#pragma unroll
+  for (int j = 0; j < G; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) colacc[j][i] = make_float2(0.f, 0.f);
+  float tokacc = 0.f;
+  const float c_f = static_cast<float>(C);
+
+  int it = 0, chunk_base = r_begin;
+  for (int r0 = r_begin; r0 < r_end; r0 += a.R, ++it) {
+    const int st = it % a.stages, k = it / a.stages;
+    mbar_wait(&sm.full[st], k & 1);
+    const unsigned char* xs = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
+    const unsigned char* bs = xs + a.tile_bytes;
+    const int rows = min(a.R, r_end - r0);
+    for (int q = ty; 4 * q < rows; q += TY) {
+      float rs[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int rl = 4 * q + rr;
+        float2 acc2 = make_float2(0.f, 0.f);
+        if (rl < rows) {  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int g = tx + j * TX;
+            if (g < groups) {
+              const uint32_t o = static_cast<uint32_t>(rl) * row_bytes + static_cast<uint32_t>(g) * 16u;
+              const H8 d = h8_sub(as_h8(lds128(xs + o)), as_h8(lds128(bs + o)));
+              if (MODE == MODE_BINARY)
+                packed[static_cast<size_t>(r0 + rl) * groups + g] = static_cast<uint8_t>(h8_ge0_bits_fast(d));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(__habs2(u2h2(d.w[i])));
+                colacc[j][i] = __fadd2_rn(colacc[j][i], f);
+                acc2 = __fadd2_rn(acc2, f);
+              }
+            }
+          }
+        }
+        rs[rr] = acc2.x + acc2.y;
+      }
+      // transposed warp reduction of the 4 row sums: 6 shuffles instead of 20 (fixed order)
+      const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+      float a0 = hi16 ? rs[2] : rs[0], s0 = hi16 ? rs[0] : rs[2];
+      float a1 = hi16 ? rs[3] : rs[1], s1 = hi16 ? rs[1] : rs[3];
+      a0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+      a1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      float c0 = hi8 ? a1 : a0;
+      const float s2 = hi8 ? a0 : a1;
+      c0 += __shfl_xor_sync(0xffffffffu, s2, 8);
+      c0 += __shfl_xor_sync(0xffffffffu, c0, 4);
+      c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+      c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
+      if ((lane & 7) == 0) {
+        const int rl = 4 * q + (lane >> 3);
+        if (rl < rows) sm.rowpart[(r0 + rl - chunk_base) * NWX + warp_x] = c0;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[st]);
+
+    const int done = r0 + rows;  // rows [chunk_base, done) have partial sums staged
+    if (done - chunk_base >= a.chunk_rows || done >= r_end) {
+      compute_sync(ncompute);
+      for (int i = tid; i < done - chunk_base; i += ncompute) {
+        float s = 0.f;
+        for (int w = 0; w < NWX; ++w) s += sm.rowpart[i * NWX + w];
+        const __half h = __float2half_rn(s / c_f);
+        p.rowmean[t][chunk_base + i] = h;
+        tokacc += __half2float(h);
+      }
+      compute_sync(ncompute);
+      chunk_base = done;
+    }
+  }
+
+  // ---- CTA partial of sum_n rowmean[n] ----
+  {
+    const float v = warp_sum(tokacc);
+    const int wid = tid >> 5, nw = ncompute >> 5;
+    if (lane == 0) sm.wsum[wid] = v;
+    compute_sync(ncompute);
+    if (tid == 0) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += sm.wsum[w];
+      p.tokpart[t][blockIdx.x] = s;
+    }
+  }
+
+  // ---- CTA partial column sums (ty reduced in order through the drained stage memory) ----
+  float* __restrict__ colout = p.colpart[t] + static_cast<size_t>(blockIdx.x) * C;
+  if (TY > 1) {
+    float* red = reinterpret_cast<float*>(sm.stage0);  // [ty][j][tx][8]
+    compute_sync(ncompute);                            // every warp is past its last stage read
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      float4* dst = reinterpret_cast<float4*>(red + ((static_cast<size_t>(ty) * G + j) * TX + tx) * 8);
+      dst[0] = make_float4(colacc[j][0].x, colacc[j][0].y, colacc[j][1].x, colacc[j][1].y);
+      dst[1] = make_float4(colacc[j][2].x, colacc[j][2].y, colacc[j][3].x, colacc[j][3].y);
+    }
+    compute_sync(ncompute);
+    if (ty == 0) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        if (g < groups) {
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          for (int yy = 0; yy < TY; ++yy) {
+            const float* src = red + ((static_cast<size_t>(yy) * G + j) * TX + tx) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += src[e];
+          }
+          float4* o = reinterpret_cast<float4*>(colout + 8 * g);
+          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int g = tx + j * TX;
+      if (g < groups) {
+        float4* o = reinterpret_cast<float4*>(colout + 8 * g);
+        o[0] = make_float4(colacc[j][0].x, colacc[j][0].y, colacc[j][1].x, colacc[j][1].y);
+        o[1] = make_float4(colacc[j][2].x, colacc[j][2].y, colacc[j][3].x, colacc[j][3].y);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Flattened tile schedule for the kernels without cross-row reductions (apply, INT2 encode):
+// tiles enumerate (tensor, row tile) pairs; every CTA owns a contiguous range of
+// `tiles_per_cta` tiles, so 148 CTAs stay evenly loaded whatever the batch size.
+// ---------------------------------------------------------------------------------------
+struct TileSched {
+  int tiles_per_tensor, total_tiles, tiles_per_cta;
+};
+
+// stage the per-row scales of all rows this CTA will touch (vectors may be only 2-byte aligned)
+template <typename P>
+__device__ __forceinline__ void stage_row_scales(const PipeSmem& sm, const P& p, const TileSched& ts, int R, int T0,
+                                                 int T1, int tid, int ncompute) {
+  const int n = (T1 - T0) * R;
+  for (int i = tid; i < n; i += ncompute) {
+    const int tile = T0 + i / R;
+    const int t = tile / ts.tiles_per_tensor;
+    const int row = (tile % ts.tiles_per_tensor) * R + i % R;
+    if (row < p.N) sm.u_s[i] = p.scale_u[t][row];
+  }
+  compute_sync(ncompute);
+}
+
+template <int G>
+__device__ __forceinline__ void load_vfrag(uint32_t (&vfrag)[G][4], const __half* __restrict__ sv, int tx, int TX,
+                                           int groups) {
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int g = tx + j * TX;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vfrag[j][i] = (g < groups) ? load_v_pair(sv, 8 * g + 2 * i) : 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// apply: recon = base + dequant(codes, U, V)        grid (nCTA); recon may alias base
+// stage = [base tile | code tile]
+// ---------------------------------------------------------------------------------------
+template <int MODE, int G>
+__global__ void __launch_bounds__(kPipeMaxThreads, 1) k_apply_codes_tma(const ApplyParams p, const PipeArgs a,
+                                                                        const TileSched ts) {
+  extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
+  const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
+  const int ncompute = TX * TY;
+  const PipeSmem sm = carve_smem(pipe_smem_raw, a, NWX);
+  const int tid = threadIdx.x;
+  const int N = p.N, C = p.C, groups = C >> 3;
+  const int T0 = blockIdx.x * ts.tiles_per_cta;
+  const int T1 = min(ts.total_tiles, T0 + ts.tiles_per_cta);
+  const uint32_t code_row = (MODE == MODE_BINARY) ? static_cast<uint32_t>(C) / 8u : static_cast<uint32_t>(C) / 4u;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
+  pipe_init(sm, a, ncompute);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (tid >= ncompute) {
+    if (tid == ncompute) {
+      for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
+        const int st = it % a.stages, k = it / a.stages;
+        if (k > 0) mbar_wait(&sm.empty[st], (k - 1) & 1);
+        const int t = tile / ts.tiles_per_tensor;
+        const int r0 = (tile % ts.tiles_per_tensor) * a.R;
+        const uint32_t rows = static_cast<uint32_t>(min(a.R, N - r0));
+        mbar_arrive_expect_tx(&sm.full[st], rows * (row_bytes + code_row));
+        unsigned char* dst = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
+        bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes,
+                 rows * row_bytes, &sm.full[st]);
+        bulk_g2s(dst + a.tile_bytes, p.packed[t] + static_cast<size_t>(r0) * code_row, rows * code_row, &sm.full[st]);
+      }
+    }
+    return;
+  }
+
+  const int tx = tid % TX, ty = tid / TX, lane = tid & 31;
+  uint32_t vfrag[G][4];
+  int cur_t = -1;
+  stage_row_scales(sm, p, ts, a.R, T0, T1, tid, ncompute);
+
+  for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
+    const int st = it % a.stages, k = it / a.stages;
+    const int t = tile / ts.tiles_per_tensor;
+    const int r0 = (tile % ts.tiles_per_tensor) * a.R;
+    if (t != cur_t) {
+      load_vfrag<G>(vfrag, p.scale_v[t], tx, TX, groups);
+      cur_t = t;
+    }
+    __half* __restrict__ recon = p.recon[t];
+    mbar_wait(&sm.full[st], k & 1);
+    const unsigned char* bs = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
+    const unsigned char* cs = bs + a.tile_bytes;
+    const int rows = min(a.R, N - r0);
+    const __half* us = sm.u_s + it * a.R;
+#pragma unroll 4
+    for (int rl = ty; rl < rows; rl += TY) {
+      const __half2 u2 = __half2half2(us[rl]);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        if (g < groups) {
+          const H8 b = as_h8(lds128(bs + static_cast<uint32_t>(rl) * row_bytes + static_cast<uint32_t>(g) * 16u));
+          H8 out;
+          if (MODE == MODE_BINARY) {
+            const uint32_t code = cs[static_cast<uint32_t>(rl) * code_row + g];
+            out = binary_apply8(b, code, u2, vfrag[j]);
+          } else {
+            const uint32_t code = *reinterpret_cast<const uint16_t*>(cs + static_cast<uint32_t>(rl) * code_row + 2 * g);
+            out = int2_apply8(b, code, u2, vfrag[j]);
+          }
+          stg_stream(recon + static_cast<size_t>(r0 + rl) * C + 8 * g, as_u4(out));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[st]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// INT2 encode (second pass): codes (+ optional new_base) from x, base and the final scales
+// stage = [x tile | base tile]
+// ---------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kPipeMaxThreads, 1) k_int2_encode_tma(const Int2EncodeParams p, const PipeArgs a,
+                                                                        const TileSched ts) {
+  extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
+  const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
+  const int ncompute = TX * TY;
+  const PipeSmem sm = carve_smem(pipe_smem_raw, a, NWX);
+  const int tid = threadIdx.x;
+  const int N = p.N, C = p.C, groups = C >> 3;
+  const int T0 = blockIdx.x * ts.tiles_per_cta;
+  const int T1 = min(ts.total_tiles, T0 + ts.tiles_per_cta);
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
+  pipe_init(sm, a, ncompute);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (tid >= ncompute) {
+    if (tid == ncompute) {
+      for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
+        const int st = it % a.stages, k = it / a.stages;
+        if (k > 0) mbar_wait(&sm.empty[st], (k - 1) & 1);
+        const int t = tile / ts.tiles_per_tensor;
+        const int r0 = (tile % ts.tiles_per_tensor) * a.R;
+        const uint32_t bytes = static_cast<uint32_t>(min(a.R, N - r0)) * row_bytes;
+        mbar_arrive_expect_tx(&sm.full[st], 2 * bytes);
+        unsigned char* dst = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
+        bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.x[t]) + static_cast<size_t>(r0) * row_bytes, bytes,
+                 &sm.full[st]);
+        bulk_g2s(dst + a.tile_bytes, reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes,
+                 bytes, &sm.full[st]);
+      }
+    }
+    return;
+  }
+
+  const int tx = tid % TX, ty = tid / TX, lane = tid & 31;
+  uint32_t vfrag[G][4];
+  int cur_t = -1;
+  stage_row_scales(sm, p, ts, a.R, T0, T1, tid, ncompute);
+  const __half2 zero2 = __float2half2_rn(0.f);
+
+  for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
+    const int st = it % a.stages, k = it / a.stages;
+    const int t = tile / ts.tiles_per_tensor;
+    const int r0 = (tile % ts.tiles_per_tensor) * a.R;
+    if (t != cur_t) {
+      load_vfrag<G>(vfrag, p.scale_v[t], tx, TX, groups);
+      cur_t = t;
+    }
+    uint8_t* __restrict__ packed = p.packed[t];
+    __half* __restrict__ new_base = p.new_base[t];
+    mbar_wait(&sm.full[st], k & 1);
+    const unsigned char* xs = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
+    const unsigned char* bs = xs + a.tile_bytes;
+    const int rows = min(a.R, N - r0);
+    const __half* us = sm.u_s + it * a.R;
+#pragma unroll 4
+    for (int rl = ty; rl < rows; rl += TY) {
+      const __half2 u2 = __half2half2(us[rl]);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int g = tx + j * TX;
+        if (g < groups) {
+          const uint32_t o = static_cast<uint32_t>(rl) * row_bytes + static_cast<uint32_t>(g) * 16u;
+          const H8 b = as_h8(lds128(bs + o));
+          const H8 d = h8_sub(as_h8(lds128(xs + o)), b);
+          uint32_t sacc = 0, macc = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __half2 thr = __hmul2_rn(u2h2(vfrag[j][i]), u2);                  // fastpath.py:536
+            const uint32_t sgn = __hge2_mask(u2h2(d.w[i]), zero2);                   // fastpath.py:539
+            const uint32_t mag = __hgt2_mask(__habs2(u2h2(d.w[i])), thr);            // fastpath.py:540
+            // element 2i -> bits 4i (mag), 4i+1 (sign); element 2i+1 -> bits 4i+2, 4i+3, taken from the
+            // high half of the mask (16 positions up, folded down below)
+            sacc |= sgn & ((2u << (4 * i)) | (8u << (4 * i + 16)));
+            macc |= mag & ((1u << (4 * i)) | (4u << (4 * i + 16)));
+          }
+          const uint32_t both = sacc | macc;
+          const uint32_t codes = (both | (both >> 16)) & 0xFFFFu;
+          *reinterpret_cast<uint16_t*>(packed + (static_cast<size_t>(r0 + rl) * groups + g) * 2) =
+              static_cast<uint16_t>(codes);
+          if (new_base != nullptr) {
+            const H8 nb = int2_apply8(b, codes, u2, vfrag[j]);
+            stg_stream(new_base + static_cast<size_t>(r0 + rl) * C + 8 * g, as_u4(nb));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[st]);
+  }
+}
+
+}  // namespace cf

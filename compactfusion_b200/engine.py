@@ -123,15 +123,18 @@ class PatchGatherEngine:
             self._ptr_cache[key] = args
         return args
 
-    def compress(self, layer, k, v, ctype):
+    def compress(self, layer, k, v, ctype, passes: int = nv.PASS_ALL):
         """K and V of this rank -> the send buffer (no cache update: the sender's own shard is
-        updated by the decompress below, like every other origin; main.py:400-405)."""
+        updated by the decompress below, like every other origin; main.py:400-405).
+        `passes` selects individual kernels of the call (bench.py times them one by one)."""
         k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
         xs, bases, nones, pk, us, vs, ws = self._compress_args(layer, k2, v2, ctype)
-        fn = nv.lib().cf_binary_compress_batched if ctype == T.BINARY else nv.lib().cf_int2_compress_batched
-        rc = fn(2, xs, bases, nones, pk, us, vs, self.n, self.c, ws.data_ptr(), ws.numel(), nv.stream_ptr())
-        nv.check(rc, "compress_batched")
-        self.kernel_launches += 2 if ctype == T.BINARY else 3
+        rc = nv.lib().cf_sign_compress_passes(_CODEC[ctype], passes, 2, xs, bases, nones, pk, us, vs, self.n, self.c,
+                                              ws.data_ptr(), ws.numel(), nv.stream_ptr())
+        nv.check(rc, "cf_sign_compress_passes")
+        if ctype == T.BINARY:
+            passes &= ~nv.PASS_ENCODE  # no cache update on the sender: BINARY has no third kernel
+        self.kernel_launches += bin(passes).count("1")
 
     def gather(self, ctype):
         send, recv = self._buffers(ctype)

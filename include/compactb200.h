@@ -123,6 +123,17 @@ CF_API int cf_int2_encode_with_scales(const void* x, const void* base, const voi
                                const void* scale_v, void* new_base, void* packed, int64_t N,
                                int64_t C, cf_stream_t stream);
 
+/* Profiling hook: run only the selected passes of cf_{binary,int2}_compress_batched, so that
+ * bench.py can time each kernel of the compress call with CUDA events on its own.
+ * CF_PASS_STATS = delta statistics (+ BINARY sign bits), CF_PASS_FINALIZE = scale vectors,
+ * CF_PASS_ENCODE = INT2 codes / error-feedback base.  Later passes read what earlier ones
+ * left in `workspace`; CF_PASS_ALL is the ordinary compress call. */
+enum cf_pass { CF_PASS_STATS = 1, CF_PASS_FINALIZE = 2, CF_PASS_ENCODE = 4, CF_PASS_ALL = 7 };
+CF_API int cf_sign_compress_passes(int codec, int passes, int batch, const void* const* x,
+                            const void* const* base, void* const* new_base, void* const* packed,
+                            void* const* scale_u, void* const* scale_v, int64_t N, int64_t C,
+                            void* workspace, size_t workspace_bytes, cf_stream_t stream);
+
 /* ---- INT4 / INT8: per-channel (over N) min/max affine codes ----------------------------
  * INT4 replaces quantize_int4 / dequantize_int4 / sim_int4(dim=0) (compress_quantize.py:
  * 487-640): scale = fp16((max-min)/(15+1e-6)), q = clamp(rne((v-min)/scale),0,15), rows

@@ -41,12 +41,22 @@ def make_xb(n, c, seed, scale_base=0.1):
     return x, base
 
 
-SHAPES = [(2048, 1024), (8192, 512), (1088, 3072), (130, 64), (77, 1152), (64, 8192), (16, 16384)]
+SHAPES = [(2048, 1024), (8192, 512), (1088, 3072), (130, 64), (77, 1152), (64, 8192), (16, 16384),
+          (4608, 3072), (5001, 1152), (3000, 1536), (2050, 6144), (9, 3072)]
+
+
+@pytest.fixture(params=["tma", "legacy"])
+def kernel_path(request, monkeypatch):
+    """Both implementations of the streaming kernels must meet the same parity bars: the
+    bulk-async (TMA) pipelined ones (default) and the register-staged ones (fallback for
+    unaligned / very wide shapes, forced here with CF_LEGACY_KERNELS=1)."""
+    monkeypatch.setenv("CF_LEGACY_KERNELS", "1" if request.param == "legacy" else "0")
+    return request.param
 
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("update_cache", [True, False])
-def test_binary_fastpath_vs_oracle(shape, update_cache):
+def test_binary_fastpath_vs_oracle(shape, update_cache, kernel_path):
     dev = _cuda()
     from compactfusion_b200.fastpath import binary_dequant_fastpath, binary_quant_fastpath
     n, c = shape
@@ -71,7 +81,7 @@ def test_binary_fastpath_vs_oracle(shape, update_cache):
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("update_cache", [True, False])
-def test_int2_fastpath_vs_oracle(shape, update_cache):
+def test_int2_fastpath_vs_oracle(shape, update_cache, kernel_path):
     dev = _cuda()
     from compactfusion_b200 import _native as nv
     from compactfusion_b200.fastpath import int2_dequant_fastpath, int2_quant_fastpath
