@@ -49,9 +49,13 @@ def parse():
     p.add_argument("--codec", default="binary", choices=["binary", "int2"])
     p.add_argument("--layers", type=int, default=LAYERS)
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    p.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                   help="payload exchange for N > 1: one-sided NVLink puts (p2p) or NCCL all-gather")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-layers", type=int, default=2)
+    p.add_argument("--hang-dump", type=float, default=0.0,
+                   help="debug: dump all Python stacks and exit if the run takes longer than this many seconds")
     return p.parse_args()
 
 
@@ -226,10 +230,22 @@ def run_reference(args, world, rank):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+_T0 = time.time()
+
+
+def note(rank, msg):
+    """progress marker on stderr (CF_BENCH_VERBOSE=1): where a multi-rank run is, with wall time"""
+    if os.environ.get("CF_BENCH_VERBOSE", "0") == "1":
+        print(f"[bench r{rank} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if args.hang_dump > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.hang_dump, exit=True)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, max(world, args.gpus), rank)
@@ -246,7 +262,13 @@ def main():
     from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
     ctype = T.BINARY if args.codec == "binary" else T.INT2
     n_local, layers = SEQ // world, args.layers
-    eng = PatchGatherEngine(layers, n_local, CH, group=None, device=device)
+    eng = PatchGatherEngine(layers, n_local, CH, group=None, device=device, transport=args.transport)
+    transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
+    note(rank, f"transport: {transport}")
+    if transport == "nccl" and not args.no_graph:
+        # NCCL collectives inside the captured step hang on replay on this stack (torch 2.11 / NCCL 2.28):
+        # with the NCCL transport the step is launched eagerly
+        args.no_graph = True
     versions = 2
     acts = synth_activations(n_local, layers, versions, device, rank)
     ks = [[acts[l][0][v] for l in range(layers)] for v in range(versions)]
@@ -257,8 +279,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    note(rank, "inputs ready")
     # step 0: WARMUP (uncompressed), not timed
     eng.step(ks[0], vs[0], T.WARMUP)
+    torch.cuda.synchronize()
+    note(rank, "warmup step done")
     graphs = None
     mode = "eager"
     if not args.no_graph:
@@ -268,6 +293,8 @@ def main():
         except Exception as e:  # capture can fail with NCCL inside: fall back to eager launches
             graphs, mode = None, f"eager (graph capture failed: {type(e).__name__})"
             torch.cuda.synchronize()
+
+    note(rank, f"launch mode: {mode}")
 
     def run_step(i):
         v = (i + 1) % versions
@@ -291,6 +318,7 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    note(rank, f"timed region done: {ms / args.steps:.3f} ms/step")
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,6 +383,7 @@ def main():
     n_launch_per_call = (2 * world + 15) // 16
     time_kernel(apply_name, lambda l: eng.decompress(l, ctype),
                 2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
+    note(rank, "per-kernel timing done")
     kernels[-1]["avg_launch_us"] /= n_launch_per_call
     kernels[-1]["algorithmic_bytes_per_launch"] //= n_launch_per_call
     peak, peak_src = measured_hbm_peak()
@@ -429,6 +458,7 @@ def main():
                "path": "pinned host K/V -> H2D -> PatchGatherEngine.exchange (C-ABI batched kernels + NCCL) -> "
                        "D2H of reconstructed global K/V, double-buffered over 3 streams"}
 
+    note(rank, "e2e done")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -443,6 +473,7 @@ def main():
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
+                       "transport": transport,
                        "l2": "inputs larger than L2 (each step streams > 6 GB of distinct K/V + cache)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
         }))

@@ -245,6 +245,10 @@ struct ApplyParams {
   const __half* scale_v[CF_MAX_BATCH];
   const __half* base[CF_MAX_BATCH];  // may be null
   __half* recon[CF_MAX_BATCH];
+  // one-sided transport (cf_p2p.cu): payload t is valid once *wait_flag[t] >= *expected
+  const uint32_t* wait_flag[CF_MAX_BATCH];  // null entries: no wait
+  const uint32_t* expected;                 // null: no waiting at all
+  uint32_t* error;                          // set to 1 if a wait timed out
   int N, C, K;
 };
 
@@ -521,7 +525,7 @@ static cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 
 static PipeArgs pipe_args(const PipeGeom& g, int rows_per_cta) {
   PipeArgs a{};
-  a.TX = g.TX; a.TY = g.TY; a.R = g.R; a.stages = g.stages; a.chunk_rows = g.chunk_rows;
+  a.TX = g.TX; a.TY = g.TY; a.R = g.R; a.stages = g.stages; a.chunk_rows = g.chunk_rows; a.u_cap = g.u_cap;
   a.tile_bytes = g.tile_bytes; a.stage_bytes = g.stage_bytes; a.rows_per_cta = rows_per_cta;
   return a;
 }
@@ -530,10 +534,10 @@ static TileSched make_tile_sched(const PipeGeom& g, int64_t N, int batch, int* n
   TileSched ts{};
   ts.tiles_per_tensor = static_cast<int>((N + g.R - 1) / g.R);
   ts.total_tiles = ts.tiles_per_tensor * batch;
-  int ctas = sm_count();
+  int ctas = sm_count() * g.ctas_per_sm;
   if (ctas > ts.total_tiles) ctas = ts.total_tiles;
   ts.tiles_per_cta = (ts.total_tiles + ctas - 1) / ctas;
-  const int cap = kPipeMaxRowsPerCta / g.R;
+  const int cap = g.u_cap / g.R > 0 ? g.u_cap / g.R : 1;
   if (ts.tiles_per_cta > cap) ts.tiles_per_cta = cap;
   *n_cta = (ts.total_tiles + ts.tiles_per_cta - 1) / ts.tiles_per_cta;
   return ts;
@@ -554,9 +558,9 @@ static StatsPlan make_stats_plan(int64_t N, int64_t C, int batch, bool allow_tma
   pl.geom = make_row_geom(C);
   pl.tma = false;
   if (allow_tma && !legacy_forced()) {
-    pl.pipe = make_pipe_geom(C, 2, 0);
+    pl.pipe = make_pipe_geom(C, 2, 0, false);
     if (pl.pipe.ok) {
-      int B = sm_count() / (batch > 0 ? batch : 1);
+      int B = sm_count() * pl.pipe.ctas_per_sm / (batch > 0 ? batch : 1);
       if (B < 1) B = 1;
       int64_t rpc = (N + B - 1) / B;
       rpc = (rpc + pl.pipe.R - 1) / pl.pipe.R * pl.pipe.R;  // tile starts stay stage-aligned
@@ -604,10 +608,13 @@ static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, c
   if (pl.tma) {
     const PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta);
     dim3 grid(pl.B, batch), block(pl.pipe.TX * pl.pipe.TY + 32);
-    if (pl.pipe.G == 1)
-      CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 1>, grid, block, pl.pipe.smem_bytes, st, true, sp, a));
-    else
-      CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 2>, grid, block, pl.pipe.smem_bytes, st, true, sp, a));
+    const int variant = (pl.pipe.G == 1 ? 0 : 2) + (pl.pipe.ctas_per_sm == 1 ? 0 : 1);
+    switch (variant) {
+      case 0: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 1, 1>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
+      case 1: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 1, 2>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
+      case 2: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 2, 1>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
+      default: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 2, 2>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
+    }
     return CF_OK;
   }
   dim3 grid(pl.B, batch), block(pl.geom.TX, pl.geom.TY);
@@ -647,22 +654,31 @@ static int apply_grid_x(const RowGeom& g, int64_t N, int batch) {
 template <int MODE>
 static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
   const int code_row = (MODE == MODE_BINARY) ? ap.C / 8 : ap.C / 4;
-  bool tma = !legacy_forced() && code_row % 16 == 0;
+  const bool need_wait = ap.expected != nullptr;
+  bool tma = (need_wait || !legacy_forced()) && code_row % 16 == 0;
   for (int t = 0; t < batch && tma; ++t)
     tma = ap.base[t] != nullptr && aligned16(ap.base[t]) && aligned16(ap.packed[t]);
   if (tma) {
-    const PipeGeom pg = make_pipe_geom(ap.C, 1, code_row);
+    const PipeGeom pg = make_pipe_geom(ap.C, 1, code_row, true);
     if (pg.ok) {
       int n_cta = 1;
       const TileSched ts = make_tile_sched(pg, ap.N, batch, &n_cta);
       const PipeArgs a = pipe_args(pg, 0);
       dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
-      if (pg.G == 1)
-        CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 1>, grid, block, pg.smem_bytes, st, true, ap, a, ts));
-      else
-        CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 2>, grid, block, pg.smem_bytes, st, true, ap, a, ts));
+      const int variant = (pg.G == 1 ? 0 : 2) + (pg.ctas_per_sm == 1 ? 0 : 1);
+      switch (variant) {
+        case 0: CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 1, 1>, grid, block, pg.smem_bytes, st, true, ap, a, ts)); break;
+        case 1: CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 1, 2>, grid, block, pg.smem_bytes, st, true, ap, a, ts)); break;
+        case 2: CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 2, 1>, grid, block, pg.smem_bytes, st, true, ap, a, ts)); break;
+        default: CF_CHECK_CUDA(launch_ex(k_apply_codes_tma<MODE, 2, 2>, grid, block, pg.smem_bytes, st, true, ap, a, ts)); break;
+      }
       return CF_OK;
     }
+  }
+  if (need_wait) {
+    set_error("flag-waiting decompress needs the pipelined kernel: 16-byte aligned base / codes, C %% 128 == 0 "
+              "(C %% 64 for INT2), C <= 8192");
+    return CF_ERR_UNSUPPORTED;
   }
   const RowGeom g = make_row_geom(ap.C);
   dim3 grid(apply_grid_x(g, ap.N, batch), batch), block(g.TX, g.TY);
@@ -684,16 +700,19 @@ static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_
   for (int t = 0; t < batch && tma; ++t)
     tma = ep.base[t] != nullptr && aligned16(ep.base[t]) && aligned16(ep.x[t]) && aligned2(ep.packed[t]);
   if (tma) {
-    const PipeGeom pg = make_pipe_geom(ep.C, 2, 0);
+    const PipeGeom pg = make_pipe_geom(ep.C, 2, 0, true);
     if (pg.ok) {
       int n_cta = 1;
       const TileSched ts = make_tile_sched(pg, ep.N, batch, &n_cta);
       const PipeArgs a = pipe_args(pg, 0);
       dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
-      if (pg.G == 1)
-        CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<1>, grid, block, pg.smem_bytes, st, true, ep, a, ts));
-      else
-        CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<2>, grid, block, pg.smem_bytes, st, true, ep, a, ts));
+      const int variant = (pg.G == 1 ? 0 : 2) + (pg.ctas_per_sm == 1 ? 0 : 1);
+      switch (variant) {
+        case 0: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<1, 1>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
+        case 1: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<1, 2>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
+        case 2: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<2, 1>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
+        default: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<2, 2>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
+      }
       return CF_OK;
     }
   }
@@ -805,7 +824,8 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
 template <int MODE>
 static int sign_decompress(int batch, const void* const* packed, const void* const* scale_u,
                            const void* const* scale_v, int K, const void* const* base, void* const* recon,
-                           int64_t N, int64_t C, cf_stream_t stream) {
+                           int64_t N, int64_t C, cf_stream_t stream, const void* const* wait_flag = nullptr,
+                           const void* expected = nullptr, void* error = nullptr) {
   if (int rc = check_shape(N, C, batch)) return rc;
   CF_CHECK_ARG(K >= 1, "K must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -821,7 +841,11 @@ static int sign_decompress(int batch, const void* const* packed, const void* con
     ap.scale_v[t] = static_cast<const __half*>(scale_v[t]);
     ap.base[t] = base ? static_cast<const __half*>(base[t]) : nullptr;
     ap.recon[t] = static_cast<__half*>(recon[t]);
+    ap.wait_flag[t] = (wait_flag && expected) ? static_cast<const uint32_t*>(wait_flag[t]) : nullptr;
   }
+  ap.expected = (wait_flag && expected) ? static_cast<const uint32_t*>(expected) : nullptr;
+  ap.error = static_cast<uint32_t*>(error);
+  CF_CHECK_ARG(ap.expected == nullptr || (K == 1 && ap.error != nullptr), "flag waiting needs K == 1 and an error word");
   if (K > 1) {
     CF_CHECK_ARG(MODE == MODE_BINARY, "rank-K scales are only defined for BINARY");
     for (int t = 0; t < batch; ++t) {
@@ -897,6 +921,17 @@ int cf_sign_compress_passes(int codec, int passes, int batch, const void* const*
                                               workspace_bytes, stream, passes);
   return cf::sign_compress<cf::MODE_INT2>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
                                           workspace_bytes, stream, passes);
+}
+int cf_sign_decompress_batched_wait(int codec, int batch, const void* const* packed, const void* const* scale_u,
+                                    const void* const* scale_v, const void* const* base, void* const* recon,
+                                    const void* const* wait_flag, const void* expected, void* error_word, int64_t N,
+                                    int64_t C, cf_stream_t stream) {
+  CF_CHECK_ARG(codec == CF_CODEC_BINARY || codec == CF_CODEC_INT2, "codec must be CF_CODEC_BINARY or CF_CODEC_INT2");
+  if (codec == CF_CODEC_BINARY)
+    return cf::sign_decompress<cf::MODE_BINARY>(batch, packed, scale_u, scale_v, 1, base, recon, N, C, stream,
+                                                wait_flag, expected, error_word);
+  return cf::sign_decompress<cf::MODE_INT2>(batch, packed, scale_u, scale_v, 1, base, recon, N, C, stream, wait_flag,
+                                            expected, error_word);
 }
 int cf_int2_encode_with_scales(const void* x, const void* base, const void* scale_u, const void* scale_v,
                                void* new_base, void* packed, int64_t N, int64_t C, cf_stream_t stream) {

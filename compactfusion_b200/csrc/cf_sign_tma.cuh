@@ -14,14 +14,15 @@
 namespace cf {
 
 constexpr int kPipeMaxThreads = 512 + 32;
-constexpr int kPipeMaxRowsPerCta = 8192;   // rows whose U scale is staged in smem (apply / encode)
-constexpr size_t kPipeSmemBudget = 216 * 1024;
+constexpr size_t kPipeSmemBudget = 216 * 1024;  // per SM, shared by `ctas_per_sm` resident CTAs
 
 struct PipeGeom {
   int TX, TY, G, NWX;
   int R;            // rows per stage (multiple of 4 * TY)
   int stages;
-  int chunk_rows;   // stats: rows between row-mean flushes (multiple of R, <= 128 + R)
+  int ctas_per_sm;  // 1 or 2
+  int chunk_rows;   // stats: rows between row-mean flushes (multiple of R, <= 128)
+  int u_cap;        // apply / encode: per-row scales staged in smem (rows per CTA <= u_cap)
   uint32_t tile_bytes;   // R * C * 2
   uint32_t code_tile;    // R * code_row_bytes rounded up to 128 (apply only)
   uint32_t stage_bytes;
@@ -29,22 +30,24 @@ struct PipeGeom {
   bool ok;
 };
 
-// nfull = number of full-size fp16 operands per stage (2: x + base, 1: base), code_row_bytes = bytes of
-// code per row staged alongside (0 if none)
 static int pipe_env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
-static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes) {
+// nfull = number of full-size fp16 operands per stage (2: x + base, 1: base), code_row_bytes = bytes of
+// code per row staged alongside (0 if none), row_scales = the kernel stages per-row scales in smem
+static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes, bool row_scales) {
   PipeGeom g{};
   g.ok = false;
-  // tunables (measured on B200, profiles/r1_tuning.md: 512 threads / 64 KB stages is the plateau)
+  // tunables (measured on B200, profiles/r1_tuning.md)
   int target_threads = pipe_env_int("CF_PIPE_THREADS", 512);
   if (target_threads > 512) target_threads = 512;
   if (target_threads < 32) target_threads = 32;
-  const size_t stage_target = static_cast<size_t>(pipe_env_int("CF_PIPE_STAGE_KB", 64)) * 1024;
-  const int max_stages = pipe_env_int("CF_PIPE_STAGES", 4);
+  const size_t stage_target = static_cast<size_t>(pipe_env_int("CF_PIPE_STAGE_KB", 48)) * 1024;
+  int max_stages = pipe_env_int("CF_PIPE_STAGES", 4);
+  if (max_stages > 8) max_stages = 8;
+  g.ctas_per_sm = pipe_env_int("CF_PIPE_CTAS", 2) >= 2 ? 2 : 1;
   if (C % 8 != 0 || C < 64) return g;
   const int groups = static_cast<int>(C / 8);
   g.G = groups > 512 ? 2 : 1;
@@ -55,28 +58,34 @@ static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes) {
   g.TY = target_threads / g.TX;
   if (g.TY < 1) g.TY = 1;
   if (g.TY > 8) g.TY = 8;
-  int qpt = 1;  // quads per thread per stage
   const size_t row_bytes = static_cast<size_t>(C) * 2 * nfull + code_row_bytes;
-  while (static_cast<size_t>(4 * g.TY * qpt) * row_bytes < stage_target && qpt < 4) qpt *= 2;
-  g.R = 4 * g.TY * qpt;
-  g.tile_bytes = static_cast<uint32_t>(static_cast<size_t>(g.R) * C * 2);
-  g.code_tile = static_cast<uint32_t>((static_cast<size_t>(g.R) * code_row_bytes + 127) / 128 * 128);
-  g.stage_bytes = g.tile_bytes * nfull + g.code_tile;
-  g.chunk_rows = g.R * (128 / g.R > 0 ? 128 / g.R : 1);
-  const size_t fixed = 256 /*barriers*/ + static_cast<size_t>(g.chunk_rows) * g.NWX * 4 + 256 /*warp sums*/ +
-                       static_cast<size_t>(kPipeMaxRowsPerCta) * 2;
-  int stages = static_cast<int>((kPipeSmemBudget - fixed) / g.stage_bytes);
-  if (stages > max_stages) stages = max_stages;
-  if (stages > 8) stages = 8;
-  if (stages < 2) return g;
-  g.stages = stages;
-  g.smem_bytes = static_cast<size_t>(stages) * g.stage_bytes + fixed;
-  g.ok = true;
+  g.u_cap = row_scales ? 2048 : 0;
+  for (; g.ctas_per_sm >= 1; --g.ctas_per_sm) {
+    const size_t budget = kPipeSmemBudget / g.ctas_per_sm;
+    for (int qpt = 4; qpt >= 1; qpt /= 2) {  // quads per thread per stage: largest stage <= target with >= 2 stages
+      g.R = 4 * g.TY * qpt;
+      if (qpt > 1 && static_cast<size_t>(g.R) * row_bytes > stage_target) continue;
+      g.tile_bytes = static_cast<uint32_t>(static_cast<size_t>(g.R) * C * 2);
+      g.code_tile = static_cast<uint32_t>((static_cast<size_t>(g.R) * code_row_bytes + 127) / 128 * 128);
+      g.stage_bytes = g.tile_bytes * nfull + g.code_tile;
+      g.chunk_rows = g.R * (128 / g.R > 0 ? 128 / g.R : 1);
+      const size_t fixed = 256 /*barriers*/ + static_cast<size_t>(g.chunk_rows) * g.NWX * 4 + 256 /*warp sums*/ +
+                           static_cast<size_t>(g.u_cap) * 2;
+      if (budget < fixed + 2 * static_cast<size_t>(g.stage_bytes)) continue;
+      int stages = static_cast<int>((budget - fixed) / g.stage_bytes);
+      if (stages > max_stages) stages = max_stages;
+      g.stages = stages;
+      g.smem_bytes = static_cast<size_t>(stages) * g.stage_bytes + fixed;
+      g.ok = true;
+      return g;
+    }
+  }
+  g.ctas_per_sm = 1;
   return g;
 }
 
 struct PipeArgs {
-  int TX, TY, R, stages, chunk_rows;
+  int TX, TY, R, stages, chunk_rows, u_cap;
   uint32_t tile_bytes, stage_bytes;
   int rows_per_cta;
 };
@@ -88,7 +97,7 @@ struct PipeSmem {
   uint64_t* empty;
   float* rowpart;   // [chunk_rows][NWX]
   float* wsum;      // [64]
-  __half* u_s;      // [kPipeMaxRowsPerCta]
+  __half* u_s;      // [u_cap]
 };
 __device__ __forceinline__ PipeSmem carve_smem(unsigned char* raw, const PipeArgs& a, int NWX) {
   PipeSmem s;
@@ -151,8 +160,8 @@ __device__ __forceinline__ uint32_t h8_ge0_bits_fast(const H8& v) {
 // ---------------------------------------------------------------------------------------
 // pass 1: delta statistics (+ sign packing for BINARY)           grid (B, batch)
 // ---------------------------------------------------------------------------------------
-template <int MODE, int G>
-__global__ void __launch_bounds__(kPipeMaxThreads, 1) k_delta_stats_tma(const StatsParams p, const PipeArgs a) {
+template <int MODE, int G, int OCC>
+__global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_delta_stats_tma(const StatsParams p, const PipeArgs a) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
   const int ncompute = TX * TY;
@@ -348,12 +357,38 @@ __device__ __forceinline__ void load_vfrag(uint32_t (&vfrag)[G][4], const __half
   }
 }
 
+// One-sided transport: block until every origin whose payload this CTA consumes has published
+// its flag (counter >= our own put count for this slot).  Bounded spin: a dead peer must not
+// hang the GPU, so after ~2 s the error word is set and the kernel proceeds.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename P>
+__device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last) {
+  const uint32_t want = ld_acquire_sys(p.expected);
+  for (int t = t_first; t <= t_last; ++t) {
+    const uint32_t* f = p.wait_flag[t];
+    if (f == nullptr) continue;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(f) - want) < 0) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(p.error, 1u);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // apply: recon = base + dequant(codes, U, V)        grid (nCTA); recon may alias base
 // stage = [base tile | code tile]
 // ---------------------------------------------------------------------------------------
-template <int MODE, int G>
-__global__ void __launch_bounds__(kPipeMaxThreads, 1) k_apply_codes_tma(const ApplyParams p, const PipeArgs a,
+template <int MODE, int G, int OCC>
+__global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const ApplyParams p, const PipeArgs a,
                                                                         const TileSched ts) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
@@ -368,6 +403,10 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) k_apply_codes_tma(const Ap
   pipe_init(sm, a, ncompute);
   pdl_wait();
   pdl_launch_dependents();
+  if (p.expected != nullptr) {
+    if (tid == 0 && T0 < T1) wait_origins(p, T0 / ts.tiles_per_tensor, (T1 - 1) / ts.tiles_per_tensor);
+    __syncthreads();
+  }
 
   if (tid >= ncompute) {
     if (tid == ncompute) {
@@ -435,8 +474,8 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) k_apply_codes_tma(const Ap
 // INT2 encode (second pass): codes (+ optional new_base) from x, base and the final scales
 // stage = [x tile | base tile]
 // ---------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(kPipeMaxThreads, 1) k_int2_encode_tma(const Int2EncodeParams p, const PipeArgs a,
+template <int G, int OCC>
+__global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_int2_encode_tma(const Int2EncodeParams p, const PipeArgs a,
                                                                         const TileSched ts) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;

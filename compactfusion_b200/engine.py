@@ -12,11 +12,19 @@ way to drive the same kernels for a whole denoising step (SURVEY.md section 7 ha
   * every buffer is allocated once, so a whole step (all layers) can be captured in a CUDA
     graph and replayed with a single launch.
 
+  * transport: NCCL all-gather of the payloads (`transport="nccl"`, what the reference does,
+    main.py:409), or one-sided NVLink puts into peer-mapped receive slots with device-side
+    flags (`transport="p2p"`, csrc/cf_p2p.cu): no collective on the path, so the whole step,
+    exchange included, is ONE CUDA graph.  `transport="auto"` tries p2p and falls back.
+
 Results are the ones `compact_all_gather` produces (same kernels, same wire format); only
 the 1-ulp freedom of the mean-scale reductions applies (batched launches split rows over a
 different number of CTAs).
 """
 from __future__ import annotations
+
+import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -35,7 +43,7 @@ class PatchGatherEngine:
     attention (identical on all ranks) and are the bases of the next step.
     """
 
-    def __init__(self, layers: int, n_local: int, c: int, group=None, device=None):
+    def __init__(self, layers: int, n_local: int, c: int, group=None, device=None, transport: str = "nccl"):
         self.layers, self.n, self.c = layers, n_local, c
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -50,6 +58,82 @@ class PatchGatherEngine:
         self._ptr_cache = {}
         self.kernel_launches = 0  # launches of our kernels since the last reset
         nv.lib()  # fail loudly now if the extension is missing
+        assert transport in ("nccl", "p2p", "auto")
+        self.transport = "nccl"
+        self._p2p = {}
+        self._p2p_requested = transport
+        # (with a single layer a fast rank could overwrite a slot its peer is still reading: the
+        #  per-layer slots are only hazard-free when another layer's exchange separates two uses)
+        if transport in ("p2p", "auto") and self.world > 1 and layers >= 2:
+            self.transport = "p2p"  # regions are mapped lazily per codec (payload size differs)
+
+    def prepare(self, ctype) -> str:
+        """Set up the transport for `ctype` now (collective call); returns the transport in use."""
+        if self.transport == "p2p" and ctype in _CODEC:
+            self._p2p_region(ctype)
+        return self.transport
+
+    # -- one-sided transport setup -----------------------------------------------------------
+    def _p2p_region(self, ctype):
+        """Allocate this rank's receive region for `ctype`, exchange CUDA IPC handles and map every
+        peer's region.  Layout: [flags: layers x W u32 | slots: layers x W x (K payload | V payload)]."""
+        st = self._p2p.get(ctype)
+        if st is not None:
+            return st
+        W, L = self.world, self.layers
+        slot_bytes = 2 * self._numel(ctype) * 2
+        ok = slot_bytes % 16 == 0 and (self._numel(ctype) * 2) % 16 == 0
+        flags_bytes = (L * W * 4 + 255) // 256 * 256
+        total = flags_bytes + L * W * slot_bytes
+        lib = nv.lib()
+        base_ptr, handle, err = ctypes.c_void_p(), ctypes.create_string_buffer(64), None
+        if ok:
+            rc = lib.cf_ipc_alloc(total, ctypes.byref(base_ptr), handle)
+            if rc != 0:
+                ok, err = False, lib.cf_last_error().decode()
+        # every rank must take the same decision
+        gathered = [None] * W
+        dist.all_gather_object(gathered, (ok, handle.raw if ok else b"", os.getpid()), group=self.group)
+        all_ok = all(g[0] for g in gathered)
+        peers = [None] * W
+        if all_ok:
+            for r, (_, h, _pid) in enumerate(gathered):
+                if r == self.rank:
+                    peers[r] = base_ptr.value
+                    continue
+                pp = ctypes.c_void_p()
+                rc = lib.cf_ipc_open(h, ctypes.byref(pp))
+                if rc != 0:
+                    all_ok, err = False, lib.cf_last_error().decode()
+                    break
+                peers[r] = pp.value
+        flag = torch.tensor([1 if all_ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if self._p2p_requested == "p2p":
+                raise nv.NativeError(f"p2p transport unavailable on rank {self.rank}: {err or 'a peer failed'}")
+            self.transport = "nccl"
+            self._p2p[ctype] = False
+            return False
+        st = {
+            "base": base_ptr.value, "peers": peers, "flags_bytes": flags_bytes, "slot_bytes": slot_bytes,
+            "count": torch.zeros(L, dtype=torch.int32, device=self.device),     # puts issued per layer slot
+            "ticket": torch.zeros(1, dtype=torch.int32, device=self.device),
+            "error": torch.zeros(1, dtype=torch.int32, device=self.device),
+        }
+        self._p2p[ctype] = st
+        dist.barrier(group=self.group)
+        return st
+
+    def _slot(self, st, region_base, layer, origin):
+        return region_base + st["flags_bytes"] + (layer * self.world + origin) * st["slot_bytes"]
+
+    def _flag(self, st, region_base, layer, origin):
+        return region_base + (layer * self.world + origin) * 4
+
+    def p2p_error(self) -> bool:
+        """True if a device-side flag wait timed out (a peer never delivered its payload)."""
+        return any(bool(st["error"].item()) for st in self._p2p.values() if st)
 
     # -- buffers ---------------------------------------------------------------------------
     def _numel(self, ctype):
@@ -101,6 +185,33 @@ class PatchGatherEngine:
             self._ptr_cache[key] = args
         return args
 
+    def _decompress_args_p2p(self, layer, ctype, st):
+        key = ("dp", layer, ctype)
+        args = self._ptr_cache.get(key)
+        if args is None:
+            per_byte = 8 if ctype == T.BINARY else 4
+            code_bytes = self.n * (self.c // per_byte)
+            pn_bytes = self._numel(ctype) * 2
+            packed, us, vs, bases, flags = [], [], [], [], []
+            for r in range(self.world):
+                slot = self._slot(st, st["base"], layer, r)
+                for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
+                    p0 = slot + j * pn_bytes
+                    packed.append(p0)
+                    us.append(p0 + code_bytes)
+                    vs.append(p0 + code_bytes + 2 * self.n)
+                    bases.append(self._shard(glob, r).data_ptr())
+                    flags.append(self._flag(st, st["base"], layer, r))
+            chunks = []
+            for s0 in range(0, len(packed), nv.CF_MAX_BATCH):
+                e0 = min(len(packed), s0 + nv.CF_MAX_BATCH)
+                arr = lambda xs: (ctypes.c_void_p * (e0 - s0))(*xs[s0:e0])  # noqa: E731
+                b = arr(bases)
+                chunks.append((e0 - s0, arr(packed), arr(us), arr(vs), b, b, arr(flags)))
+            args = chunks
+            self._ptr_cache[key] = args
+        return args
+
     def _decompress_args(self, layer, ctype):
         key = ("d", layer, ctype)
         args = self._ptr_cache.get(key)
@@ -136,13 +247,42 @@ class PatchGatherEngine:
             passes &= ~nv.PASS_ENCODE  # no cache update on the sender: BINARY has no third kernel
         self.kernel_launches += bin(passes).count("1")
 
-    def gather(self, ctype):
+    def gather(self, ctype, layer: int = 0):
+        """Move this rank's [K payload | V payload] to every rank: NCCL all-gather, or one put
+        kernel writing all W receive slots (own included) over NVLink + flag publication."""
         send, recv = self._buffers(ctype)
-        if self.world > 1:
+        if self.world == 1:
+            return
+        st = self._p2p_region(ctype) if self.transport == "p2p" else None
+        if not st:
             dist.all_gather_into_tensor(recv.view(self.world, -1), send.view(-1), group=self.group)
+            return
+        key = ("put", layer, ctype)
+        args = self._ptr_cache.get(key)
+        if args is None:
+            W = self.world
+            dst = (ctypes.c_void_p * W)(*[self._slot(st, st["peers"][q], layer, self.rank) for q in range(W)])
+            flg = (ctypes.c_void_p * W)(*[self._flag(st, st["peers"][q], layer, self.rank) for q in range(W)])
+            args = (dst, flg, st["count"][layer:layer + 1].data_ptr())
+            self._ptr_cache[key] = args
+        dst, flg, count_ptr = args
+        rc = nv.lib().cf_p2p_put(send.data_ptr(), st["slot_bytes"], self.world, dst, flg, count_ptr,
+                                 st["ticket"].data_ptr(), nv.stream_ptr())
+        nv.check(rc, "cf_p2p_put")
+        self.kernel_launches += 1
 
     def decompress(self, layer, ctype):
         """All W origins x {K, V}: recon = base + dequant, in place in the global buffers."""
+        st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
+        if st:
+            expected = st["count"][layer:layer + 1].data_ptr()
+            for cnt, pk, us, vs, bases, recon, flags in self._decompress_args_p2p(layer, ctype, st):
+                rc = nv.lib().cf_sign_decompress_batched_wait(_CODEC[ctype], cnt, pk, us, vs, bases, recon, flags,
+                                                              expected, st["error"].data_ptr(), self.n, self.c,
+                                                              nv.stream_ptr())
+                nv.check(rc, "cf_sign_decompress_batched_wait")
+                self.kernel_launches += 1
+            return
         fn = nv.lib().cf_binary_decompress_batched if ctype == T.BINARY else nv.lib().cf_int2_decompress_batched
         for cnt, pk, us, vs, bases, recon in self._decompress_args(layer, ctype):
             rc = fn(cnt, pk, us, vs, bases, recon, self.n, self.c, nv.stream_ptr())
@@ -155,7 +295,7 @@ class PatchGatherEngine:
             return self.warmup(layer, k, v)
         assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
         self.compress(layer, k, v, ctype)
-        self.gather(ctype)
+        self.gather(ctype, layer)
         self.decompress(layer, ctype)
         return self.global_k[layer], self.global_v[layer]
 

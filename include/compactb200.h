@@ -41,6 +41,7 @@ extern "C" {
 
 #define CF_ABI_VERSION 1
 #define CF_MAX_BATCH 16
+#define CF_MAX_PEERS 16
 
 typedef void* cf_stream_t; /* cudaStream_t */
 
@@ -180,6 +181,32 @@ CF_API int cf_lowrank_project(const void* x, const void* base, const float* q0, 
  * residual add: recon = base + fp16(U V) (base may be NULL). */
 CF_API int cf_lowrank_reconstruct(const void* U, const void* V, const void* base, void* recon,
                            int64_t N, int64_t C, int rank, cf_stream_t stream);
+
+/* ---- one-sided NVLink transport of the payloads (replaces dist.all_gather of
+ * compact_all_gather, main.py:409, and the ring's batch_isend_irecv, ring.py:268-269) -----
+ * cf_ipc_alloc: cudaMalloc + zero a buffer and export its 64-byte CUDA IPC handle (HOST
+ * buffer `handle64`); cf_ipc_open maps a peer process's buffer (peer access is enabled
+ * lazily); cf_ipc_close / cf_ipc_free undo them.  These four calls synchronise the device.
+ * cf_p2p_put: copy `bytes` (multiple of 16) from the local payload `src` to `n_peers`
+ * destinations (device pointers, local or peer-mapped), then publish ++(*local_count) to every
+ * peer_flag[q] with release semantics.  local_count / local_ticket are local device u32 words
+ * (ticket must start at 0).  Enqueues one kernel; CUDA-graph capturable. */
+CF_API int cf_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64);
+CF_API int cf_ipc_open(const void* handle64, void** peer_ptr);
+CF_API int cf_ipc_close(void* peer_ptr);
+CF_API int cf_ipc_free(void* dev_ptr);
+CF_API int cf_p2p_put(const void* src, size_t bytes, int n_peers, void* const* peer_dst,
+               void* const* peer_flag, void* local_count, void* local_ticket, cf_stream_t stream);
+/* cf_{binary,int2}_decompress_batched that first waits, on the device, until
+ * *wait_flag[t] >= *expected for every tensor t with a non-null flag (the counters cf_p2p_put
+ * publishes; `expected` is normally the caller's own local_count of the same slot).  A wait
+ * that exceeds ~2 s sets *error_word = 1 instead of hanging the GPU.  Requires the pipelined
+ * kernel: 16-byte aligned base/codes, C % 128 == 0 (BINARY) or C % 64 == 0 (INT2). */
+CF_API int cf_sign_decompress_batched_wait(int codec, int batch, const void* const* packed,
+                                    const void* const* scale_u, const void* const* scale_v,
+                                    const void* const* base, void* const* recon,
+                                    const void* const* wait_flag, const void* expected,
+                                    void* error_word, int64_t N, int64_t C, cf_stream_t stream);
 
 /* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside the call) ---------
  * x_host/base_host/recon_host are HOST (ideally pinned) buffers; payload_host receives /

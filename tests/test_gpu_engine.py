@@ -159,6 +159,9 @@ for codec in (T.BINARY, T.INT2):
                            ef=True, fastpath=True)
     cf.compact_init(cfg)
     eng = PatchGatherEngine(layers, n, c, device=dev)
+    # one-sided NVLink transport (cf_p2p.cu): must reproduce the NCCL engine bit for bit
+    eng_p2p = PatchGatherEngine(layers, n, c, device=dev, transport="p2p")
+    assert eng_p2p.prepare(codec) == "p2p"
     for t in range(steps):
         ct = cfg.compress_func(0, t)
         for l in range(layers):
@@ -167,6 +170,8 @@ for codec in (T.BINARY, T.INT2):
             k_list = cf.compact_all_gather(f"{l}-k", k, ct)
             v_list = cf.compact_all_gather(f"{l}-v", v, ct)
             gk, gv = eng.exchange(l, k, v, ct)
+            pk, pv = eng_p2p.exchange(l, k, v, ct)
+            assert torch.equal(pk, gk) and torch.equal(pv, gv), ("p2p != nccl engine", codec, t, l)
             for r in range(world):
                 # every rank holds the same reconstruction of every origin (EF invariant) ...
                 ref = k_list[r].reshape(n, c)
@@ -183,6 +188,21 @@ for codec in (T.BINARY, T.INT2):
             eg = [torch.empty_like(gk) for _ in range(world)]
             dist.all_gather(eg, gk)
             assert all(torch.equal(b, eg[0]) for b in eg), ("engine", codec, t, l)
+    assert not eng_p2p.p2p_error(), "a device-side flag wait timed out"
+    # the p2p step is ONE CUDA graph (no collective inside): capture, replay, compare with eager
+    ks = [shard(steps, l, 0, rank).to(dev) for l in range(layers)]
+    vs = [shard(steps, l, 1, rank).to(dev) for l in range(layers)]
+    snap = [eng_p2p.global_k[l].clone() for l in range(layers)]
+    g = eng_p2p.capture_step(ks, vs, codec, warmup_iters=0)
+    for l in range(layers):
+        eng_p2p.global_k[l].copy_(snap[l])  # capture does not execute: caches are still the snapshot
+    g.replay()
+    torch.cuda.synchronize()
+    graph_k = [eng_p2p.global_k[l].clone() for l in range(layers)]
+    for l in range(layers):
+        gk, _ = eng.exchange(l, ks[l], vs[l], codec)
+        assert torch.equal(graph_k[l], gk), ("p2p graph replay != nccl eager", codec, l)
+    assert not eng_p2p.p2p_error()
     cfg = cf.CompactConfig(enabled=True, compress_func=lambda l, s: codec if s >= 1 else T.WARMUP, comp_rank=-1,
                            residual=1, ef=True, fastpath=True, check_consist=True)
     cf.compact_init(cfg)
