@@ -138,20 +138,36 @@ __device__ __forceinline__ void finalize_column(__half mn, __half mx, int c, __h
   }
 }
 
+// grid ceil(C/32), block 256 = 32 columns x 8 partial lanes: every thread folds ceil(B/8) partials with
+// independent loads (the old one-thread-per-column loop was a chain of B dependent L2 round trips)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_minmax_finalize(const __half* __restrict__ pmin,
                                                          const __half* __restrict__ pmax, int B, int C,
                                                          __half* __restrict__ scale_out,
                                                          void* __restrict__ second_out,
                                                          __half* __restrict__ min_ws) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  __half mn = pmin[c], mx = pmax[c];
-  for (int b = 1; b < B; ++b) {
-    mn = __hmin(mn, pmin[static_cast<size_t>(b) * C + c]);
-    mx = __hmax(mx, pmax[static_cast<size_t>(b) * C + c]);
+  __shared__ __half smn[8][33], smx[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  __half mn = __ushort_as_half(0x7C00), mx = __ushort_as_half(0xFC00);
+  if (c < C) {
+#pragma unroll 4
+    for (int b = py; b < B; b += 8) {
+      mn = __hmin(mn, pmin[static_cast<size_t>(b) * C + c]);
+      mx = __hmax(mx, pmax[static_cast<size_t>(b) * C + c]);
+    }
   }
-  finalize_column<MODE>(mn, mx, c, scale_out, second_out, min_ws);
+  smn[py][cx] = mn;
+  smx[py][cx] = mx;
+  __syncthreads();
+  if (py == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      mn = __hmin(mn, smn[k][cx]);
+      mx = __hmax(mx, smx[k][cx]);
+    }
+    finalize_column<MODE>(mn, mx, c, scale_out, second_out, min_ws);
+  }
 }
 
 // ---- generic path for C % 8 != 0 (tall-skinny low-rank factors, LOW_RANK_Q: slowpath.py:69-70) ----
@@ -505,7 +521,7 @@ static int minmax_compress(const void* x, const void* base, void* new_base, void
   }
 #undef CF_MM_STATS
   CF_CHECK_LAUNCH();
-  k_minmax_finalize<MODE><<<(c + 255) / 256, 256, 0, st>>>(pmin, pmax, pl.B, c, static_cast<__half*>(scale), second, min_ws);
+  k_minmax_finalize<MODE><<<(c + 31) / 32, 256, 0, st>>>(pmin, pmax, pl.B, c, static_cast<__half*>(scale), second, min_ws);
   CF_CHECK_LAUNCH();
   if (MODE == MODE_INT4) {
     dim3 grid(grid_rows(pl.geom, N / 2));
