@@ -221,7 +221,8 @@ def run_reference(args, world, rank):
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": args.layers, "seq": SEQ,
-                   "channels": CH, "world": world},
+                   "channels": CH, "world": world, "shard_rows": SEQ // world, "launch_mode": "cpu (no GPU work)",
+                   "transport": "in-process (all ranks' work on this host)", "l2": "n/a"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -379,6 +380,14 @@ def main():
     if args.codec == "int2":
         time_kernel("k_int2_encode_tma", lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
                     2 * (4 * e_tensor + e_tensor // 4 + 2 * (n_local + CH)))
+    if transport == "p2p":
+        # one-sided exchange: this rank's [K payload | V payload] stored into all W receive slots; W-1 of them
+        # cross NVLink (measured peer-copy peak 770 GB/s per direction, B200_PROFILING.md)
+        slot_bytes = 2 * (e_tensor // per_byte + 2 * (n_local + CH))
+        time_kernel("k_p2p_put", lambda l: eng.gather(ctype, l), (world + 1) * slot_bytes)
+        kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * slot_bytes
+        kernels[-1]["nvlink_gbs"] = (world - 1) * slot_bytes / kernels[-1]["avg_launch_us"] / 1e3
+        kernels[-1]["nvlink_frac_of_770"] = kernels[-1]["nvlink_gbs"] / 770.0
     # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
     n_launch_per_call = (2 * world + 15) // 16
     time_kernel(apply_name, lambda l: eng.decompress(l, ctype),
@@ -476,6 +485,7 @@ def main():
                        "transport": transport,
                        "l2": "inputs larger than L2 (each step streams > 6 GB of distinct K/V + cache)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+            "p2p_wait_timeouts": bool(eng.p2p_error()),
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -11,7 +11,10 @@
 //
 // All intermediates are fp32 row-major with leading dimension RP = round_up(r, 8); padding
 // columns are kept at zero.
+#include <stdlib.h>
+
 #include "cf_common.cuh"
+#include "cf_lowrank_mma.cuh"
 
 namespace cf {
 
@@ -359,9 +362,12 @@ static LrPlan make_lr_plan(int64_t N, int64_t C, int r) {
   p.total = off;
   return p;
 }
+struct LrMmaPlan;
+static size_t lr_mma_total(int64_t N, int64_t C, int r);
 size_t lowrank_workspace_bytes(int64_t N, int64_t C, int rank) {
   if (rank < 1 || rank > kMaxRank) return 256;
-  return make_lr_plan(N, C, rank).total;
+  const size_t a = make_lr_plan(N, C, rank).total, b = (C % 8 == 0) ? lr_mma_total(N, C, rank) : 0;
+  return a > b ? a : b;
 }
 
 template <int RP>
@@ -390,6 +396,138 @@ static int orthonormalise(float* X, int M, int RP, int r, double* gpart, float* 
   return CF_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// tensor-core path (cf_lowrank_mma.cuh): C % 8 == 0 and 16-byte aligned operands
+// ---------------------------------------------------------------------------------------
+struct LrMmaPlan {
+  int RP;
+  int aq_splits, aq_kper;    // Y = A Q:   M = N, K = C
+  int aty_splits, aty_kper;  // Z = A^T Y: M = C, K = N
+  int gram_ctas_c, gram_rows_c, gram_ctas_n, gram_rows_n;
+  size_t q2_off, y2_off, xsum_off, part_off, gpart_off, rinv_off, ticket_off, total;
+};
+static void lr_split_cfg(int64_t M, int64_t K, int* splits, int* kper) {
+  const int64_t m_tiles = (M + kLrBM - 1) / kLrBM;
+  int64_t s = (static_cast<int64_t>(sm_count()) + m_tiles / 2) / m_tiles;  // ~one CTA per SM, one wave
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  int64_t kp = ((K + s - 1) / s + kLrBK - 1) / kLrBK * kLrBK;
+  *kper = static_cast<int>(kp);
+  *splits = static_cast<int>((K + kp - 1) / kp);
+}
+static void lr_gram_cfg(int64_t M, int r, int* ctas, int* rows) {
+  (void)r;
+  int64_t parts = 16;  // few partials: the CTA that draws the last ticket adds them up alone
+  int64_t rp = ((M + parts - 1) / parts + 31) / 32 * 32;
+  *rows = static_cast<int>(rp);
+  *ctas = static_cast<int>((M + rp - 1) / rp);
+}
+static LrMmaPlan make_lr_mma_plan(int64_t N, int64_t C, int r) {
+  LrMmaPlan p;
+  p.RP = rp_of(r);
+  lr_split_cfg(N, C, &p.aq_splits, &p.aq_kper);
+  lr_split_cfg(C, N, &p.aty_splits, &p.aty_kper);
+  lr_gram_cfg(C, r, &p.gram_ctas_c, &p.gram_rows_c);
+  lr_gram_cfg(N, r, &p.gram_ctas_n, &p.gram_rows_n);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return o; };
+  const size_t maxm = static_cast<size_t>(N > C ? N : C);
+  p.q2_off = take(static_cast<size_t>(C) * p.RP * 8);
+  p.y2_off = take(static_cast<size_t>(N) * p.RP * 8);
+  p.xsum_off = take(maxm * p.RP * 4);
+  const size_t part_aq = static_cast<size_t>(p.aq_splits) * N * p.RP * 4;
+  const size_t part_aty = static_cast<size_t>(p.aty_splits) * C * p.RP * 4;
+  p.part_off = take(part_aq > part_aty ? part_aq : part_aty);
+  p.gpart_off = take(static_cast<size_t>(16) * r * r * 8);
+  p.rinv_off = take(static_cast<size_t>(p.RP) * p.RP * 4 + static_cast<size_t>(p.RP) * 4);
+  p.ticket_off = take(256);
+  p.total = off;
+  return p;
+}
+
+template <int RP>
+static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, __half* U, __half* V, float* q_out,
+                          int n, int c, int r, int iters, char* ws, const LrMmaPlan& p, cudaStream_t st) {
+  float2* Q2 = reinterpret_cast<float2*>(ws + p.q2_off);
+  float2* Y2 = reinterpret_cast<float2*>(ws + p.y2_off);
+  float* Xsum = reinterpret_cast<float*>(ws + p.xsum_off);
+  float* part = reinterpret_cast<float*>(ws + p.part_off);
+  double* gpart = reinterpret_cast<double*>(ws + p.gpart_off);
+  float* rfac = reinterpret_cast<float*>(ws + p.rinv_off);
+  float* rdinv = rfac + RP * RP;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws + p.ticket_off);
+  const int small_grid = 2 * sm_count();
+  const size_t smem_n = lr_gemm_smem<RP, false>(), smem_t = lr_gemm_smem<RP, true>();
+  CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_n)));
+  CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t)));
+  CF_CHECK_CUDA(cudaMemsetAsync(ticket, 0, 256, st));
+  k_lr_pad_split<<<small_grid, 256, 0, st>>>(q0, Q2, c, r, RP);
+  CF_CHECK_LAUNCH();
+
+  auto gemm_AQ = [&]() {  // part[s] (N, RP) = A Q
+    dim3 grid((n + kLrBM - 1) / kLrBM, p.aq_splits);
+    k_lr_gemm<RP, false><<<grid, kLrThreads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
+  };
+  auto gemm_AtY = [&]() {  // part[s] (C, RP) = A^T Y
+    dim3 grid((c + kLrBM - 1) / kLrBM, p.aty_splits);
+    k_lr_gemm<RP, true><<<grid, kLrThreads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
+  };
+  // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies)
+  auto orth = [&](int S, int M, int ctas, int rows, float2* out2, __half* out16, float* out32c) -> int {
+    // the S split-K partials are added by a wide kernel (all SMs); the 16 Gram CTAs then read one copy
+    k_lr_sum_split<<<small_grid, 256, 0, st>>>(part, S, static_cast<size_t>(M) * RP, nullptr, Xsum,
+                                               static_cast<size_t>(M) * RP);
+    CF_CHECK_LAUNCH();
+    GramParams g{};
+    g.xpart = Xsum; g.S = 1; g.part_stride = static_cast<size_t>(M) * RP; g.X = Xsum;
+    g.M = M; g.r = r; g.rows_per_cta = rows; g.gpart = gpart; g.ticket = ticket; g.r_out = rfac; g.rdinv_out = rdinv;
+    k_lr_gram_chol<RP><<<ctas, 256, 0, st>>>(g);
+    CF_CHECK_LAUNCH();
+    k_lr_solve_out<RP><<<(M + 127) / 128, 128, 0, st>>>(Xsum, rfac, rdinv, M, r, nullptr, nullptr, nullptr);
+    CF_CHECK_LAUNCH();
+    g.xpart = Xsum; g.S = 1;
+    k_lr_gram_chol<RP><<<ctas, 256, 0, st>>>(g);
+    CF_CHECK_LAUNCH();
+    k_lr_solve_out<RP><<<(M + 127) / 128, 128, 0, st>>>(Xsum, rfac, rdinv, M, r, out2, out16, out32c);
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+  };
+
+  bool q_written = false;
+  for (int it = 0; it < iters; ++it) {
+    gemm_AQ();
+    CF_CHECK_LAUNCH();
+    k_lr_sum_split<<<small_grid, 256, 0, st>>>(part, p.aq_splits, static_cast<size_t>(n) * RP, Y2, nullptr,
+                                               static_cast<size_t>(n) * RP);
+    CF_CHECK_LAUNCH();
+    gemm_AtY();
+    CF_CHECK_LAUNCH();
+    const bool last = it == iters - 1;
+    if (int rc = orth(p.aty_splits, c, p.gram_ctas_c, p.gram_rows_c, Q2, nullptr, (last && q_out) ? q_out : nullptr))
+      return rc;
+    q_written = q_written || (last && q_out);
+  }
+  if (q_out != nullptr && !q_written)
+    CF_CHECK_CUDA(cudaMemcpyAsync(q_out, q0, static_cast<size_t>(c) * r * 4, cudaMemcpyDeviceToDevice, st));
+  gemm_AQ();  // U_temp = A Q
+  CF_CHECK_LAUNCH();
+  if (int rc = orth(p.aq_splits, n, p.gram_ctas_n, p.gram_rows_n, Y2, U, nullptr)) return rc;  // U = orth(A Q)
+  gemm_AtY();  // V^T = A^T U
+  CF_CHECK_LAUNCH();
+  k_lr_store_v_sum<<<small_grid, 256, 0, st>>>(part, p.aty_splits, static_cast<size_t>(c) * RP, V, c, RP, r);
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
+static size_t lr_mma_total(int64_t N, int64_t C, int r) { return make_lr_mma_plan(N, C, r).total; }
+
+static bool lr_mma_eligible(const void* x, const void* base, int64_t N, int64_t C) {
+  const char* e = getenv("CF_LEGACY_KERNELS");
+  if (e && e[0] == '1') return false;
+  return C % 8 == 0 && C >= 8 && N >= 1 && aligned16(x) && (!base || aligned16(base));
+}
+
 }  // namespace cf
 
 extern "C" {
@@ -403,9 +541,27 @@ int cf_lowrank_project(const void* x, const void* base, const float* q0, void* U
   CF_CHECK_ARG(iters >= 0 && iters <= 1000, "iters out of range");
   CF_CHECK_ARG(N >= 1 && C >= 1 && N < (int64_t(1) << 31) && C < (int64_t(1) << 31), "bad shape");
   CF_CHECK_ARG(rank <= N && rank <= C, "rank larger than the matrix");
-  const LrPlan p = make_lr_plan(N, C, rank);
   CF_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                "workspace must be non-null and 256-byte aligned");
+  if (lr_mma_eligible(x, base, N, C)) {
+    const LrMmaPlan mp = make_lr_mma_plan(N, C, rank);
+    if (mp.total > workspace_bytes) {
+      set_error("workspace too small: need %zu bytes, got %zu", mp.total, workspace_bytes);
+      return CF_ERR_WORKSPACE;
+    }
+    const __half* xh2 = static_cast<const __half*>(x);
+    const __half* bh2 = static_cast<const __half*>(base);
+    char* ws2 = static_cast<char*>(workspace);
+    cudaStream_t st2 = static_cast<cudaStream_t>(stream);
+    const int n2 = static_cast<int>(N), c2 = static_cast<int>(C);
+    switch (mp.RP) {
+      case 8: return lr_mma_project<8>(xh2, bh2, q0, static_cast<__half*>(U), static_cast<__half*>(V), q_out, n2, c2, rank, iters, ws2, mp, st2);
+      case 16: return lr_mma_project<16>(xh2, bh2, q0, static_cast<__half*>(U), static_cast<__half*>(V), q_out, n2, c2, rank, iters, ws2, mp, st2);
+      case 32: return lr_mma_project<32>(xh2, bh2, q0, static_cast<__half*>(U), static_cast<__half*>(V), q_out, n2, c2, rank, iters, ws2, mp, st2);
+      default: return lr_mma_project<64>(xh2, bh2, q0, static_cast<__half*>(U), static_cast<__half*>(V), q_out, n2, c2, rank, iters, ws2, mp, st2);
+    }
+  }
+  const LrPlan p = make_lr_plan(N, C, rank);
   if (p.total > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", p.total, workspace_bytes);
     return CF_ERR_WORKSPACE;
@@ -471,6 +627,25 @@ int cf_lowrank_reconstruct(const void* U, const void* V, const void* base, void*
   CF_CHECK_ARG(aligned16(V) && aligned16(recon) && (!base || aligned16(base)) && aligned2(U),
                "V/base/recon must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const char* e = getenv("CF_LEGACY_KERNELS");
+    if (!(e && e[0] == '1')) {  // tensor-core path
+      dim3 mgrid(static_cast<unsigned>((C + 255) / 256), static_cast<unsigned>((N + 63) / 64));
+      const __half* u = static_cast<const __half*>(U);
+      const __half* v = static_cast<const __half*>(V);
+      const __half* b = static_cast<const __half*>(base);
+      __half* o = static_cast<__half*>(recon);
+      const int n = static_cast<int>(N), c = static_cast<int>(C);
+      switch ((rank + 15) / 16) {
+        case 1: k_lr_reconstruct_mma<1><<<mgrid, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+        case 2: k_lr_reconstruct_mma<2><<<mgrid, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+        case 3: k_lr_reconstruct_mma<3><<<mgrid, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+        default: k_lr_reconstruct_mma<4><<<mgrid, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+      }
+      CF_CHECK_LAUNCH();
+      return CF_OK;
+    }
+  }
   dim3 grid(static_cast<unsigned>((C + 255) / 256), static_cast<unsigned>((N + 31) / 32));
   const size_t smem = static_cast<size_t>(rank) * 256 * 2 + 32 * static_cast<size_t>(rank) * 2;
   k_lr_reconstruct<<<grid, 256, smem, st>>>(static_cast<const __half*>(U), static_cast<const __half*>(V),

@@ -9,10 +9,10 @@
 // on the flags of the origins it consumes.  No collective, no host involvement: the whole
 // step (compress -> put -> decompress, all layers) is one CUDA graph.
 //
-// Memory model: every copying thread fences (system scope) after its stores, the CTA
-// synchronises, thread 0 fences again (cumulativity over the CTA's stores) and takes a ticket;
-// the CTA that draws the last ticket publishes the flags with a release store.  Receivers
-// poll with acquire loads at system scope.
+// Memory model: the CTA synchronises after its stores, thread 0 issues a system-scope fence
+// (cumulative over the CTA's stores, which the barrier ordered before it) and takes a ticket;
+// the CTA that draws the last ticket fences again and publishes the flags with release
+// stores.  Receivers poll with relaxed system-scope loads and then issue one acquire fence.
 #include <stdlib.h>
 #include <string.h>
 
@@ -51,9 +51,9 @@ __global__ void __launch_bounds__(256) k_p2p_put(const PutParams p) {
     dst[i + 3 * stride] = d;
   }
   for (; i < p.n16; i += stride) dst[i] = p.src[i];
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // cumulative over the whole CTA's stores (ordered before this fence by the barrier)
     __threadfence_system();
     const unsigned total = gridDim.x * gridDim.y;
     const unsigned ticket = atomicAdd(p.done, 1u);

@@ -360,26 +360,31 @@ __device__ __forceinline__ void load_vfrag(uint32_t (&vfrag)[G][4], const __half
 // One-sided transport: block until every origin whose payload this CTA consumes has published
 // its flag (counter >= our own put count for this slot).  Bounded spin: a dead peer must not
 // hang the GPU, so after ~2 s the error word is set and the kernel proceeds.
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Called by warp 0 of the CTA: lane i polls the flag of tensor t_first + i with relaxed loads (all
+// origins in parallel: one L2 round trip per poll, not one per origin), then a single acquire fence
+// at system scope orders the payload reads behind the observed flags.
 template <typename P>
-__device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last) {
-  const uint32_t want = ld_acquire_sys(p.expected);
-  for (int t = t_first; t <= t_last; ++t) {
+__device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last, int lane) {
+  const uint32_t want = ld_relaxed_sys(p.expected);
+  for (int t = t_first + lane; t <= t_last; t += 32) {
     const uint32_t* f = p.wait_flag[t];
     if (f == nullptr) continue;
     const long long t0 = clock64();
-    while (static_cast<int32_t>(ld_acquire_sys(f) - want) < 0) {
+    while (static_cast<int32_t>(ld_relaxed_sys(f) - want) < 0) {
       if (clock64() - t0 > 4000000000LL) {
         atomicExch(p.error, 1u);
         break;
       }
-      __nanosleep(64);
+      __nanosleep(32);
     }
   }
+  __syncwarp();
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const 
   pdl_wait();
   pdl_launch_dependents();
   if (p.expected != nullptr) {
-    if (tid == 0 && T0 < T1) wait_origins(p, T0 / ts.tiles_per_tensor, (T1 - 1) / ts.tiles_per_tensor);
+    if (tid < 32 && T0 < T1) wait_origins(p, T0 / ts.tiles_per_tensor, (T1 - 1) / ts.tiles_per_tensor, tid);
     __syncthreads();
   }
 
