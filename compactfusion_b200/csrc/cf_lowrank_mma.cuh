@@ -226,6 +226,21 @@ constexpr int kLrMaxRank = 64;
 // update uses the unscaled pivot row, G[i][j] -= G[k][i] G[k][j] / G[k][k], so row k never has to be scaled
 // in place first; thread (ti, tj) of a 16 x 16 grid owns the entries (ti + 16a, tj + 16b).
 // On return G[k][j] (j >= k) holds the unscaled pivot rows: R[k][j] = G[k][j] * piv[k], piv[k] = G[k][k]^-1/2.
+// 1/d and d^-1/2 in fp64 from fp32 seeds + two Newton steps each (the library double division / rsqrt are
+// ~40-instruction dependent chains that sat on the critical path of every elimination step)
+__device__ __forceinline__ double fast_rcp(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return 1.0 / d;  // outside the fp32 seed's comfortable range
+  double y = static_cast<double>(__frcp_rn(static_cast<float>(d)));
+  y = y * (2.0 - d * y);
+  return y * (2.0 - d * y);
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+  double y = static_cast<double>(rsqrtf(static_cast<float>(d)));
+  y = y * (1.5 - 0.5 * d * y * y);
+  return y * (1.5 - 0.5 * d * y * y);
+}
+
 __device__ void cholesky_upper_256(double (*G)[kLrMaxRank + 1], double* piv, int r, int t) {
   const int ti = t >> 4, tj = t & 15;
   double maxdiag = 0.0;
@@ -235,8 +250,9 @@ __device__ void cholesky_upper_256(double (*G)[kLrMaxRank + 1], double* piv, int
   for (int k = 0; k < r; ++k) {
     double d = G[k][k];
     if (!(d > floor_piv)) d = floor_piv;  // rank-deficient input: keep things finite
-    const double inv_d = 1.0 / d;
-    if (t == 0) piv[k] = rsqrt(d);
+    // (d is within fp32 range: a squared column norm of fp16-derived data)
+    const double inv_d = fast_rcp(d);
+    if (t == 0) piv[k] = fast_rsqrt(d);
 #pragma unroll
     for (int a = 0; a < kLrMaxRank / 16; ++a) {
       const int i = ti + 16 * a;
