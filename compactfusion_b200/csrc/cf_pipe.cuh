@@ -93,6 +93,23 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
   return r;
 }
 
+// same from a precomputed 32-bit shared-window address (no generic -> shared conversion per load)
+__device__ __forceinline__ uint4 lds128a(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds8a(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds16a(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace cf

@@ -197,39 +197,78 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_delta_stats_tma(const 
     for (int i = 0; i < 4; ++i) colacc[j][i] = make_float2(0.f, 0.f);
   float tokacc = 0.f;
   const float c_f = static_cast<float>(C);
+  // shared-window addresses: stage base + this thread's first 16-byte column group
+  const uint32_t thr_a = smem_addr(sm.stage0) + static_cast<uint32_t>(tx) * 16u;
+  const uint32_t jstride = static_cast<uint32_t>(TX) * 16u;
+  bool act[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) act[j] = tx + j * TX < groups;
+  const bool all_act = act[G - 1];  // groups are assigned in increasing j: the last one decides
+  constexpr int kFly = (G == 1) ? 4 : (OCC == 2 ? 1 : 2);  // rows whose loads are issued before the first use
 
   int it = 0, chunk_base = r_begin;
   for (int r0 = r_begin; r0 < r_end; r0 += a.R, ++it) {
     const int st = it % a.stages, k = it / a.stages;
     mbar_wait(&sm.full[st], k & 1);
-    const unsigned char* xs = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
-    const unsigned char* bs = xs + a.tile_bytes;
+    const uint32_t xs_a = thr_a + static_cast<uint32_t>(st) * a.stage_bytes;
+    const uint32_t bs_off = a.tile_bytes;
     const int rows = min(a.R, r_end - r0);
+    uint8_t* pk_tile = packed + static_cast<size_t>(r0) * groups + tx;
     for (int q = ty; 4 * q < rows; q += TY) {
       float rs[4];
+      const uint32_t qa = xs_a + static_cast<uint32_t>(4 * q) * row_bytes;
+      uint8_t* pk = pk_tile + static_cast<size_t>(4 * q) * groups;
+      if (4 * q + 4 <= rows && all_act) {  // full quad: branch-free, loads of kFly rows in flight
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int rl = 4 * q + rr;
-        float2 acc2 = make_float2(0.f, 0.f);
-        if (rl < rows) {  // warp-uniform
+        for (int h = 0; h < 4; h += kFly) {
+          H8 d[kFly][G];
 #pragma unroll
-          for (int j = 0; j < G; ++j) {
-            const int g = tx + j * TX;
-            if (g < groups) {
-              const uint32_t o = static_cast<uint32_t>(rl) * row_bytes + static_cast<uint32_t>(g) * 16u;
-              const H8 d = h8_sub(as_h8(lds128(xs + o)), as_h8(lds128(bs + o)));
+          for (int rr = 0; rr < kFly; ++rr)
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+              const uint32_t o = qa + static_cast<uint32_t>(h + rr) * row_bytes + static_cast<uint32_t>(j) * jstride;
+              d[rr][j] = h8_sub(as_h8(lds128a(o)), as_h8(lds128a(o + bs_off)));
+            }
+#pragma unroll
+          for (int rr = 0; rr < kFly; ++rr) {
+            float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
               if (MODE == MODE_BINARY)
-                packed[static_cast<size_t>(r0 + rl) * groups + g] = static_cast<uint8_t>(h8_ge0_bits_fast(d));
+                pk[(h + rr) * groups + j * TX] = static_cast<uint8_t>(h8_ge0_bits_fast(d[rr][j]));
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(__habs2(u2h2(d.w[i])));
+                const float2 f = __half22float2(__habs2(u2h2(d[rr][j].w[i])));
                 colacc[j][i] = __fadd2_rn(colacc[j][i], f);
                 acc2 = __fadd2_rn(acc2, f);
               }
             }
+            rs[h + rr] = acc2.x + acc2.y;
           }
         }
-        rs[rr] = acc2.x + acc2.y;
+      } else {  // ragged tail of the tensor
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int rl = 4 * q + rr;
+          float2 acc2 = make_float2(0.f, 0.f);
+          if (rl < rows) {  // warp-uniform
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+              if (act[j]) {
+                const uint32_t o = qa + static_cast<uint32_t>(rr) * row_bytes + static_cast<uint32_t>(j) * jstride;
+                const H8 d = h8_sub(as_h8(lds128a(o)), as_h8(lds128a(o + bs_off)));
+                if (MODE == MODE_BINARY) pk[rr * groups + j * TX] = static_cast<uint8_t>(h8_ge0_bits_fast(d));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __half22float2(__habs2(u2h2(d.w[i])));
+                  colacc[j][i] = __fadd2_rn(colacc[j][i], f);
+                  acc2 = __fadd2_rn(acc2, f);
+                }
+              }
+            }
+          }
+          rs[rr] = acc2.x + acc2.y;
+        }
       }
       // transposed warp reduction of the 4 row sums: 6 shuffles instead of 20 (fixed order)
       const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
