@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libcompactb200.so")
 CF_MAX_BATCH = 16
 CODEC_BINARY, CODEC_INT2, CODEC_INT4, CODEC_INT8, CODEC_TOPK, CODEC_LOWRANK = 1, 2, 4, 8, 16, 32
 PASS_STATS, PASS_FINALIZE, PASS_ENCODE, PASS_ALL = 1, 2, 4, 7
+FLAG_INPUTS_STABLE = 0x100  # include/compactb200.h: enum cf_flag
 
 # every symbol include/compactb200.h declares: (restype, argtypes)
 _VPP = POINTER(c_void_p)

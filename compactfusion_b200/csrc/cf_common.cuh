@@ -79,6 +79,16 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                : "memory");
 }
 
+// same with an L2 eviction-priority policy (createpolicy); policy == 0: plain streaming store
+__device__ __forceinline__ void stg_stream_pol(void* p, const uint4& v, uint64_t policy) {
+  if (policy != 0)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                 : "memory");
+  else
+    stg_stream(p, v);
+}
+
 __device__ __forceinline__ __half2 u2h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t h22u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 

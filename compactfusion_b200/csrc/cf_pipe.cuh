@@ -64,6 +64,14 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
       "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
       : "memory");
 }
+// hinted copy when `policy` != 0, plain copy otherwise
+__device__ __forceinline__ void bulk_g2s_pol(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                             uint64_t policy) {
+  if (policy != 0)
+    bulk_g2s_hint(dst_smem, src_gmem, bytes, bar, policy);
+  else
+    bulk_g2s(dst_smem, src_gmem, bytes, bar);
+}
 __device__ __forceinline__ uint64_t make_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

@@ -258,35 +258,36 @@ __device__ __forceinline__ uint32_t load_v_pair(const __half* v, int c) {
          (static_cast<uint32_t>(__half_as_ushort(v[c + 1])) << 16);
 }
 
-// BINARY: 8 elements from one code byte
+// BINARY: 8 elements from one code byte (zero-extended)
 __device__ __forceinline__ H8 binary_apply8(const H8& b, uint32_t bits, __half2 u2, const uint32_t* vfrag) {
   H8 r;
+  const uint32_t nb = bits ^ 0xFFu;  // 1 where the code bit is 0: (2 bit - 1) * scale flips the sign there (exact)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t scale = h22u(__hmul2_rn(u2, u2h2(vfrag[i])));  // fp16(U[n] V[c]), fastpath.py:109
-    // (2 bit - 1) * scale: flip the sign where the bit is 0 (exact)
-    const uint32_t b0 = (bits >> (2 * i)) & 1u, b1 = (bits >> (2 * i + 1)) & 1u;
-    const uint32_t flip = ((b0 ^ 1u) << 15) | ((b1 ^ 1u) << 31);
+    // one multiply moves bit 2i to position 15 and bit 2i+1 to position 31: the two partial products
+    // occupy disjoint bit ranges (no carries), everything else is masked off
+    const uint32_t flip = (nb * ((1u << (15 - 2 * i)) + (1u << (30 - 2 * i)))) & 0x80008000u;
     r.w[i] = h22u(__hadd2_rn(u2h2(b.w[i]), u2h2(scale ^ flip)));  // fastpath.py:116 / :363
   }
   return r;
 }
 
-// INT2: 8 elements from two code bytes (element e at bits 2e..2e+1 of the 16-bit word)
+// INT2: 8 elements from two code bytes (element e at bits 2e..2e+1 of the zero-extended 16-bit word).
+// level = thr * f with f in {-0.5, -2, +0.5, +2} picked per element by a byte permute: the same fp16
+// values as the reference's +-(0.5 thr) / +-(2 thr) (fastpath.py:565-572; scaling by a power of two and
+// negation commute with the rounding).
 __device__ __forceinline__ H8 int2_apply8(const H8& b, uint32_t codes, __half2 u2, const uint32_t* vfrag) {
   H8 r;
-  const __half2 half2_05 = __float2half2_rn(0.5f), half2_2 = __float2half2_rn(2.0f);
+  const uint32_t lut = 0x4038C0B8u;  // high bytes of fp16 -0.5, -2, +0.5, +2 indexed by the 2-bit code
+  const uint32_t ca = codes << 4, cb = codes << 10;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const __half2 thr = __hmul2_rn(u2h2(vfrag[i]), u2);  // fp16(chan tok), fastpath.py:714
-    const uint32_t small = h22u(__hmul2_rn(half2_05, thr));
-    const uint32_t large = h22u(__hmul2_rn(half2_2, thr));
-    const uint32_t c0 = (codes >> (4 * i)) & 3u, c1 = (codes >> (4 * i + 2)) & 3u;
-    uint32_t lo = ((c0 & 1u) ? large : small) & 0xFFFFu;
-    uint32_t hi = ((c1 & 1u) ? large : small) & 0xFFFF0000u;
-    uint32_t lvl = lo | hi;
-    lvl ^= (((c0 >> 1) ^ 1u) << 15) | (((c1 >> 1) ^ 1u) << 31);  // sign bit 0 -> negative
-    r.w[i] = h22u(__hadd2_rn(u2h2(b.w[i]), u2h2(lvl)));
+    // selector nibbles: byte 1 <- lut[code of element 2i], byte 3 <- lut[code of element 2i+1], bytes 0/2 <- 0
+    const uint32_t sel = ((ca >> (4 * i)) & 0x30u) | ((cb >> (4 * i)) & 0x3000u) | 0x0404u;
+    const uint32_t fac = __byte_perm(lut, 0u, sel);
+    r.w[i] = h22u(__hadd2_rn(u2h2(b.w[i]), __hmul2_rn(thr, u2h2(fac))));
   }
   return r;
 }
@@ -523,8 +524,21 @@ static cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-static PipeArgs pipe_args(const PipeGeom& g, int rows_per_cta) {
+// L2 residency plan (CF_L2_HINTS=0 disables): pass 1 loads `base` with an evict_last policy when all the
+// bases of the launch (batch * N * C * 2 bytes) fit comfortably in the 126 MB L2, so the apply / INT2 encode
+// pass that follows re-reads them from L2 instead of HBM; x, the codes and the rewritten base lines are
+// evict_first (they are not touched again before the next denoising step).
+static int l2_keep_base(int64_t N, int64_t C, int batch) {
+  if (pipe_env_int("CF_L2_HINTS", 1) == 0) return 0;
+  const int64_t cap = static_cast<int64_t>(pipe_env_int("CF_L2_KEEP_MB", 72)) << 20;
+  return N * C * 2 * batch <= cap ? 1 : 0;
+}
+static int l2_stream_hints() { return pipe_env_int("CF_L2_HINTS", 1) != 0 ? 1 : 0; }
+
+static PipeArgs pipe_args(const PipeGeom& g, int rows_per_cta, int l2_hints, bool early_load) {
   PipeArgs a{};
+  a.l2_hints = l2_hints;
+  a.early_load = (early_load && pdl_enabled()) ? 1 : 0;
   a.TX = g.TX; a.TY = g.TY; a.R = g.R; a.stages = g.stages; a.chunk_rows = g.chunk_rows; a.u_cap = g.u_cap;
   a.tile_bytes = g.tile_bytes; a.stage_bytes = g.stage_bytes; a.rows_per_cta = rows_per_cta;
   return a;
@@ -604,9 +618,9 @@ size_t sign_codec_workspace_bytes(int64_t N, int64_t C, int batch) {
 }
 
 template <int MODE>
-static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st) {
+static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st, bool stable = false) {
   if (pl.tma) {
-    const PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta);
+    const PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta, l2_keep_base(sp.N, sp.C, batch), stable);
     dim3 grid(pl.B, batch), block(pl.pipe.TX * pl.pipe.TY + 32);
     const int variant = (pl.pipe.G == 1 ? 0 : 2) + (pl.pipe.ctas_per_sm == 1 ? 0 : 1);
     switch (variant) {
@@ -652,7 +666,7 @@ static int apply_grid_x(const RowGeom& g, int64_t N, int batch) {
 }
 
 template <int MODE>
-static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
+static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st, bool stable = false) {
   const int code_row = (MODE == MODE_BINARY) ? ap.C / 8 : ap.C / 4;
   const bool need_wait = ap.expected != nullptr;
   bool tma = (need_wait || !legacy_forced()) && code_row % 16 == 0;
@@ -663,7 +677,7 @@ static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
     if (pg.ok) {
       int n_cta = 1;
       const TileSched ts = make_tile_sched(pg, ap.N, batch, &n_cta);
-      const PipeArgs a = pipe_args(pg, 0);
+      const PipeArgs a = pipe_args(pg, 0, l2_stream_hints(), stable);
       dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
       const int variant = (pg.G == 1 ? 0 : 2) + (pg.ctas_per_sm == 1 ? 0 : 1);
       switch (variant) {
@@ -695,7 +709,7 @@ static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st) {
   return CF_OK;
 }
 
-static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_t st) {
+static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_t st, bool stable = false) {
   bool tma = !legacy_forced();
   for (int t = 0; t < batch && tma; ++t)
     tma = ep.base[t] != nullptr && aligned16(ep.base[t]) && aligned16(ep.x[t]) && aligned2(ep.packed[t]);
@@ -704,7 +718,7 @@ static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_
     if (pg.ok) {
       int n_cta = 1;
       const TileSched ts = make_tile_sched(pg, ep.N, batch, &n_cta);
-      const PipeArgs a = pipe_args(pg, 0);
+      const PipeArgs a = pipe_args(pg, 0, l2_keep_base(ep.N, ep.C, batch), stable);
       dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
       const int variant = (pg.G == 1 ? 0 : 2) + (pg.ctas_per_sm == 1 ? 0 : 1);
       switch (variant) {
@@ -743,7 +757,7 @@ template <int MODE>
 static int sign_compress(int batch, const void* const* x, const void* const* base, void* const* new_base,
                          void* const* packed, void* const* scale_u, void* const* scale_v, int64_t N,
                          int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream,
-                         int passes = CF_PASS_ALL) {
+                         int passes = CF_PASS_ALL, bool stable = false) {
   if (int rc = check_shape(N, C, batch)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool all_base = base != nullptr;
@@ -783,7 +797,7 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
     if (new_base && new_base[t]) any_update = true;
   }
   if (passes & CF_PASS_STATS)
-    if (int rc = launch_stats<MODE>(pl, sp, batch, st)) return rc;
+    if (int rc = launch_stats<MODE>(pl, sp, batch, st, stable)) return rc;
   if (passes & CF_PASS_FINALIZE) {
     dim3 grid(static_cast<unsigned>((C + 31) / 32), batch);  // one CTA per 32 columns
     CF_CHECK_CUDA(launch_ex(k_finalize_scales<MODE>, grid, dim3(1024), 0, st, true, fp));
@@ -801,7 +815,7 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
         ap.base[t] = sp.base[t];
         ap.recon[t] = static_cast<__half*>(new_base[t]);
       }
-      if (int rc = launch_apply<MODE_BINARY>(ap, batch, st)) return rc;
+      if (int rc = launch_apply<MODE_BINARY>(ap, batch, st, stable)) return rc;
     }
   } else {
     Int2EncodeParams ep{};
@@ -816,7 +830,7 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
       ep.packed[t] = sp.packed[t];
       ep.new_base[t] = any_update ? static_cast<__half*>(new_base[t]) : nullptr;
     }
-    if (int rc = launch_int2_encode(ep, batch, st)) return rc;
+    if (int rc = launch_int2_encode(ep, batch, st, stable)) return rc;
   }
   return CF_OK;
 }
@@ -825,7 +839,7 @@ template <int MODE>
 static int sign_decompress(int batch, const void* const* packed, const void* const* scale_u,
                            const void* const* scale_v, int K, const void* const* base, void* const* recon,
                            int64_t N, int64_t C, cf_stream_t stream, const void* const* wait_flag = nullptr,
-                           const void* expected = nullptr, void* error = nullptr) {
+                           const void* expected = nullptr, void* error = nullptr, bool stable = false) {
   if (int rc = check_shape(N, C, batch)) return rc;
   CF_CHECK_ARG(K >= 1, "K must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -859,7 +873,7 @@ static int sign_decompress(int batch, const void* const* packed, const void* con
     }
     return CF_OK;
   }
-  return launch_apply<MODE>(ap, batch, st);
+  return launch_apply<MODE>(ap, batch, st, stable);
 }
 
 }  // namespace cf
@@ -914,24 +928,28 @@ int cf_int2_decompress(const void* packed, const void* scale_u, const void* scal
 int cf_sign_compress_passes(int codec, int passes, int batch, const void* const* x, const void* const* base,
                             void* const* new_base, void* const* packed, void* const* scale_u, void* const* scale_v,
                             int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  const bool stable = (codec & CF_FLAG_INPUTS_STABLE) != 0;
+  codec &= ~CF_FLAG_INPUTS_STABLE;
   CF_CHECK_ARG(codec == CF_CODEC_BINARY || codec == CF_CODEC_INT2, "codec must be CF_CODEC_BINARY or CF_CODEC_INT2");
   CF_CHECK_ARG(passes > 0 && (passes & ~CF_PASS_ALL) == 0, "bad pass mask %d", passes);
   if (codec == CF_CODEC_BINARY)
     return cf::sign_compress<cf::MODE_BINARY>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
-                                              workspace_bytes, stream, passes);
+                                              workspace_bytes, stream, passes, stable);
   return cf::sign_compress<cf::MODE_INT2>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
-                                          workspace_bytes, stream, passes);
+                                          workspace_bytes, stream, passes, stable);
 }
 int cf_sign_decompress_batched_wait(int codec, int batch, const void* const* packed, const void* const* scale_u,
                                     const void* const* scale_v, const void* const* base, void* const* recon,
                                     const void* const* wait_flag, const void* expected, void* error_word, int64_t N,
                                     int64_t C, cf_stream_t stream) {
+  const bool stable = (codec & CF_FLAG_INPUTS_STABLE) != 0;
+  codec &= ~CF_FLAG_INPUTS_STABLE;
   CF_CHECK_ARG(codec == CF_CODEC_BINARY || codec == CF_CODEC_INT2, "codec must be CF_CODEC_BINARY or CF_CODEC_INT2");
   if (codec == CF_CODEC_BINARY)
     return cf::sign_decompress<cf::MODE_BINARY>(batch, packed, scale_u, scale_v, 1, base, recon, N, C, stream,
-                                                wait_flag, expected, error_word);
+                                                wait_flag, expected, error_word, stable);
   return cf::sign_decompress<cf::MODE_INT2>(batch, packed, scale_u, scale_v, 1, base, recon, N, C, stream, wait_flag,
-                                            expected, error_word);
+                                            expected, error_word, stable);
 }
 int cf_int2_encode_with_scales(const void* x, const void* base, const void* scale_u, const void* scale_v,
                                void* new_base, void* packed, int64_t N, int64_t C, cf_stream_t stream) {

@@ -13,7 +13,8 @@
 
 namespace cf {
 
-constexpr int kPipeMaxThreads = 512 + 32;
+constexpr int kPipeMaxThreads = 512 + 32;   // one CTA per SM
+constexpr int kPipeThreadsOcc2 = 384 + 32;  // two CTAs per SM
 constexpr size_t kPipeSmemBudget = 216 * 1024;  // per SM, shared by `ctas_per_sm` resident CTAs
 
 struct PipeGeom {
@@ -55,12 +56,16 @@ static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes, bool ro
   const int per = (groups + g.G - 1) / g.G;
   g.TX = (per + 31) / 32 * 32;
   g.NWX = g.TX / 32;
-  g.TY = target_threads / g.TX;
-  if (g.TY < 1) g.TY = 1;
-  if (g.TY > 8) g.TY = 8;
   const size_t row_bytes = static_cast<size_t>(C) * 2 * nfull + code_row_bytes;
   g.u_cap = row_scales ? 2048 : 0;
   for (; g.ctas_per_sm >= 1; --g.ctas_per_sm) {
+    // two resident CTAs are compiled for blocks of <= kPipeThreadsOcc2 threads (72 registers per thread
+    // instead of 56): cap the compute threads, or fall to one CTA per SM when a row needs more
+    const int cap_threads = g.ctas_per_sm == 2 ? kPipeThreadsOcc2 - 32 : kPipeMaxThreads - 32;
+    if (g.TX > cap_threads) continue;
+    g.TY = (target_threads < cap_threads ? target_threads : cap_threads) / g.TX;
+    if (g.TY < 1) g.TY = 1;
+    if (g.TY > 8) g.TY = 8;
     const size_t budget = kPipeSmemBudget / g.ctas_per_sm;
     for (int qpt = 4; qpt >= 1; qpt /= 2) {  // quads per thread per stage: largest stage <= target with >= 2 stages
       g.R = 4 * g.TY * qpt;
@@ -88,6 +93,13 @@ struct PipeArgs {
   int TX, TY, R, stages, chunk_rows, u_cap;
   uint32_t tile_bytes, stage_bytes;
   int rows_per_cta;
+  // L2 residency plan (see l2_hints_for): pass 1 loads base with evict_last so the apply / encode pass
+  // that follows re-reads it from L2; x, codes and the rewritten base lines are evict_first
+  int l2_hints;
+  // CF_FLAG_INPUTS_STABLE: the tensors this launch only reads (x, base) were not written by the kernel
+  // launched right before it, so the producer may fill the pipeline before the programmatic dependency
+  // on that kernel resolves (the bytes flow while the previous kernel drains)
+  int early_load;
 };
 
 // ---- shared-memory carve-up --------------------------------------------------------------
@@ -129,7 +141,8 @@ __device__ __forceinline__ void pipe_init(const PipeSmem& s, const PipeArgs& a, 
 // row and lands at stage offset `off[o]`
 template <int NOPS>
 __device__ __forceinline__ void pipe_produce(const PipeSmem& s, const PipeArgs& a, const unsigned char* const* src,
-                                             const uint32_t* row_bytes, const uint32_t* off, int r_begin, int r_end) {
+                                             const uint32_t* row_bytes, const uint32_t* off, const uint64_t* pol,
+                                             int r_begin, int r_end) {
   int it = 0;
   for (int r0 = r_begin; r0 < r_end; r0 += a.R, ++it) {
     const int st = it % a.stages, k = it / a.stages;
@@ -142,8 +155,8 @@ __device__ __forceinline__ void pipe_produce(const PipeSmem& s, const PipeArgs& 
     unsigned char* dst = s.stage0 + static_cast<size_t>(st) * a.stage_bytes;
 #pragma unroll
     for (int o = 0; o < NOPS; ++o)
-      bulk_g2s(dst + off[o], src[o] + static_cast<size_t>(r0) * row_bytes[o], static_cast<uint32_t>(rows) * row_bytes[o],
-               &s.full[st]);
+      bulk_g2s_pol(dst + off[o], src[o] + static_cast<size_t>(r0) * row_bytes[o],
+                   static_cast<uint32_t>(rows) * row_bytes[o], &s.full[st], pol[o]);
   }
 }
 
@@ -161,7 +174,7 @@ __device__ __forceinline__ uint32_t h8_ge0_bits_fast(const H8& v) {
 // pass 1: delta statistics (+ sign packing for BINARY)           grid (B, batch)
 // ---------------------------------------------------------------------------------------
 template <int MODE, int G, int OCC>
-__global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_delta_stats_tma(const StatsParams p, const PipeArgs a) {
+__global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads, OCC) k_delta_stats_tma(const StatsParams p, const PipeArgs a) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
   const int ncompute = TX * TY;
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_delta_stats_tma(const 
   const int r_begin = blockIdx.x * a.rows_per_cta;
   const int r_end = min(N, r_begin + a.rows_per_cta);
   pipe_init(sm, a, ncompute);
-  pdl_wait();
+  if (tid < ncompute || !a.early_load) pdl_wait();  // every global WRITE of this kernel is behind the wait
   pdl_launch_dependents();
 
   if (tid >= ncompute) {  // producer warp
@@ -181,7 +194,9 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_delta_stats_tma(const 
                                      reinterpret_cast<const unsigned char*>(p.base[t])};
       const uint32_t rb[2] = {static_cast<uint32_t>(C) * 2u, static_cast<uint32_t>(C) * 2u};
       const uint32_t off[2] = {0u, a.tile_bytes};
-      pipe_produce<2>(sm, a, src, rb, off, r_begin, r_end);
+      const uint64_t pol[2] = {a.l2_hints ? make_policy_evict_first() : 0ull,
+                               a.l2_hints ? make_policy_evict_last() : 0ull};
+      pipe_produce<2>(sm, a, src, rb, off, pol, r_begin, r_end);
     }
     return;
   }
@@ -432,7 +447,7 @@ __device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last
 // stage = [base tile | code tile]
 // ---------------------------------------------------------------------------------------
 template <int MODE, int G, int OCC>
-__global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const ApplyParams p, const PipeArgs a,
+__global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads, OCC) k_apply_codes_tma(const ApplyParams p, const PipeArgs a,
                                                                         const TileSched ts) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
@@ -445,6 +460,22 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const 
   const uint32_t code_row = (MODE == MODE_BINARY) ? static_cast<uint32_t>(C) / 8u : static_cast<uint32_t>(C) / 4u;
   const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
   pipe_init(sm, a, ncompute);
+  const uint64_t ld_pol = a.l2_hints ? make_policy_evict_first() : 0ull;  // last use of these lines
+  // early fill: the base tiles of the first `stages` tiles do not depend on the previous kernel
+  int early_tiles = 0;
+  if (a.early_load && tid == ncompute) {
+    early_tiles = min(a.stages, T1 - T0);
+    for (int it = 0; it < early_tiles; ++it) {
+      const int tile = T0 + it;
+      const int t = tile / ts.tiles_per_tensor;
+      const int r0 = (tile % ts.tiles_per_tensor) * a.R;
+      const uint32_t rows = static_cast<uint32_t>(min(a.R, N - r0));
+      mbar_arrive_expect_tx(&sm.full[it], rows * (row_bytes + code_row));
+      bulk_g2s_pol(sm.stage0 + static_cast<size_t>(it) * a.stage_bytes,
+                   reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes,
+                   rows * row_bytes, &sm.full[it], ld_pol);
+    }
+  }
   pdl_wait();
   pdl_launch_dependents();
   if (p.expected != nullptr) {
@@ -460,11 +491,14 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const 
         const int t = tile / ts.tiles_per_tensor;
         const int r0 = (tile % ts.tiles_per_tensor) * a.R;
         const uint32_t rows = static_cast<uint32_t>(min(a.R, N - r0));
-        mbar_arrive_expect_tx(&sm.full[st], rows * (row_bytes + code_row));
         unsigned char* dst = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
-        bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes,
-                 rows * row_bytes, &sm.full[st]);
-        bulk_g2s(dst + a.tile_bytes, p.packed[t] + static_cast<size_t>(r0) * code_row, rows * code_row, &sm.full[st]);
+        if (it >= early_tiles) {
+          mbar_arrive_expect_tx(&sm.full[st], rows * (row_bytes + code_row));
+          bulk_g2s_pol(dst, reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes,
+                       rows * row_bytes, &sm.full[st], ld_pol);
+        }
+        bulk_g2s_pol(dst + a.tile_bytes, p.packed[t] + static_cast<size_t>(r0) * code_row, rows * code_row,
+                     &sm.full[st], ld_pol);
       }
     }
     return;
@@ -474,6 +508,13 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const 
   uint32_t vfrag[G][4];
   int cur_t = -1;
   stage_row_scales(sm, p, ts, a.R, T0, T1, tid, ncompute);
+  // shared-window addresses of this thread's first column group in a stage: base tile, code tile
+  constexpr uint32_t kCodeGrp = (MODE == MODE_BINARY) ? 1u : 2u;  // code bytes per 8 elements
+  const uint32_t stage_a = smem_addr(sm.stage0);
+  const uint32_t us_a = smem_addr(sm.u_s);
+  const bool all_act = tx + (G - 1) * TX < groups;
+  constexpr int kFly = (G == 1) ? 4 : 2;  // rows whose loads are issued before the first use
+  const uint64_t st_pol = a.l2_hints ? make_policy_evict_first() : 0ull;
 
   for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
     const int st = it % a.stages, k = it / a.stages;
@@ -483,29 +524,52 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const 
       load_vfrag<G>(vfrag, p.scale_v[t], tx, TX, groups);
       cur_t = t;
     }
-    __half* __restrict__ recon = p.recon[t];
     mbar_wait(&sm.full[st], k & 1);
-    const unsigned char* bs = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
-    const unsigned char* cs = bs + a.tile_bytes;
     const int rows = min(a.R, N - r0);
-    const __half* us = sm.u_s + it * a.R;
-#pragma unroll 4
-    for (int rl = ty; rl < rows; rl += TY) {
-      const __half2 u2 = __half2half2(us[rl]);
+    const uint32_t bs_a = stage_a + static_cast<uint32_t>(st) * a.stage_bytes + static_cast<uint32_t>(tx) * 16u;
+    const uint32_t cs_a = stage_a + static_cast<uint32_t>(st) * a.stage_bytes + a.tile_bytes +
+                          static_cast<uint32_t>(tx) * kCodeGrp;
+    const uint32_t ut_a = us_a + static_cast<uint32_t>(it * a.R) * 2u;
+    __half* __restrict__ rp = p.recon[t] + static_cast<size_t>(r0) * C + 8 * tx;
+    int rl = ty;
+    if (all_act) {
+      for (; rl + (kFly - 1) * TY < rows; rl += kFly * TY) {
+        uint4 bv[kFly][G];
+        uint32_t cd[kFly][G], uu[kFly];
+#pragma unroll
+        for (int f = 0; f < kFly; ++f) {
+          const uint32_t r = static_cast<uint32_t>(rl + f * TY);
+          uu[f] = lds16a(ut_a + r * 2u);
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            bv[f][j] = lds128a(bs_a + r * row_bytes + static_cast<uint32_t>(j * TX) * 16u);
+            cd[f][j] = (MODE == MODE_BINARY) ? lds8a(cs_a + r * code_row + static_cast<uint32_t>(j * TX) * kCodeGrp)
+                                             : lds16a(cs_a + r * code_row + static_cast<uint32_t>(j * TX) * kCodeGrp);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < kFly; ++f) {
+          const __half2 u2 = u2h2(uu[f] * 0x10001u);  // broadcast the 16-bit row scale to both halves
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const H8 out = (MODE == MODE_BINARY) ? binary_apply8(as_h8(bv[f][j]), cd[f][j], u2, vfrag[j])
+                                                 : int2_apply8(as_h8(bv[f][j]), cd[f][j], u2, vfrag[j]);
+            stg_stream_pol(rp + static_cast<size_t>(rl + f * TY) * C + 8 * j * TX, as_u4(out), st_pol);
+          }
+        }
+      }
+    }
+    for (; rl < rows; rl += TY) {  // leftover rows / threads with an inactive column group
+      const uint32_t r = static_cast<uint32_t>(rl);
+      const __half2 u2 = u2h2(lds16a(ut_a + r * 2u) * 0x10001u);
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const int g = tx + j * TX;
-        if (g < groups) {
-          const H8 b = as_h8(lds128(bs + static_cast<uint32_t>(rl) * row_bytes + static_cast<uint32_t>(g) * 16u));
-          H8 out;
-          if (MODE == MODE_BINARY) {
-            const uint32_t code = cs[static_cast<uint32_t>(rl) * code_row + g];
-            out = binary_apply8(b, code, u2, vfrag[j]);
-          } else {
-            const uint32_t code = *reinterpret_cast<const uint16_t*>(cs + static_cast<uint32_t>(rl) * code_row + 2 * g);
-            out = int2_apply8(b, code, u2, vfrag[j]);
-          }
-          stg_stream(recon + static_cast<size_t>(r0 + rl) * C + 8 * g, as_u4(out));
+        if (tx + j * TX < groups) {
+          const H8 b = as_h8(lds128a(bs_a + r * row_bytes + static_cast<uint32_t>(j * TX) * 16u));
+          const uint32_t ca = cs_a + r * code_row + static_cast<uint32_t>(j * TX) * kCodeGrp;
+          const H8 out = (MODE == MODE_BINARY) ? binary_apply8(b, lds8a(ca), u2, vfrag[j])
+                                               : int2_apply8(b, lds16a(ca), u2, vfrag[j]);
+          stg_stream_pol(rp + static_cast<size_t>(rl) * C + 8 * j * TX, as_u4(out), st_pol);
         }
       }
     }
@@ -519,7 +583,7 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_apply_codes_tma(const 
 // stage = [x tile | base tile]
 // ---------------------------------------------------------------------------------------
 template <int G, int OCC>
-__global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_int2_encode_tma(const Int2EncodeParams p, const PipeArgs a,
+__global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads, OCC) k_int2_encode_tma(const Int2EncodeParams p, const PipeArgs a,
                                                                         const TileSched ts) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
@@ -531,11 +595,13 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_int2_encode_tma(const 
   const int T1 = min(ts.total_tiles, T0 + ts.tiles_per_cta);
   const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
   pipe_init(sm, a, ncompute);
-  pdl_wait();
+  if (tid < ncompute || !a.early_load) pdl_wait();  // x / base tiles may flow before the dependency resolves
   pdl_launch_dependents();
 
   if (tid >= ncompute) {
     if (tid == ncompute) {
+      const uint64_t pol_x = a.l2_hints ? make_policy_evict_first() : 0ull;
+      const uint64_t pol_b = a.l2_hints ? make_policy_evict_last() : 0ull;  // the apply pass re-reads base
       for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
         const int st = it % a.stages, k = it / a.stages;
         if (k > 0) mbar_wait(&sm.empty[st], (k - 1) & 1);
@@ -544,10 +610,11 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_int2_encode_tma(const 
         const uint32_t bytes = static_cast<uint32_t>(min(a.R, N - r0)) * row_bytes;
         mbar_arrive_expect_tx(&sm.full[st], 2 * bytes);
         unsigned char* dst = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
-        bulk_g2s(dst, reinterpret_cast<const unsigned char*>(p.x[t]) + static_cast<size_t>(r0) * row_bytes, bytes,
-                 &sm.full[st]);
-        bulk_g2s(dst + a.tile_bytes, reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes,
-                 bytes, &sm.full[st]);
+        bulk_g2s_pol(dst, reinterpret_cast<const unsigned char*>(p.x[t]) + static_cast<size_t>(r0) * row_bytes, bytes,
+                     &sm.full[st], pol_x);
+        bulk_g2s_pol(dst + a.tile_bytes,
+                     reinterpret_cast<const unsigned char*>(p.base[t]) + static_cast<size_t>(r0) * row_bytes, bytes,
+                     &sm.full[st], pol_b);
       }
     }
     return;
@@ -557,7 +624,32 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_int2_encode_tma(const 
   uint32_t vfrag[G][4];
   int cur_t = -1;
   stage_row_scales(sm, p, ts, a.R, T0, T1, tid, ncompute);
-  const __half2 zero2 = __float2half2_rn(0.f);
+  const uint32_t stage_a = smem_addr(sm.stage0);
+  const uint32_t us_a = smem_addr(sm.u_s);
+  const bool all_act = tx + (G - 1) * TX < groups;
+  constexpr int kFly = (G == 1) ? 4 : 2;  // rows whose loads are issued before the first use
+  const uint64_t st_pol = a.l2_hints ? make_policy_evict_first() : 0ull;
+
+  // codes of 8 elements (+ optional error-feedback base) from delta and the final scales
+  auto encode8 = [&](const H8& xv, const H8& b, __half2 u2, const uint32_t* vf, uint8_t* code_dst, __half* nb_dst) {
+    const __half2 zero2 = __float2half2_rn(0.f);
+    const H8 d = h8_sub(xv, b);
+    uint32_t sacc = 0, macc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 thr = __hmul2_rn(u2h2(vf[i]), u2);                   // fastpath.py:536
+      const uint32_t sgn = __hge2_mask(u2h2(d.w[i]), zero2);              // fastpath.py:539
+      const uint32_t mag = __hgt2_mask(__habs2(u2h2(d.w[i])), thr);       // fastpath.py:540
+      // element 2i -> bits 4i (mag), 4i+1 (sign); element 2i+1 -> bits 4i+2, 4i+3, taken from the
+      // high half of the mask (16 positions up, folded down below)
+      sacc |= sgn & ((2u << (4 * i)) | (8u << (4 * i + 16)));
+      macc |= mag & ((1u << (4 * i)) | (4u << (4 * i + 16)));
+    }
+    const uint32_t both = sacc | macc;
+    const uint32_t codes = (both | (both >> 16)) & 0xFFFFu;
+    *reinterpret_cast<uint16_t*>(code_dst) = static_cast<uint16_t>(codes);
+    if (nb_dst != nullptr) stg_stream_pol(nb_dst, as_u4(int2_apply8(b, codes, u2, vf)), st_pol);
+  };
 
   for (int tile = T0, it = 0; tile < T1; ++tile, ++it) {
     const int st = it % a.stages, k = it / a.stages;
@@ -567,42 +659,50 @@ __global__ void __launch_bounds__(kPipeMaxThreads, OCC) k_int2_encode_tma(const 
       load_vfrag<G>(vfrag, p.scale_v[t], tx, TX, groups);
       cur_t = t;
     }
-    uint8_t* __restrict__ packed = p.packed[t];
-    __half* __restrict__ new_base = p.new_base[t];
+    uint8_t* __restrict__ pk = p.packed[t] + (static_cast<size_t>(r0) * groups + tx) * 2;
+    __half* __restrict__ nbp = p.new_base[t] != nullptr ? p.new_base[t] + static_cast<size_t>(r0) * C + 8 * tx : nullptr;
     mbar_wait(&sm.full[st], k & 1);
-    const unsigned char* xs = sm.stage0 + static_cast<size_t>(st) * a.stage_bytes;
-    const unsigned char* bs = xs + a.tile_bytes;
+    const uint32_t xs_a = stage_a + static_cast<uint32_t>(st) * a.stage_bytes + static_cast<uint32_t>(tx) * 16u;
+    const uint32_t bs_off = a.tile_bytes;
+    const uint32_t ut_a = us_a + static_cast<uint32_t>(it * a.R) * 2u;
     const int rows = min(a.R, N - r0);
-    const __half* us = sm.u_s + it * a.R;
-#pragma unroll 4
-    for (int rl = ty; rl < rows; rl += TY) {
-      const __half2 u2 = __half2half2(us[rl]);
+    int rl = ty;
+    if (all_act) {
+      for (; rl + (kFly - 1) * TY < rows; rl += kFly * TY) {
+        uint4 xv[kFly][G], bv[kFly][G];
+        uint32_t uu[kFly];
+#pragma unroll
+        for (int f = 0; f < kFly; ++f) {
+          const uint32_t r = static_cast<uint32_t>(rl + f * TY);
+          uu[f] = lds16a(ut_a + r * 2u);
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const uint32_t o = xs_a + r * row_bytes + static_cast<uint32_t>(j * TX) * 16u;
+            xv[f][j] = lds128a(o);
+            bv[f][j] = lds128a(o + bs_off);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < kFly; ++f) {
+          const __half2 u2 = u2h2(uu[f] * 0x10001u);
+          const size_t row = static_cast<size_t>(rl + f * TY);
+#pragma unroll
+          for (int j = 0; j < G; ++j)
+            encode8(as_h8(xv[f][j]), as_h8(bv[f][j]), u2, vfrag[j], pk + (row * groups + j * TX) * 2,
+                    nbp != nullptr ? nbp + row * C + 8 * j * TX : nullptr);
+        }
+      }
+    }
+    for (; rl < rows; rl += TY) {  // leftover rows / threads with an inactive column group
+      const uint32_t r = static_cast<uint32_t>(rl);
+      const __half2 u2 = u2h2(lds16a(ut_a + r * 2u) * 0x10001u);
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const int g = tx + j * TX;
-        if (g < groups) {
-          const uint32_t o = static_cast<uint32_t>(rl) * row_bytes + static_cast<uint32_t>(g) * 16u;
-          const H8 b = as_h8(lds128(bs + o));
-          const H8 d = h8_sub(as_h8(lds128(xs + o)), b);
-          uint32_t sacc = 0, macc = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half2 thr = __hmul2_rn(u2h2(vfrag[j][i]), u2);                  // fastpath.py:536
-            const uint32_t sgn = __hge2_mask(u2h2(d.w[i]), zero2);                   // fastpath.py:539
-            const uint32_t mag = __hgt2_mask(__habs2(u2h2(d.w[i])), thr);            // fastpath.py:540
-            // element 2i -> bits 4i (mag), 4i+1 (sign); element 2i+1 -> bits 4i+2, 4i+3, taken from the
-            // high half of the mask (16 positions up, folded down below)
-            sacc |= sgn & ((2u << (4 * i)) | (8u << (4 * i + 16)));
-            macc |= mag & ((1u << (4 * i)) | (4u << (4 * i + 16)));
-          }
-          const uint32_t both = sacc | macc;
-          const uint32_t codes = (both | (both >> 16)) & 0xFFFFu;
-          *reinterpret_cast<uint16_t*>(packed + (static_cast<size_t>(r0 + rl) * groups + g) * 2) =
-              static_cast<uint16_t>(codes);
-          if (new_base != nullptr) {
-            const H8 nb = int2_apply8(b, codes, u2, vfrag[j]);
-            stg_stream(new_base + static_cast<size_t>(r0 + rl) * C + 8 * g, as_u4(nb));
-          }
+        if (tx + j * TX < groups) {
+          const uint32_t o = xs_a + r * row_bytes + static_cast<uint32_t>(j * TX) * 16u;
+          encode8(as_h8(lds128a(o)), as_h8(lds128a(o + bs_off)), u2, vfrag[j],
+                  pk + (static_cast<size_t>(rl) * groups + j * TX) * 2,
+                  nbp != nullptr ? nbp + static_cast<size_t>(rl) * C + 8 * j * TX : nullptr);
         }
       }
     }

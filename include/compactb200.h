@@ -130,6 +130,14 @@ CF_API int cf_int2_encode_with_scales(const void* x, const void* base, const voi
  * CF_PASS_ENCODE = INT2 codes / error-feedback base.  Later passes read what earlier ones
  * left in `workspace`; CF_PASS_ALL is the ordinary compress call. */
 enum cf_pass { CF_PASS_STATS = 1, CF_PASS_FINALIZE = 2, CF_PASS_ENCODE = 4, CF_PASS_ALL = 7 };
+/* Optional flag OR-ed into the `codec` argument of cf_sign_compress_passes and
+ * cf_sign_decompress_batched_wait.  The library's kernels are chained with programmatic
+ * dependent launch; with this flag the caller promises that the tensors the call only READS
+ * (x, base) were NOT written by the kernel launched immediately before it on `stream`, so
+ * their first tiles are fetched before that kernel has drained.  A whole-step runtime that
+ * walks distinct per-layer buffers (compactfusion_b200/engine.py) can promise this; a caller
+ * that decompresses and re-compresses the same cache entry back to back cannot. */
+enum cf_flag { CF_FLAG_INPUTS_STABLE = 0x100 };
 CF_API int cf_sign_compress_passes(int codec, int passes, int batch, const void* const* x,
                             const void* const* base, void* const* new_base, void* const* packed,
                             void* const* scale_u, void* const* scale_v, int64_t N, int64_t C,
@@ -201,7 +209,9 @@ CF_API int cf_p2p_put(const void* src, size_t bytes, int n_peers, void* const* p
  * *wait_flag[t] >= *expected for every tensor t with a non-null flag (the counters cf_p2p_put
  * publishes; `expected` is normally the caller's own local_count of the same slot).  A wait
  * that exceeds ~2 s sets *error_word = 1 instead of hanging the GPU.  Requires the pipelined
- * kernel: 16-byte aligned base/codes, C % 128 == 0 (BINARY) or C % 64 == 0 (INT2). */
+ * kernel: 16-byte aligned base/codes, C % 128 == 0 (BINARY) or C % 64 == 0 (INT2).
+ * With wait_flag == expected == NULL it is the plain batched decompress (codec may carry
+ * CF_FLAG_INPUTS_STABLE). */
 CF_API int cf_sign_decompress_batched_wait(int codec, int batch, const void* const* packed,
                                     const void* const* scale_u, const void* const* scale_v,
                                     const void* const* base, void* const* recon,

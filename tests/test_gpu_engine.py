@@ -65,6 +65,40 @@ def test_engine_matches_plain_api_world1(codec):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("codec", ["binary", "int2"])
+def test_engine_fast_launch_options_are_bit_neutral(codec, monkeypatch):
+    """L2 eviction hints, programmatic dependent launch and the early pipeline fill
+    (CF_FLAG_INPUTS_STABLE) only change WHEN bytes move: a 4-step run of a 3-layer engine is
+    bit-identical with all of them switched off."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200.engine import PatchGatherEngine
+    T = cf.COMPACT_COMPRESS_TYPE
+    ctype = T(codec)
+    n, c, layers, steps = 1150, 3072, 3, 4  # ragged: 1150 = 287 full tiles of 4 rows + 2
+    data = _data(n, c, steps, layers, dev, seed=11)
+
+    def run(fast):
+        if not fast:
+            monkeypatch.setenv("CF_L2_HINTS", "0")
+            monkeypatch.setenv("CF_PDL", "0")
+        eng = PatchGatherEngine(layers, n, c, device=dev)
+        if not fast:
+            eng._flags = 0
+        for t in range(steps):
+            ks = [data[t][l][0] for l in range(layers)]
+            vs = [data[t][l][1] for l in range(layers)]
+            eng.step(ks, vs, ctype if t >= 1 else T.WARMUP)
+        torch.cuda.synchronize()
+        monkeypatch.delenv("CF_L2_HINTS", raising=False)
+        monkeypatch.delenv("CF_PDL", raising=False)
+        return [g.clone() for g in eng.global_k + eng.global_v]
+
+    fast, plain = run(True), run(False)
+    for a, b in zip(fast, plain):
+        assert torch.equal(a, b)
+
+
 def test_engine_graph_replay_equals_eager():
     dev = _cuda()
     import compactfusion_b200 as cf
