@@ -196,15 +196,52 @@ __global__ void __launch_bounds__(256) k_minmax_column_generic(const __half* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// INT4 pass 2 / decode.  A thread handles the row pair (2i, 2i+1) of its column groups.
+// Exact fp16 quotient without a division per element.
+//
+// Eager torch computes fp16 a / s as RN16(RN32(float(a) / float(s))).  With a per-column reciprocal
+// rcp = RN32(1 / s), t = RN32(a * rcp) is within 2 fp32 ulps of the true quotient, so RN16(t) can differ
+// from the reference only when t lies within a few ulps of a rounding boundary of the fp16 grid (the 13
+// discarded mantissa bits within +-4 of 0x1000), or when the result is subnormal in fp16, zero, infinite
+// or NaN.  Those elements (< 0.1 % on activations) take the IEEE division; every other element costs one
+// multiply and three integer instructions.  (Checked against the division for all fp16 numerators x 3000
+// scales and 1.6e8 random pairs: tools-free numpy experiment recorded in DESIGN.md section 4.)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t int4_code(__half d, __half mn, __half s) {
-  const __half a = __hsub_rn(d, mn);                     // (input - min_val)          :561
-  const float q = rintf(__half2float(hdiv_exact(a, s))); // round(. / scale), half-even :561
-  return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), 15.f));  // clamp; NaN -> 0         :564
+__device__ __forceinline__ float quot_for_rn16(float a, float rcp, __half s_h) {
+  float t = a * rcp;
+  const uint32_t b = __float_as_uint(t);
+  const uint32_t e = (b >> 23) & 0xFFu;
+  if (((b - 0x0FFCu) & 0x1FFFu) <= 8u || e - 113u > 29u)  // near a tie | outside the normal fp16 range
+    t = __fdiv_rn(a, __half2float(s_h));
+  return t;
 }
-__device__ __forceinline__ __half int4_value(uint32_t q, __half mn, __half s) {
-  return __hadd_rn(__hmul_rn(__ushort2half_rn(static_cast<unsigned short>(q)), s), mn);  // q*scale + min :636
+
+__device__ __forceinline__ uint32_t ld_h2(const __half* v, int c) {  // 2-byte aligned pair load
+  return static_cast<uint32_t>(__half_as_ushort(v[c])) | (static_cast<uint32_t>(__half_as_ushort(v[c + 1])) << 16);
+}
+__device__ __forceinline__ __half lo_h(uint32_t w) { return __ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu)); }
+__device__ __forceinline__ __half hi_h(uint32_t w) { return __ushort_as_half(static_cast<unsigned short>(w >> 16)); }
+
+// ---------------------------------------------------------------------------------------
+// INT4 pass 2 / decode.  A thread handles the row pair (2i, 2i+1) of its column groups; all
+// fp16 arithmetic is packed (two columns per instruction).
+//   code  = clamp(rne(fp16((d - min) / scale)), 0, 15)        compress_quantize.py:561-564
+//   value = fp16(fp16(code * scale) + min)                    compress_quantize.py:636
+// Rounding to integer: clamp first (monotone, integer bounds), then add 1024.0 in fp16 -- the sum lies in
+// [1024, 2048) where the fp16 spacing is 1, so the addition itself rounds half-to-even and the code is the
+// low mantissa bits.  NaN -> 0 (hmax2 returns the non-NaN operand).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t int4_codes2(uint32_t d2, uint32_t mn2, uint32_t s2, float rcp0, float rcp1) {
+  const float2 a = __half22float2(__hsub2_rn(u2h2(d2), u2h2(mn2)));  // (input - min_val)  :561
+  const float t0 = quot_for_rn16(a.x, rcp0, lo_h(s2));
+  const float t1 = quot_for_rn16(a.y, rcp1, hi_h(s2));
+  __half2 h = __floats2half2_rn(t0, t1);                             // fp16(. / scale)
+  h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(15.f));
+  return h22u(__hadd2_rn(h, __float2half2_rn(1024.f)));              // 0x6400 + code per half
+}
+// biased (1024 + code) pair -> fp16(code * scale) + min
+__device__ __forceinline__ __half2 int4_values2(uint32_t r2, uint32_t mn2, uint32_t s2) {
+  const __half2 q = __hsub2_rn(u2h2(r2), __float2half2_rn(1024.f));  // exact
+  return __hadd2_rn(__hmul2_rn(q, u2h2(s2)), u2h2(mn2));
 }
 
 template <int G, bool ENCODE>
@@ -216,14 +253,19 @@ __global__ void __launch_bounds__(512) k_int4_codec(const __half* __restrict__ x
   // !ENCODE: packed, base -> out = base + deq
   const int groups = C >> 3;
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-  __half sfrag[G][8], mfrag[G][8];
+  uint32_t sfrag[G][4], mfrag[G][4];
+  float rfrag[G][ENCODE ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < G; ++j) {
     const int g = tx + j * TX;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      sfrag[j][e] = (g < groups) ? scale[8 * g + e] : __float2half_rn(1.f);
-      mfrag[j][e] = (g < groups) ? minv[8 * g + e] : __float2half_rn(0.f);
+    for (int i = 0; i < 4; ++i) {
+      sfrag[j][i] = (g < groups) ? ld_h2(scale, 8 * g + 2 * i) : 0x3C003C00u;
+      mfrag[j][i] = (g < groups) ? ld_h2(minv, 8 * g + 2 * i) : 0u;
+      if (ENCODE) {
+        rfrag[j][2 * i] = __frcp_rn(__half2float(lo_h(sfrag[j][i])));
+        rfrag[j][2 * i + 1] = __frcp_rn(__half2float(hi_h(sfrag[j][i])));
+      }
     }
   }
   const int pairs = N >> 1;
@@ -236,62 +278,67 @@ __global__ void __launch_bounds__(512) k_int4_codec(const __half* __restrict__ x
       const size_t off0 = static_cast<size_t>(2 * pi) * C + 8 * g, off1 = off0 + C;
       uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
       if (base != nullptr) { b0 = ldg_stream(base + off0); b1 = ldg_stream(base + off1); }
-      const __half* b0h = reinterpret_cast<const __half*>(&b0);
-      const __half* b1h = reinterpret_cast<const __half*>(&b1);
-      uint32_t q0[8], q1[8];
+      const H8 b0h = as_h8(b0), b1h = as_h8(b1);
+      uint32_t r0[4], r1[4];  // 1024 + code, two columns per word
       uint8_t* pk = packed + static_cast<size_t>(pi) * C + 8 * g;
       if (ENCODE) {
         const uint4 x0 = ldg_stream(x + off0), x1 = ldg_stream(x + off1);
-        const H8 d0 = h8_sub(as_h8(x0), as_h8(b0)), d1 = h8_sub(as_h8(x1), as_h8(b1));
-        const __half* d0h = reinterpret_cast<const __half*>(&d0);
-        const __half* d1h = reinterpret_cast<const __half*>(&d1);
-        uint32_t lo = 0, hi = 0;
+        const H8 d0 = h8_sub(as_h8(x0), b0h), d1 = h8_sub(as_h8(x1), b1h);
+        uint32_t m[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          q0[e] = int4_code(d0h[e], mfrag[j][e], sfrag[j][e]);
-          q1[e] = int4_code(d1h[e], mfrag[j][e], sfrag[j][e]);
-          const uint32_t byte = q0[e] | (q1[e] << 4);  // low nibble = even row  :573
-          if (e < 4) lo |= byte << (8 * e); else hi |= byte << (8 * (e - 4));
+        for (int i = 0; i < 4; ++i) {
+          r0[i] = int4_codes2(d0.w[i], mfrag[j][i], sfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
+          r1[i] = int4_codes2(d1.w[i], mfrag[j][i], sfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
+          m[i] = (r0[i] & 0x000F000Fu) | ((r1[i] & 0x000F000Fu) << 4);  // low nibble = even row  :573
         }
-        *reinterpret_cast<uint2*>(pk) = make_uint2(lo, hi);
+        // byte of column 2i sits in bits 0-7 of m[i], column 2i+1 in bits 16-23
+        *reinterpret_cast<uint2*>(pk) = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
       } else {
         const uint2 pv = *reinterpret_cast<const uint2*>(pk);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t byte = ((e < 4 ? pv.x : pv.y) >> (8 * (e & 3))) & 0xFFu;
-          q0[e] = byte & 0xFu;
-          q1[e] = byte >> 4;
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t w = __byte_perm(i < 2 ? pv.x : pv.y, 0u, (i & 1) ? 0x4342u : 0x4140u);  // [b(2i), 0, b(2i+1), 0]
+          r0[i] = (w & 0x000F000Fu) | 0x64006400u;
+          r1[i] = ((w >> 4) & 0x000F000Fu) | 0x64006400u;
         }
       }
       if (out != nullptr) {
-        __align__(16) __half o0[8], o1[8];
+        H8 o0, o1;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const __half v0 = int4_value(q0[e], mfrag[j][e], sfrag[j][e]);
-          const __half v1 = int4_value(q1[e], mfrag[j][e], sfrag[j][e]);
-          o0[e] = (base != nullptr) ? __hadd_rn(b0h[e], v0) : v0;
-          o1[e] = (base != nullptr) ? __hadd_rn(b1h[e], v1) : v1;
+        for (int i = 0; i < 4; ++i) {
+          const __half2 v0 = int4_values2(r0[i], mfrag[j][i], sfrag[j][i]);
+          const __half2 v1 = int4_values2(r1[i], mfrag[j][i], sfrag[j][i]);
+          o0.w[i] = h22u((base != nullptr) ? __hadd2_rn(u2h2(b0h.w[i]), v0) : v0);
+          o1.w[i] = h22u((base != nullptr) ? __hadd2_rn(u2h2(b1h.w[i]), v1) : v1);
         }
-        stg_stream(out + off0, *reinterpret_cast<uint4*>(o0));
-        stg_stream(out + off1, *reinterpret_cast<uint4*>(o1));
+        stg_stream(out + off0, as_u4(o0));
+        stg_stream(out + off1, as_u4(o1));
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// INT8 pass 2 / decode
+// INT8 pass 2 / decode (packed fp16, same exact-quotient and magic-add rounding; the bias is 1536 so
+// that 1536 + q stays inside [1024, 2048) for q in [-128, 127]; the code byte is the low mantissa byte)
+//   q     = clamp(rne(fp16(fp16(x / scale) + zero_point)), -128, 127)     compress_quantize.py:465-467
+//   value = fp16((q - zero_point) * scale)                                compress_quantize.py:482
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int int8_code(__half d, __half s, __half zp_h) {
-  // q = clamp(round(x / scale + zero_point), -128, 127)     compress_quantize.py:465-467
-  const __half t = __hadd_rn(hdiv_exact(d, s), zp_h);
-  const float q = rintf(__half2float(t));
-  if (q != q) return 0;
-  return static_cast<int>(fminf(fmaxf(q, -128.f), 127.f));
+__device__ __forceinline__ uint32_t int8_codes2(uint32_t d2, uint32_t s2, uint32_t zp2, float rcp0, float rcp1) {
+  const float2 a = __half22float2(u2h2(d2));
+  float t0 = quot_for_rn16(a.x, rcp0, lo_h(s2));
+  float t1 = quot_for_rn16(a.y, rcp1, hi_h(s2));
+  // NaN (zero scale with a zero numerator, or NaN input): the reference's integer cast is undefined,
+  // we define code 0: fp16(-zp) + zp == 0
+  if (t0 != t0) t0 = -__half2float(lo_h(zp2));
+  if (t1 != t1) t1 = -__half2float(hi_h(zp2));
+  __half2 h = __hadd2_rn(__floats2half2_rn(t0, t1), u2h2(zp2));
+  h = __hmin2(__hmax2(h, __float2half2_rn(-128.f)), __float2half2_rn(127.f));
+  return h22u(__hadd2_rn(h, __float2half2_rn(1536.f)));  // 0x6400 + 512 + q per half
 }
-__device__ __forceinline__ __half int8_value(int q, __half s, __half zp_h) {
-  // (q.half() - zero_point.half()) * scale                  compress_quantize.py:482
-  return __hmul_rn(__hsub_rn(__short2half_rn(static_cast<short>(q)), zp_h), s);
+__device__ __forceinline__ __half2 int8_values2(uint32_t r2, uint32_t s2, uint32_t zp2) {
+  const __half2 q = __hsub2_rn(u2h2(r2), __float2half2_rn(1536.f));  // exact
+  return __hmul2_rn(__hsub2_rn(q, u2h2(zp2)), u2h2(s2));
 }
 
 template <int G, bool ENCODE>
@@ -301,14 +348,21 @@ __global__ void __launch_bounds__(512) k_int8_codec(const __half* __restrict__ x
                                                     __half* __restrict__ out, int N, int C) {
   const int groups = C >> 3;
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-  __half sfrag[G][8], zfrag[G][8];
+  uint32_t sfrag[G][4], zfrag[G][4];
+  float rfrag[G][ENCODE ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < G; ++j) {
     const int g = tx + j * TX;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      sfrag[j][e] = (g < groups) ? scale[8 * g + e] : __float2half_rn(1.f);
-      zfrag[j][e] = (g < groups) ? __short2half_rn(zpv[8 * g + e]) : __float2half_rn(0.f);
+    for (int i = 0; i < 4; ++i) {
+      sfrag[j][i] = (g < groups) ? ld_h2(scale, 8 * g + 2 * i) : 0x3C003C00u;
+      zfrag[j][i] = (g < groups) ? h22u(__halves2half2(__short2half_rn(zpv[8 * g + 2 * i]),
+                                                        __short2half_rn(zpv[8 * g + 2 * i + 1])))
+                                 : 0u;
+      if (ENCODE) {
+        rfrag[j][2 * i] = __frcp_rn(__half2float(lo_h(sfrag[j][i])));
+        rfrag[j][2 * i + 1] = __frcp_rn(__half2float(hi_h(sfrag[j][i])));
+      }
     }
   }
   const int row_stride = gridDim.x * TY;
@@ -320,38 +374,60 @@ __global__ void __launch_bounds__(512) k_int8_codec(const __half* __restrict__ x
       const size_t off = static_cast<size_t>(r) * C + 8 * g;
       uint4 b = make_uint4(0, 0, 0, 0);
       if (base != nullptr) b = ldg_stream(base + off);
-      const __half* bh = reinterpret_cast<const __half*>(&b);
-      int q[8];
+      const H8 bh = as_h8(b);
+      uint32_t rq[4];  // 1536 + q, two columns per word
       int8_t* qp = qout + off;
       if (ENCODE) {
-        const uint4 xv = ldg_stream(x + off);
-        const H8 d = h8_sub(as_h8(xv), as_h8(b));
-        const __half* dh = reinterpret_cast<const __half*>(&d);
-        uint32_t lo = 0, hi = 0;
+        const H8 d = h8_sub(as_h8(ldg_stream(x + off)), bh);
+        uint32_t m[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          q[e] = int8_code(dh[e], sfrag[j][e], zfrag[j][e]);
-          const uint32_t byte = static_cast<uint32_t>(q[e]) & 0xFFu;
-          if (e < 4) lo |= byte << (8 * e); else hi |= byte << (8 * (e - 4));
+        for (int i = 0; i < 4; ++i) {
+          rq[i] = int8_codes2(d.w[i], sfrag[j][i], zfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
+          m[i] = rq[i] & 0x00FF00FFu;  // two's-complement byte of q: 512 is a multiple of 256
         }
-        *reinterpret_cast<uint2*>(qp) = make_uint2(lo, hi);
+        *reinterpret_cast<uint2*>(qp) = make_uint2(__byte_perm(m[0], m[1], 0x6420), __byte_perm(m[2], m[3], 0x6420));
       } else {
         const uint2 pv = *reinterpret_cast<const uint2*>(qp);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          q[e] = static_cast<int8_t>(((e < 4 ? pv.x : pv.y) >> (8 * (e & 3))) & 0xFFu);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t w = __byte_perm(i < 2 ? pv.x : pv.y, 0u, (i & 1) ? 0x4342u : 0x4140u);  // [b(2i), 0, b(2i+1), 0]
+          // mantissa of 1536 + q is 512 + q: the byte, with bits 9:8 = 10 for q >= 0 and 01 for q < 0
+          const uint32_t neg = (w >> 7) & 0x00010001u;
+          rq[i] = ((w | 0x02000200u) ^ (neg * 0x300u)) | 0x64006400u;
+        }
       }
       if (out != nullptr) {
-        __align__(16) __half o[8];
+        H8 o;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const __half v = int8_value(q[e], sfrag[j][e], zfrag[j][e]);
-          o[e] = (base != nullptr) ? __hadd_rn(bh[e], v) : v;
+        for (int i = 0; i < 4; ++i) {
+          const __half2 v = int8_values2(rq[i], sfrag[j][i], zfrag[j][i]);
+          o.w[i] = h22u((base != nullptr) ? __hadd2_rn(u2h2(bh.w[i]), v) : v);
         }
-        stg_stream(out + off, *reinterpret_cast<uint4*>(o));
+        stg_stream(out + off, as_u4(o));
       }
     }
   }
+}
+
+// scalar forms for the generic (C % 8 != 0) path
+__device__ __forceinline__ uint32_t int4_code(__half d, __half mn, __half s) {
+  const __half a = __hsub_rn(d, mn);                     // (input - min_val)          :561
+  const float q = rintf(__half2float(hdiv_exact(a, s))); // round(. / scale), half-even :561
+  return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), 15.f));  // clamp; NaN -> 0         :564
+}
+__device__ __forceinline__ __half int4_value(uint32_t q, __half mn, __half s) {
+  return __hadd_rn(__hmul_rn(__ushort2half_rn(static_cast<unsigned short>(q)), s), mn);  // q*scale + min :636
+}
+__device__ __forceinline__ int int8_code(__half d, __half s, __half zp_h) {
+  // q = clamp(round(x / scale + zero_point), -128, 127)     compress_quantize.py:465-467
+  const __half t = __hadd_rn(hdiv_exact(d, s), zp_h);
+  const float q = rintf(__half2float(t));
+  if (q != q) return 0;
+  return static_cast<int>(fminf(fmaxf(q, -128.f), 127.f));
+}
+__device__ __forceinline__ __half int8_value(int q, __half s, __half zp_h) {
+  // (q.half() - zero_point.half()) * scale                  compress_quantize.py:482
+  return __hmul_rn(__hsub_rn(__short2half_rn(static_cast<short>(q)), zp_h), s);
 }
 
 // ---- generic element-per-thread codecs for C % 8 != 0 --------------------------------------

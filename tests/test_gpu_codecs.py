@@ -138,6 +138,72 @@ def test_int4_int8_bit_exact(shape):
     assert_bits_equal(dequantize_int8(q8, s8, z8), oc.int8_dequantize(oq8, os8, oz8), "int8 deq")
 
 
+def test_int4_int8_exact_quotient_edge_cases():
+    """The encode kernels replace the per-element IEEE division by a reciprocal multiply plus an
+    exactness check (csrc/cf_minmax_codecs.cu: quot_for_rn16).  Columns built to sit ON the rounding
+    ties, with tiny / huge / zero scales and subnormal quotients must still give the oracle's codes."""
+    dev = _cuda()
+    from compactfusion_b200.compress_quantize import dequantize_int4, dequantize_int8, quantize_int4, quantize_int8
+    n, c = 4096, 512
+    g = torch.Generator().manual_seed(2024)
+    d = torch.randn(n, c, generator=g) * torch.exp(3.0 * torch.randn(1, c, generator=g))
+    k = torch.randint(0, 16, (n, 64), generator=g).float()
+    lo = torch.randn(1, 64, generator=g)
+    step = torch.rand(1, 64, generator=g) * 0.3 + 1e-3
+    d[:, :64] = lo + (k + 0.5) * step                 # exact ties of the 16-level grid
+    d[:, 64:96] = (k[:, :32] + 0.5) / 256.0 * 7.0     # ties of the 256-level grid
+    d[:, 96:112] *= 1e-6                               # subnormal fp16 values
+    d[:, 112:120] = (torch.randn(n, 8, generator=g) * 9000.0).clamp(-30000, 30000)  # large, finite max - min
+    d[:, 120] = 0.0                                    # constant columns (zero scale)
+    d[:, 121] = 1.5
+    d[:, 122] = 2.25
+    d[0, 123] = 30000.0
+    d[1, 123] = -30000.0
+    d = d.clamp(-30000, 30000).half()
+    dd = d.to(dev)
+    q, s, m = quantize_int4(dd)
+    oq, os_, om = oc.int4_quantize(d)
+    assert_bits_equal(s, os_, "int4 scale")
+    assert_bits_equal(m, om, "int4 min")
+    live = (os_.float().view(-1) != 0).numpy()         # zero-scale columns: the reference's cast is undefined
+    assert np.array_equal(q.cpu().numpy()[:, live], oq[:, live]), "int4 codes"
+    got, want = dequantize_int4(q, s, m).cpu(), oc.int4_dequantize(oq, os_, om)
+    assert_bits_equal(got[:, live], want[:, live], "int4 deq")
+    assert_bits_equal(got[:, ~live], d[:, ~live], "int4 constant columns reconstruct exactly")
+    q8, s8, z8 = quantize_int8(dd)
+    oq8, os8, oz8 = oc.int8_quantize(d)
+    assert_bits_equal(s8, os8, "int8 scale")
+    assert np.array_equal(z8.cpu().numpy(), oz8.numpy()), "int8 zero point"
+    assert np.array_equal(q8.cpu().numpy(), oq8), "int8 codes"
+    assert_bits_equal(dequantize_int8(q8, s8, z8), oc.int8_dequantize(oq8, os8, oz8), "int8 deq")
+
+
+def test_int4_error_feedback_round_trip_baseline_config():
+    """BASELINE config 0 at full size (4096 x 3072, INT4 residual + error feedback): the fused
+    sender update equals what the receiver reconstructs from the wire bytes, codes match the
+    oracle on a 256-column slice, and the EF residual stays bounded over the steps."""
+    dev = _cuda()
+    from compactfusion_b200 import _native as nv
+    from compactfusion_b200.compress_quantize import _minmax_compress, dequantize_int4
+    n, c = 4096, 3072
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(n, c, generator=g, device=dev)
+    base = x.half()
+    errs = []
+    for t in range(1, 5):
+        x = x + 0.05 * torch.randn(n, c, generator=g, device=dev)
+        xh = x.half()
+        codes, s, m, new_base = _minmax_compress(nv.CODEC_INT4, xh, base, want_recon=True)
+        recv = base + dequantize_int4(codes, s, m)
+        assert torch.equal(recv, new_base), "receiver != sender after step %d" % t
+        d = (xh - base)[:, :256].cpu()
+        oq, os_, om = oc.int4_quantize(d)
+        assert np.array_equal(codes[:, :256].cpu().numpy(), oq)
+        errs.append(rel_l2(new_base, xh))
+        base = new_base
+    assert max(errs) < 0.02 and errs[-1] < 1.5 * errs[0] + 1e-3, errs
+
+
 def test_int4_fused_residual_matches_composition():
     """cf_int4_compress(x, base, new_base) == base + dequant(quant(x - base)) bit-exactly."""
     dev = _cuda()
