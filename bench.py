@@ -372,15 +372,26 @@ def main():
 
     stats_name = "k_delta_stats_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_delta_stats"
     apply_name = "k_apply_codes_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_apply_codes"
+    fused = world > 1 and eng.fused(ctype)
+    comp = eng.compress_put if fused else eng.compress
+    fan = world if fused else 1  # fused put: codes and scales are stored to all W receive slots (W-1 over NVLink)
     # pass 1 over K and V of this rank: read x and base, write sign bits (BINARY) + partial sums
-    time_kernel(stats_name, lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
-                2 * (4 * e_tensor + (e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
-    time_kernel("k_finalize_scales", lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
-                2 * (4 * part_b * CH + 4 * n_local + 2 * CH))
+    time_kernel(stats_name, lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
+                2 * (4 * e_tensor + (fan * e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
+    time_kernel("k_finalize_scales", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
+                2 * (4 * part_b * CH + 2 * n_local + fan * 2 * (n_local + CH)))
+    if fused:
+        for k_ in kernels:
+            k_["fused_put"] = True
+            k_["nvlink_bytes_per_launch"] = (world - 1) * 2 * (
+                (e_tensor // 8 if args.codec == "binary" else 0) if k_["kernel"] == stats_name else 2 * (n_local + CH))
     if args.codec == "int2":
-        time_kernel("k_int2_encode_tma", lambda l: eng.compress(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
-                    2 * (4 * e_tensor + e_tensor // 4 + 2 * (n_local + CH)))
-    if transport == "p2p":
+        time_kernel("k_int2_encode_tma", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
+                    2 * (4 * e_tensor + fan * e_tensor // 4 + 2 * (n_local + CH)))
+        if fused:
+            kernels[-1]["fused_put"] = True
+            kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * 2 * (e_tensor // 4)
+    if transport == "p2p" and not fused:
         # one-sided exchange: this rank's [K payload | V payload] stored into all W receive slots; W-1 of them
         # cross NVLink (measured peer-copy peak 770 GB/s per direction, B200_PROFILING.md)
         slot_bytes = 2 * (e_tensor // per_byte + 2 * (n_local + CH))
@@ -482,7 +493,7 @@ def main():
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
-                       "transport": transport,
+                       "transport": transport + (" (fused into the codec kernels)" if world > 1 and eng.fused(ctype) else ""),
                        "l2": "inputs larger than L2 (each step streams > 6 GB of distinct K/V + cache)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
             "p2p_wait_timeouts": bool(eng.p2p_error()),

@@ -50,6 +50,8 @@ SYMBOLS = {
     "cf_ipc_close": (c_int, [c_void_p]),
     "cf_ipc_free": (c_int, [c_void_p]),
     "cf_p2p_put": (c_int, [c_void_p, c_size_t, c_int, _VPP, _VPP, c_void_p, c_void_p, c_void_p]),
+    "cf_sign_compress_put": (c_int, [c_int, c_int, c_int, _VPP, _VPP, c_int, c_int, _VPP, _VPP, c_void_p, c_void_p, c_int64, c_int64,
+                                     c_void_p, c_size_t, c_void_p]),
     "cf_sign_decompress_batched_wait": (c_int, [c_int, c_int] + [_VPP] * 6 + [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "cf_host_scratch_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "cf_host_compress": (c_int, [c_int] + [c_void_p] * 4 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),

@@ -11,8 +11,9 @@
 //
 // Memory model: the CTA synchronises after its stores, thread 0 issues a system-scope fence
 // (cumulative over the CTA's stores, which the barrier ordered before it) and takes a ticket;
-// the CTA that draws the last ticket fences again and publishes the flags with release
-// stores.  Receivers poll with relaxed system-scope loads and then issue one acquire fence.
+// the CTA that draws the last ticket fences again and publishes the flags with relaxed
+// system-scope stores (fence + store = release pattern).  Receivers poll with relaxed
+// system-scope loads and re-read the satisfied flag with an acquire load.
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,8 +32,8 @@ struct PutParams {
   uint32_t* done;   // local: CTA ticket counter, reset by the last CTA
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // grid (chunks, n_peers), block 256
@@ -51,6 +52,8 @@ __global__ void __launch_bounds__(256) k_p2p_put(const PutParams p) {
     dst[i + 3 * stride] = d;
   }
   for (; i < p.n16; i += stride) dst[i] = p.src[i];
+  uint32_t v = 0;
+  if (threadIdx.x == 0) v = *p.count + 1u;  // written only by the previous put's last CTA: long complete
   __syncthreads();
   if (threadIdx.x == 0) {
     // cumulative over the whole CTA's stores (ordered before this fence by the barrier)
@@ -58,11 +61,12 @@ __global__ void __launch_bounds__(256) k_p2p_put(const PutParams p) {
     const unsigned total = gridDim.x * gridDim.y;
     const unsigned ticket = atomicAdd(p.done, 1u);
     if (ticket == total - 1) {
+      // one fence (cumulative over the other CTAs' stores, observed through the ticket) + relaxed flag
+      // stores: a st.release per flag would cost a MEMBAR.SYS round trip per destination
       __threadfence_system();
-      const uint32_t v = *p.count + 1u;
+      for (int q = 0; q < p.n_peers; ++q) st_relaxed_sys(p.flag[q], v);
       *p.count = v;
       *p.done = 0u;
-      for (int q = 0; q < p.n_peers; ++q) st_release_sys(p.flag[q], v);
     }
   }
 }

@@ -35,6 +35,50 @@ struct StatsParams {
   int N, C, rows_per_cta;
 };
 
+// Fused compress + one-sided exchange (cf_sign_compress_put): instead of a local send buffer, the codec
+// kernels store the codes and scales of tensor t straight into `n_dst` receive slots -- local memory or
+// peer memory mapped over NVLink -- and the last CTA of the call's last kernel publishes the flags.
+struct FanOut {
+  unsigned char* dst[CF_MAX_FANOUT];  // [t * n_dst + q]: start of tensor t's payload [codes | U | V] at destination q
+  uint32_t* flag[CF_MAX_PEERS];       // per destination: this origin's counter flag
+  uint32_t* count;                    // local: puts issued so far on this slot (the value published)
+  uint32_t* done;                     // local: CTA ticket counter, reset by the last CTA
+  unsigned long long u_off, v_off;    // byte offsets of U (N) and V (C) inside a payload
+  int n_dst;
+};
+
+__device__ __forceinline__ void red_add_relaxed_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Tail of the kernel that completes a fused put.  Every CTA calls it after its last payload store: the
+// barrier orders the CTA's stores before thread 0's system-scope fence (cumulative), then thread 0 adds 1
+// to this origin's flag at every destination (fence + relaxed RMW = release; an NVLink atomic for the
+// peers).  A flag therefore counts CTA arrivals, and *count -- the value the receivers' decompress kernels
+// wait for (wait_origins: flag >= count, observed through the RMW chain) -- advances by the grid size per
+// put.  Nothing remote sits behind a second fence or a ticket: the critical path of a put is one fence.
+// The ticket only keeps the LOCAL count: the CTA that draws the last one adds the grid size to it.
+// `ncompute` > 0: only threads [0, ncompute) of the CTA call (named barrier 1, the pipelined kernels'
+// compute warps); 0: the whole CTA calls.
+__device__ __forceinline__ void fanout_publish_impl(const FanOut& f, unsigned total_ctas, int ncompute) {
+  if (ncompute > 0)
+    asm volatile("bar.sync 1, %0;" ::"r"(ncompute) : "memory");
+  else
+    __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int q = 0; q < f.n_dst; ++q) red_add_relaxed_sys_u32(f.flag[q], 1u);
+    const unsigned ticket = atomicAdd(f.done, 1u);
+    if (ticket == total_ctas - 1) {
+      *f.count += total_ctas;  // read by kernels launched after this one (stream order / PDL wait)
+      *f.done = 0u;
+    }
+  }
+}
+__device__ __forceinline__ void fanout_publish(const FanOut& f, unsigned total_ctas) { fanout_publish_impl(f, total_ctas, 0); }
+__device__ __forceinline__ void fanout_publish_compute(const FanOut& f, unsigned total_ctas, int ncompute) {
+  fanout_publish_impl(f, total_ctas, ncompute);
+}
+
 // ---------------------------------------------------------------------------------------
 // pass 1: delta statistics (+ sign packing for BINARY)
 // grid (B, batch), block (TX, TY)
@@ -189,8 +233,8 @@ struct FinalizeParams {
   int N, C, B;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(1024) k_finalize_scales(const FinalizeParams p) {
+template <int MODE, bool PUT>
+__global__ void __launch_bounds__(1024) k_finalize_scales(const FinalizeParams p, const FanOut f, const int publish) {
   // block = 32 columns x 32 partial lanes: every thread issues ceil(B/32) independent loads
   __shared__ float red[32][33];
   __shared__ float denom_s;
@@ -228,11 +272,23 @@ __global__ void __launch_bounds__(1024) k_finalize_scales(const FinalizeParams p
     float tot = 0.f;
 #pragma unroll
     for (int k = 0; k < 32; ++k) tot += red[k][cx];
-    p.scale_v[t][c] = __float2half_rn(tot / n_f);
+    const __half v = __float2half_rn(tot / n_f);
+    if (PUT) {
+      for (int q = 0; q < f.n_dst; ++q) reinterpret_cast<__half*>(f.dst[t * f.n_dst + q] + f.v_off)[c] = v;
+    } else {
+      p.scale_v[t][c] = v;
+    }
   }
   const float denom = denom_s;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x)
-    p.scale_u[t][n] = __float2half_rn(__half2float(p.rowmean[t][n]) / denom);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const __half u = __float2half_rn(__half2float(p.rowmean[t][n]) / denom);
+    if (PUT) {
+      for (int q = 0; q < f.n_dst; ++q) reinterpret_cast<__half*>(f.dst[t * f.n_dst + q] + f.u_off)[n] = u;
+    } else {
+      p.scale_u[t][n] = u;
+    }
+  }
+  if (PUT && publish) fanout_publish(f, gridDim.x * gridDim.y);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -249,6 +305,7 @@ struct ApplyParams {
   const uint32_t* wait_flag[CF_MAX_BATCH];  // null entries: no wait
   const uint32_t* expected;                 // null: no waiting at all
   uint32_t* error;                          // set to 1 if a wait timed out
+  int wait_mode;                            // 0: acquire loads (default); 1: relaxed polls + system fence
   int N, C, K;
 };
 
@@ -618,18 +675,32 @@ size_t sign_codec_workspace_bytes(int64_t N, int64_t C, int batch) {
 }
 
 template <int MODE>
-static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st, bool stable = false) {
+static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st, bool stable = false,
+                        const FanOut* fan = nullptr) {
   if (pl.tma) {
     const PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta, l2_keep_base(sp.N, sp.C, batch), stable);
     dim3 grid(pl.B, batch), block(pl.pipe.TX * pl.pipe.TY + 32);
     const int variant = (pl.pipe.G == 1 ? 0 : 2) + (pl.pipe.ctas_per_sm == 1 ? 0 : 1);
+    // only BINARY emits codes in pass 1: the INT2 fused put stores them from the encode kernel
+    const bool put = fan != nullptr && MODE == MODE_BINARY;
+    const FanOut f = fan != nullptr ? *fan : FanOut{};
+#define CF_LAUNCH_STATS_TMA(GG, OO)                                                                                  \
+  CF_CHECK_CUDA(put ? launch_ex(k_delta_stats_tma<MODE, GG, OO, (MODE == MODE_BINARY)>, grid, block,                 \
+                                pl.pipe.smem_bytes, st, true, sp, a, f)                                              \
+                    : launch_ex(k_delta_stats_tma<MODE, GG, OO, false>, grid, block, pl.pipe.smem_bytes, st, true,   \
+                                sp, a, f))
     switch (variant) {
-      case 0: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 1, 1>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
-      case 1: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 1, 2>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
-      case 2: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 2, 1>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
-      default: CF_CHECK_CUDA(launch_ex(k_delta_stats_tma<MODE, 2, 2>, grid, block, pl.pipe.smem_bytes, st, true, sp, a)); break;
+      case 0: CF_LAUNCH_STATS_TMA(1, 1); break;
+      case 1: CF_LAUNCH_STATS_TMA(1, 2); break;
+      case 2: CF_LAUNCH_STATS_TMA(2, 1); break;
+      default: CF_LAUNCH_STATS_TMA(2, 2); break;
     }
+#undef CF_LAUNCH_STATS_TMA
     return CF_OK;
+  }
+  if (fan != nullptr) {
+    set_error("the fused put needs the pipelined kernels: base set, C %% 8 == 0, 64 <= C <= 8192");
+    return CF_ERR_UNSUPPORTED;
   }
   dim3 grid(pl.B, batch), block(pl.geom.TX, pl.geom.TY);
 #define CF_LAUNCH_STATS(GG)                                                                    \
@@ -709,8 +780,9 @@ static int launch_apply(const ApplyParams& ap, int batch, cudaStream_t st, bool 
   return CF_OK;
 }
 
-static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_t st, bool stable = false) {
-  bool tma = !legacy_forced();
+static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_t st, bool stable = false,
+                              const FanOut* fan = nullptr) {
+  bool tma = fan != nullptr || !legacy_forced();
   for (int t = 0; t < batch && tma; ++t)
     tma = ep.base[t] != nullptr && aligned16(ep.base[t]) && aligned16(ep.x[t]) && aligned2(ep.packed[t]);
   if (tma) {
@@ -721,14 +793,24 @@ static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_
       const PipeArgs a = pipe_args(pg, 0, l2_keep_base(ep.N, ep.C, batch), stable);
       dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
       const int variant = (pg.G == 1 ? 0 : 2) + (pg.ctas_per_sm == 1 ? 0 : 1);
+      const bool put = fan != nullptr;
+      const FanOut f = put ? *fan : FanOut{};
+#define CF_LAUNCH_ENC_TMA(GG, OO)                                                                                      \
+  CF_CHECK_CUDA(put ? launch_ex(k_int2_encode_tma<GG, OO, true>, grid, block, pg.smem_bytes, st, true, ep, a, ts, f)   \
+                    : launch_ex(k_int2_encode_tma<GG, OO, false>, grid, block, pg.smem_bytes, st, true, ep, a, ts, f))
       switch (variant) {
-        case 0: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<1, 1>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
-        case 1: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<1, 2>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
-        case 2: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<2, 1>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
-        default: CF_CHECK_CUDA(launch_ex(k_int2_encode_tma<2, 2>, grid, block, pg.smem_bytes, st, true, ep, a, ts)); break;
+        case 0: CF_LAUNCH_ENC_TMA(1, 1); break;
+        case 1: CF_LAUNCH_ENC_TMA(1, 2); break;
+        case 2: CF_LAUNCH_ENC_TMA(2, 1); break;
+        default: CF_LAUNCH_ENC_TMA(2, 2); break;
       }
+#undef CF_LAUNCH_ENC_TMA
       return CF_OK;
     }
+  }
+  if (fan != nullptr) {
+    set_error("the fused put needs the pipelined kernels: 16-byte aligned x / base, C %% 8 == 0, 64 <= C <= 8192");
+    return CF_ERR_UNSUPPORTED;
   }
   const RowGeom g = make_row_geom(ep.C);
   dim3 grid(apply_grid_x(g, ep.N, batch), batch), block(g.TX, g.TY);
@@ -800,7 +882,7 @@ static int sign_compress(int batch, const void* const* x, const void* const* bas
     if (int rc = launch_stats<MODE>(pl, sp, batch, st, stable)) return rc;
   if (passes & CF_PASS_FINALIZE) {
     dim3 grid(static_cast<unsigned>((C + 31) / 32), batch);  // one CTA per 32 columns
-    CF_CHECK_CUDA(launch_ex(k_finalize_scales<MODE>, grid, dim3(1024), 0, st, true, fp));
+    CF_CHECK_CUDA(launch_ex(k_finalize_scales<MODE, false>, grid, dim3(1024), 0, st, true, fp, FanOut{}, 0));
   }
   if (!(passes & CF_PASS_ENCODE)) return CF_OK;
   if (MODE == MODE_BINARY) {
@@ -859,6 +941,7 @@ static int sign_decompress(int batch, const void* const* packed, const void* con
   }
   ap.expected = (wait_flag && expected) ? static_cast<const uint32_t*>(expected) : nullptr;
   ap.error = static_cast<uint32_t*>(error);
+  ap.wait_mode = pipe_env_int("CF_WAIT_MODE", 0);
   CF_CHECK_ARG(ap.expected == nullptr || (K == 1 && ap.error != nullptr), "flag waiting needs K == 1 and an error word");
   if (K > 1) {
     CF_CHECK_ARG(MODE == MODE_BINARY, "rank-K scales are only defined for BINARY");
@@ -874,6 +957,89 @@ static int sign_decompress(int batch, const void* const* packed, const void* con
     return CF_OK;
   }
   return launch_apply<MODE>(ap, batch, st, stable);
+}
+
+// Fused compress + put: no local send buffer, no put kernel.
+//   BINARY: stats<PUT> stores the sign bytes into every destination slot, finalize<PUT> stores the scale
+//           vectors and publishes the flags.
+//   INT2:   finalize<PUT> stores the scale vectors, encode<PUT> (which reads them back from the local
+//           destination `self_dst`) stores the code words and publishes the flags.
+template <int MODE>
+static int sign_compress_put(int passes, int batch, const void* const* x, const void* const* base, int n_dst,
+                             int self_dst, void* const* dst_payload, void* const* dst_flag, void* local_count,
+                             void* local_ticket, int64_t N, int64_t C, void* workspace, size_t workspace_bytes,
+                             cf_stream_t stream, bool stable) {
+  if (int rc = check_shape(N, C, batch)) return rc;
+  CF_CHECK_ARG(x && base && dst_payload && dst_flag && local_count && local_ticket, "null pointer");
+  CF_CHECK_ARG(MODE == MODE_BINARY || (self_dst >= 0 && self_dst < n_dst),
+               "INT2 needs self_dst (the local destination the encode pass reads the scales from)");
+  CF_CHECK_ARG(n_dst >= 1 && n_dst <= CF_MAX_PEERS && batch * n_dst <= CF_MAX_FANOUT,
+               "n_dst %d / batch %d out of range (n_dst <= %d, batch * n_dst <= %d)", n_dst, batch, CF_MAX_PEERS,
+               CF_MAX_FANOUT);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int t = 0; t < batch; ++t)
+    CF_CHECK_ARG(x[t] && base[t] && aligned16(x[t]) && aligned16(base[t]), "x/base must be set and 16-byte aligned");
+  StatsPlan pl = make_stats_plan(N, C, batch, true);
+  CF_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+               "workspace must be non-null and 256-byte aligned");
+  if (pl.per_tensor_bytes * batch > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", pl.per_tensor_bytes * batch, workspace_bytes);
+    return CF_ERR_WORKSPACE;
+  }
+  StatsParams sp{};
+  FinalizeParams fp{};
+  FanOut f{};
+  sp.N = fp.N = static_cast<int>(N);
+  sp.C = fp.C = static_cast<int>(C);
+  sp.rows_per_cta = pl.rows_per_cta;
+  fp.B = pl.B;
+  f.n_dst = n_dst;
+  f.u_off = static_cast<unsigned long long>(N) * (MODE == MODE_BINARY ? C / 8 : C / 4);
+  f.v_off = f.u_off + static_cast<unsigned long long>(N) * 2;
+  f.count = static_cast<uint32_t*>(local_count);
+  f.done = static_cast<uint32_t*>(local_ticket);
+  for (int q = 0; q < n_dst; ++q) {
+    CF_CHECK_ARG(dst_flag[q] != nullptr, "destination %d: null flag", q);
+    f.flag[q] = static_cast<uint32_t*>(dst_flag[q]);
+  }
+  for (int t = 0; t < batch; ++t) {
+    char* ws = static_cast<char*>(workspace) + pl.per_tensor_bytes * t;
+    sp.x[t] = static_cast<const __half*>(x[t]);
+    sp.base[t] = static_cast<const __half*>(base[t]);
+    sp.rowmean[t] = reinterpret_cast<__half*>(ws);
+    sp.tokpart[t] = reinterpret_cast<float*>(ws + pl.rowmean_bytes);
+    sp.colpart[t] = reinterpret_cast<float*>(ws + pl.rowmean_bytes + pl.tokpart_bytes);
+    fp.rowmean[t] = sp.rowmean[t];
+    fp.tokpart[t] = sp.tokpart[t];
+    fp.colpart[t] = sp.colpart[t];
+    for (int q = 0; q < n_dst; ++q) {
+      void* d = dst_payload[t * n_dst + q];
+      CF_CHECK_ARG(d != nullptr && aligned2(d), "tensor %d destination %d: bad payload pointer", t, q);
+      f.dst[t * n_dst + q] = static_cast<unsigned char*>(d);
+    }
+  }
+  if (passes & CF_PASS_STATS)
+    if (int rc = launch_stats<MODE>(pl, sp, batch, st, stable, &f)) return rc;
+  if (passes & CF_PASS_FINALIZE) {
+    dim3 grid(static_cast<unsigned>((C + 31) / 32), batch);
+    CF_CHECK_CUDA(launch_ex(k_finalize_scales<MODE, true>, grid, dim3(1024), 0, st, true, fp, f,
+                            MODE == MODE_BINARY ? 1 : 0));
+  }
+  if (MODE == MODE_INT2 && (passes & CF_PASS_ENCODE)) {
+    Int2EncodeParams ep{};
+    ep.N = sp.N; ep.C = sp.C;
+    for (int t = 0; t < batch; ++t) {
+      unsigned char* own = f.dst[t * n_dst + self_dst];
+      ep.x[t] = sp.x[t];
+      ep.base[t] = sp.base[t];
+      ep.scale_u[t] = reinterpret_cast<const __half*>(own + f.u_off);
+      ep.scale_v[t] = reinterpret_cast<const __half*>(own + f.v_off);
+      ep.packed[t] = own;  // unused by the PUT kernel (it stores to every f.dst)
+      ep.new_base[t] = nullptr;
+    }
+    if (int rc = launch_int2_encode(ep, batch, st, stable, &f)) return rc;
+  }
+  return CF_OK;
 }
 
 }  // namespace cf
@@ -937,6 +1103,22 @@ int cf_sign_compress_passes(int codec, int passes, int batch, const void* const*
                                               workspace_bytes, stream, passes, stable);
   return cf::sign_compress<cf::MODE_INT2>(batch, x, base, new_base, packed, scale_u, scale_v, N, C, workspace,
                                           workspace_bytes, stream, passes, stable);
+}
+int cf_sign_compress_put(int codec, int passes, int batch, const void* const* x, const void* const* base, int n_dst,
+                         int self_dst, void* const* dst_payload, void* const* dst_flag, void* local_count,
+                         void* local_ticket, int64_t N, int64_t C, void* workspace, size_t workspace_bytes,
+                         cf_stream_t stream) {
+  const bool stable = (codec & CF_FLAG_INPUTS_STABLE) != 0;
+  codec &= ~CF_FLAG_INPUTS_STABLE;
+  CF_CHECK_ARG(codec == CF_CODEC_BINARY || codec == CF_CODEC_INT2, "codec must be CF_CODEC_BINARY or CF_CODEC_INT2");
+  CF_CHECK_ARG(passes > 0 && (passes & ~CF_PASS_ALL) == 0, "bad pass mask %d", passes);
+  if (codec == CF_CODEC_BINARY)
+    return cf::sign_compress_put<cf::MODE_BINARY>(passes, batch, x, base, n_dst, self_dst, dst_payload, dst_flag,
+                                                  local_count, local_ticket, N, C, workspace, workspace_bytes, stream,
+                                                  stable);
+  return cf::sign_compress_put<cf::MODE_INT2>(passes, batch, x, base, n_dst, self_dst, dst_payload, dst_flag,
+                                              local_count, local_ticket, N, C, workspace, workspace_bytes, stream,
+                                              stable);
 }
 int cf_sign_decompress_batched_wait(int codec, int batch, const void* const* packed, const void* const* scale_u,
                                     const void* const* scale_v, const void* const* base, void* const* recon,

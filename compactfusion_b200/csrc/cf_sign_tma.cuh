@@ -173,8 +173,10 @@ __device__ __forceinline__ uint32_t h8_ge0_bits_fast(const H8& v) {
 // ---------------------------------------------------------------------------------------
 // pass 1: delta statistics (+ sign packing for BINARY)           grid (B, batch)
 // ---------------------------------------------------------------------------------------
-template <int MODE, int G, int OCC>
-__global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads, OCC) k_delta_stats_tma(const StatsParams p, const PipeArgs a) {
+// PUT: the sign bytes go to the f.n_dst receive slots of a fused put (FanOut) instead of p.packed[t]
+template <int MODE, int G, int OCC, bool PUT>
+__global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads, OCC) k_delta_stats_tma(const StatsParams p, const PipeArgs a,
+                                                                                                  const FanOut f) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
   const int ncompute = TX * TY;
@@ -228,11 +230,21 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     const uint32_t xs_a = thr_a + static_cast<uint32_t>(st) * a.stage_bytes;
     const uint32_t bs_off = a.tile_bytes;
     const int rows = min(a.R, r_end - r0);
-    uint8_t* pk_tile = packed + static_cast<size_t>(r0) * groups + tx;
+    const size_t pk_tile_off = static_cast<size_t>(r0) * groups + tx;
+    uint8_t* pk_tile = PUT ? nullptr : packed + pk_tile_off;
     for (int q = ty; 4 * q < rows; q += TY) {
       float rs[4];
       const uint32_t qa = xs_a + static_cast<uint32_t>(4 * q) * row_bytes;
-      uint8_t* pk = pk_tile + static_cast<size_t>(4 * q) * groups;
+      uint8_t* pk = PUT ? nullptr : pk_tile + static_cast<size_t>(4 * q) * groups;
+      const size_t pk_off = pk_tile_off + static_cast<size_t>(4 * q) * groups;
+      // one code byte to p.packed[t], or to every destination slot of the fused put
+      auto emit = [&](int idx, uint32_t bits) {
+        if (PUT) {
+          for (int qq = 0; qq < f.n_dst; ++qq) f.dst[t * f.n_dst + qq][pk_off + idx] = static_cast<uint8_t>(bits);
+        } else {
+          pk[idx] = static_cast<uint8_t>(bits);
+        }
+      };
       if (4 * q + 4 <= rows && all_act) {  // full quad: branch-free, loads of kFly rows in flight
 #pragma unroll
         for (int h = 0; h < 4; h += kFly) {
@@ -249,8 +261,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
             float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-              if (MODE == MODE_BINARY)
-                pk[(h + rr) * groups + j * TX] = static_cast<uint8_t>(h8_ge0_bits_fast(d[rr][j]));
+              if (MODE == MODE_BINARY) emit((h + rr) * groups + j * TX, h8_ge0_bits_fast(d[rr][j]));
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 f = __half22float2(__habs2(u2h2(d[rr][j].w[i])));
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
               if (act[j]) {
                 const uint32_t o = qa + static_cast<uint32_t>(rr) * row_bytes + static_cast<uint32_t>(j) * jstride;
                 const H8 d = h8_sub(as_h8(lds128a(o)), as_h8(lds128a(o + bs_off)));
-                if (MODE == MODE_BINARY) pk[rr * groups + j * TX] = static_cast<uint8_t>(h8_ge0_bits_fast(d));
+                if (MODE == MODE_BINARY) emit(rr * groups + j * TX, h8_ge0_bits_fast(d));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 f = __half22float2(__habs2(u2h2(d.w[i])));
@@ -419,27 +430,36 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Called by warp 0 of the CTA: lane i polls the flag of tensor t_first + i with relaxed loads (all
-// origins in parallel: one L2 round trip per poll, not one per origin), then a single acquire fence
-// at system scope orders the payload reads behind the observed flags.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Called by warp 0 of the CTA: lane i polls the flag of tensor t_first + i (all origins in parallel: one
+// L2 round trip per poll, not one per origin; `expected` and the first poll are issued together).  Polls
+// are relaxed; the poll that observes the awaited count is repeated as an acquire load (LDG.STRONG.SYS +
+// L1 invalidate -- no MEMBAR.SYS, which costs microseconds when 296 CTAs issue it at once), which orders
+// the payload reads of the CTA (behind the __syncthreads that follows) after the origin's release.
 template <typename P>
 __device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last, int lane) {
-  const uint32_t want = ld_relaxed_sys(p.expected);
   for (int t = t_first + lane; t <= t_last; t += 32) {
     const uint32_t* f = p.wait_flag[t];
     if (f == nullptr) continue;
+    const uint32_t want = ld_relaxed_sys(p.expected);
+    uint32_t cur = ld_relaxed_sys(f);
     const long long t0 = clock64();
-    while (static_cast<int32_t>(ld_relaxed_sys(f) - want) < 0) {
+    while (static_cast<int32_t>(cur - want) < 0) {
       if (clock64() - t0 > 4000000000LL) {
         atomicExch(p.error, 1u);
         break;
       }
       __nanosleep(32);
+      cur = ld_relaxed_sys(f);
     }
+    if (p.wait_mode == 0) (void)ld_acquire_sys(f);
   }
   __syncwarp();
-  asm volatile("fence.acq_rel.sys;" ::: "memory");
-  asm volatile("fence.proxy.async;" ::: "memory");
+  if (p.wait_mode != 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -481,6 +501,8 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
   if (p.expected != nullptr) {
     if (tid < 32 && T0 < T1) wait_origins(p, T0 / ts.tiles_per_tensor, (T1 - 1) / ts.tiles_per_tensor, tid);
     __syncthreads();
+    // the codes are fetched by the async proxy (TMA): order its reads behind the acquire above
+    if (tid == ncompute) asm volatile("fence.proxy.async;" ::: "memory");
   }
 
   if (tid >= ncompute) {
@@ -582,9 +604,11 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
 // INT2 encode (second pass): codes (+ optional new_base) from x, base and the final scales
 // stage = [x tile | base tile]
 // ---------------------------------------------------------------------------------------
-template <int G, int OCC>
+// PUT: the code words go to the f.n_dst receive slots of a fused put (FanOut) instead of p.packed[t], and the
+// last CTA publishes the flags (the scales were stored to the slots by k_finalize_scales<.., true>)
+template <int G, int OCC, bool PUT>
 __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads, OCC) k_int2_encode_tma(const Int2EncodeParams p, const PipeArgs a,
-                                                                        const TileSched ts) {
+                                                                        const TileSched ts, const FanOut f) {
   extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
   const int TX = a.TX, TY = a.TY, NWX = TX >> 5;
   const int ncompute = TX * TY;
@@ -631,7 +655,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
   const uint64_t st_pol = a.l2_hints ? make_policy_evict_first() : 0ull;
 
   // codes of 8 elements (+ optional error-feedback base) from delta and the final scales
-  auto encode8 = [&](const H8& xv, const H8& b, __half2 u2, const uint32_t* vf, uint8_t* code_dst, __half* nb_dst) {
+  auto encode8 = [&](const H8& xv, const H8& b, __half2 u2, const uint32_t* vf, int t, size_t code_off, __half* nb_dst) {
     const __half2 zero2 = __float2half2_rn(0.f);
     const H8 d = h8_sub(xv, b);
     uint32_t sacc = 0, macc = 0;
@@ -647,7 +671,12 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     }
     const uint32_t both = sacc | macc;
     const uint32_t codes = (both | (both >> 16)) & 0xFFFFu;
-    *reinterpret_cast<uint16_t*>(code_dst) = static_cast<uint16_t>(codes);
+    if (PUT) {
+      for (int q = 0; q < f.n_dst; ++q)
+        *reinterpret_cast<uint16_t*>(f.dst[t * f.n_dst + q] + code_off) = static_cast<uint16_t>(codes);
+    } else {
+      *reinterpret_cast<uint16_t*>(p.packed[t] + code_off) = static_cast<uint16_t>(codes);
+    }
     if (nb_dst != nullptr) stg_stream_pol(nb_dst, as_u4(int2_apply8(b, codes, u2, vf)), st_pol);
   };
 
@@ -659,7 +688,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
       load_vfrag<G>(vfrag, p.scale_v[t], tx, TX, groups);
       cur_t = t;
     }
-    uint8_t* __restrict__ pk = p.packed[t] + (static_cast<size_t>(r0) * groups + tx) * 2;
+    const size_t pk_off = (static_cast<size_t>(r0) * groups + tx) * 2;  // byte offset of this thread's codes in the tile
     __half* __restrict__ nbp = p.new_base[t] != nullptr ? p.new_base[t] + static_cast<size_t>(r0) * C + 8 * tx : nullptr;
     mbar_wait(&sm.full[st], k & 1);
     const uint32_t xs_a = stage_a + static_cast<uint32_t>(st) * a.stage_bytes + static_cast<uint32_t>(tx) * 16u;
@@ -672,23 +701,23 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
         uint4 xv[kFly][G], bv[kFly][G];
         uint32_t uu[kFly];
 #pragma unroll
-        for (int f = 0; f < kFly; ++f) {
-          const uint32_t r = static_cast<uint32_t>(rl + f * TY);
-          uu[f] = lds16a(ut_a + r * 2u);
+        for (int fl = 0; fl < kFly; ++fl) {
+          const uint32_t r = static_cast<uint32_t>(rl + fl * TY);
+          uu[fl] = lds16a(ut_a + r * 2u);
 #pragma unroll
           for (int j = 0; j < G; ++j) {
             const uint32_t o = xs_a + r * row_bytes + static_cast<uint32_t>(j * TX) * 16u;
-            xv[f][j] = lds128a(o);
-            bv[f][j] = lds128a(o + bs_off);
+            xv[fl][j] = lds128a(o);
+            bv[fl][j] = lds128a(o + bs_off);
           }
         }
 #pragma unroll
-        for (int f = 0; f < kFly; ++f) {
-          const __half2 u2 = u2h2(uu[f] * 0x10001u);
-          const size_t row = static_cast<size_t>(rl + f * TY);
+        for (int fl = 0; fl < kFly; ++fl) {
+          const __half2 u2 = u2h2(uu[fl] * 0x10001u);
+          const size_t row = static_cast<size_t>(rl + fl * TY);
 #pragma unroll
           for (int j = 0; j < G; ++j)
-            encode8(as_h8(xv[f][j]), as_h8(bv[f][j]), u2, vfrag[j], pk + (row * groups + j * TX) * 2,
+            encode8(as_h8(xv[fl][j]), as_h8(bv[fl][j]), u2, vfrag[j], t, pk_off + (row * groups + j * TX) * 2,
                     nbp != nullptr ? nbp + row * C + 8 * j * TX : nullptr);
         }
       }
@@ -700,8 +729,8 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
       for (int j = 0; j < G; ++j) {
         if (tx + j * TX < groups) {
           const uint32_t o = xs_a + r * row_bytes + static_cast<uint32_t>(j * TX) * 16u;
-          encode8(as_h8(lds128a(o)), as_h8(lds128a(o + bs_off)), u2, vfrag[j],
-                  pk + (static_cast<size_t>(rl) * groups + j * TX) * 2,
+          encode8(as_h8(lds128a(o)), as_h8(lds128a(o + bs_off)), u2, vfrag[j], t,
+                  pk_off + (static_cast<size_t>(rl) * groups + j * TX) * 2,
                   nbp != nullptr ? nbp + static_cast<size_t>(rl) * C + 8 * j * TX : nullptr);
         }
       }
@@ -709,6 +738,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[st]);
   }
+  if (PUT) fanout_publish_compute(f, gridDim.x, ncompute);  // compute threads only: the producer warp has exited
 }
 
 }  // namespace cf

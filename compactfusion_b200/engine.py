@@ -13,9 +13,12 @@ way to drive the same kernels for a whole denoising step (SURVEY.md section 7 ha
     graph and replayed with a single launch.
 
   * transport: NCCL all-gather of the payloads (`transport="nccl"`, what the reference does,
-    main.py:409), or one-sided NVLink puts into peer-mapped receive slots with device-side
-    flags (`transport="p2p"`, csrc/cf_p2p.cu): no collective on the path, so the whole step,
-    exchange included, is ONE CUDA graph.  `transport="auto"` tries p2p and falls back.
+    main.py:409), or one-sided NVLink stores into peer-mapped receive slots with device-side
+    flags (`transport="p2p"`): no collective on the path, so the whole step, exchange
+    included, is ONE CUDA graph.  The exchange is fused into the codec kernels
+    (`cf_sign_compress_put`: they store codes, scales and finally the flags straight into
+    every rank's slot); `CF_FUSED_PUT=0` compresses into a send buffer and pushes it with the
+    separate `cf_p2p_put` kernel (csrc/cf_p2p.cu).  `transport="auto"` tries p2p and falls back.
 
 Results are the ones `compact_all_gather` produces (same kernels, same wire format); only
 the 1-ulp freedom of the mean-scale reductions applies (batched launches split rows over a
@@ -70,6 +73,9 @@ class PatchGatherEngine:
         # belongs to another layer (or only writes codes / scales), so it never writes the K/V inputs or the
         # cached bases this call reads -- their first tiles may be fetched while that kernel drains
         self._flags = nv.FLAG_INPUTS_STABLE if layers >= 2 else 0
+        # fused compress + put (cf_sign_compress_put): the codec kernels store the payload straight into every
+        # rank's receive slot; CF_FUSED_PUT=0 keeps the separate put kernel (A/B)
+        self.fused_put = os.environ.get("CF_FUSED_PUT", "1") != "0"
 
     def prepare(self, ctype) -> str:
         """Set up the transport for `ctype` now (collective call); returns the transport in use."""
@@ -251,6 +257,36 @@ class PatchGatherEngine:
             passes &= ~nv.PASS_ENCODE  # no cache update on the sender: BINARY has no third kernel
         self.kernel_launches += bin(passes).count("1")
 
+    def fused(self, ctype) -> bool:
+        """True if compress and exchange of `ctype` run as one fused call (no send buffer, no put kernel)."""
+        return self.fused_put and self.transport == "p2p" and self.world > 1 and ctype in _CODEC
+
+    def compress_put(self, layer, k, v, ctype, passes: int = nv.PASS_ALL):
+        """Fused compress + one-sided exchange: the kernels write K's and V's payload into slot
+        (layer, this rank) of every rank's receive region (own included) and publish the flags."""
+        st = self._p2p_region(ctype)
+        assert st, "compress_put needs the p2p transport"
+        k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
+        key = ("cp", layer, k2.data_ptr(), v2.data_ptr(), ctype)
+        args = self._ptr_cache.get(key)
+        if args is None:
+            W, pn_bytes = self.world, self._numel(ctype) * 2
+            bases = [self._shard(self.global_k[layer], self.rank), self._shard(self.global_v[layer], self.rank)]
+            dst = (ctypes.c_void_p * (2 * W))(*[self._slot(st, st["peers"][q], layer, self.rank) + j * pn_bytes
+                                               for j in range(2) for q in range(W)])
+            flg = (ctypes.c_void_p * W)(*[self._flag(st, st["peers"][q], layer, self.rank) for q in range(W)])
+            ws = nv.workspace(nv.workspace_bytes(_CODEC[ctype], self.n, self.c, 0, 2), self.device)
+            args = (nv.ptr_array([k2, v2]), nv.ptr_array(bases), dst, flg, st["count"][layer:layer + 1].data_ptr(), ws)
+            self._ptr_cache[key] = args
+        xs, bases, dst, flg, count_ptr, ws = args
+        rc = nv.lib().cf_sign_compress_put(_CODEC[ctype] | self._flags, passes, 2, xs, bases, self.world, self.rank, dst, flg, count_ptr,
+                                           st["ticket"].data_ptr(), self.n, self.c, ws.data_ptr(), ws.numel(),
+                                           nv.stream_ptr())
+        nv.check(rc, "cf_sign_compress_put")
+        if ctype == T.BINARY:
+            passes &= ~nv.PASS_ENCODE
+        self.kernel_launches += bin(passes).count("1")
+
     def gather(self, ctype, layer: int = 0):
         """Move this rank's [K payload | V payload] to every rank: NCCL all-gather, or one put
         kernel writing all W receive slots (own included) over NVLink + flag publication."""
@@ -298,8 +334,11 @@ class PatchGatherEngine:
         if ctype == T.WARMUP:
             return self.warmup(layer, k, v)
         assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
-        self.compress(layer, k, v, ctype)
-        self.gather(ctype, layer)
+        if self.fused(ctype):
+            self.compress_put(layer, k, v, ctype)
+        else:
+            self.compress(layer, k, v, ctype)
+            self.gather(ctype, layer)
         self.decompress(layer, ctype)
         return self.global_k[layer], self.global_v[layer]
 

@@ -42,6 +42,7 @@ extern "C" {
 #define CF_ABI_VERSION 1
 #define CF_MAX_BATCH 16
 #define CF_MAX_PEERS 16
+#define CF_MAX_FANOUT 32 /* batch * n_dst of cf_sign_compress_put */
 
 typedef void* cf_stream_t; /* cudaStream_t */
 
@@ -205,6 +206,29 @@ CF_API int cf_ipc_close(void* peer_ptr);
 CF_API int cf_ipc_free(void* dev_ptr);
 CF_API int cf_p2p_put(const void* src, size_t bytes, int n_peers, void* const* peer_dst,
                void* const* peer_flag, void* local_count, void* local_ticket, cf_stream_t stream);
+/* Fused compress + put: cf_sign_compress_passes (no cache update) whose kernels store the payload of
+ * tensor t -- [codes | U (N) | V (C)], the App-A wire layout -- straight into `n_dst` receive slots
+ * instead of a local send buffer: dst_payload is a HOST array of batch * n_dst device pointers, entry
+ * [t * n_dst + q] = start of tensor t's payload at destination q (local memory or a peer mapping
+ * from cf_ipc_open; 2-byte aligned, 16-byte aligned for the flag-waiting decompress).
+ *   BINARY: the pass-1 kernel writes the sign bytes to every destination while it streams x and
+ *           base; the finalize kernel writes the scale vectors and publishes the flags.
+ *   INT2:   the finalize kernel writes the scale vectors; the encode kernel reads them back from
+ *           destination `self_dst` (which must be LOCAL memory; ignored for BINARY), writes the code
+ *           words to every destination and publishes the flags.
+ * Publishing: every CTA of the call's last kernel, after a system-scope fence behind its stores,
+ * adds 1 to every dst_flag[q] (an NVLink atomic for peers), and *local_count advances by that
+ * kernel's grid size -- so "*flag >= *local_count" means "this put has fully landed", the
+ * condition cf_sign_decompress_batched_wait waits for, whether the slot was filled by this call
+ * or by cf_p2p_put (+1 per put), as long as all ranks issue the same sequence of puts.  Replaces compress + torch.cat + dist.all_gather of
+ * compact_all_gather (main.py:400-409): there is no separate transport kernel or collective.
+ * batch * n_dst <= CF_MAX_FANOUT; needs the pipelined kernels (base set, 64 <= C <= 8192).
+ * `passes` as in cf_sign_compress_passes. */
+CF_API int cf_sign_compress_put(int codec, int passes, int batch, const void* const* x,
+                         const void* const* base, int n_dst, int self_dst,
+                         void* const* dst_payload, void* const* dst_flag, void* local_count,
+                         void* local_ticket, int64_t N, int64_t C, void* workspace,
+                         size_t workspace_bytes, cf_stream_t stream);
 /* cf_{binary,int2}_decompress_batched that first waits, on the device, until
  * *wait_flag[t] >= *expected for every tensor t with a non-null flag (the counters cf_p2p_put
  * publishes; `expected` is normally the caller's own local_count of the same slot).  A wait

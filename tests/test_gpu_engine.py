@@ -167,6 +167,80 @@ def test_host_buffer_c_abi_round_trip():
             assert torch.equal(new_base, nb.cpu())
 
 
+@pytest.mark.parametrize("codec", ["binary", "int2"])
+@pytest.mark.parametrize("n,c", [(576, 3072), (1150, 3072), (130, 1152), (64, 4096)])
+def test_fused_compress_put_matches_compress_on_local_slots(n, c, codec):
+    """cf_sign_compress_put with every destination in local memory (what a peer mapping looks like to the
+    kernel): all n_dst slots receive exactly the payload cf_{binary,int2}_compress_batched writes, the flags
+    carry the put count, and the flag-waiting decompress reconstructs from a slot."""
+    import ctypes
+    dev = _cuda()
+    from compactfusion_b200 import _native as nv
+    lib = nv.lib()
+    g = torch.Generator().manual_seed(n + c)
+    xs = [torch.randn(n, c, generator=g).half().to(dev) for _ in range(2)]
+    bases = [(x.float().cpu() * 0.97 + 0.2 * torch.randn(n, c, generator=g)).half().to(dev) for x in xs]
+    cid = nv.CODEC_BINARY if codec == "binary" else nv.CODEC_INT2
+    code_b, n_dst = n * c // (8 if codec == "binary" else 4), 3
+    pn = code_b + 2 * n + 2 * c
+    pn_pad = (pn + 15) // 16 * 16
+    # reference: the plain batched compress into a local payload
+    ref = torch.zeros(2, pn_pad, dtype=torch.uint8, device=dev)
+    ws = nv.workspace(nv.workspace_bytes(cid, n, c, 0, 2), dev)
+    arr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*ptrs)  # noqa: E731
+    plain_compress = lib.cf_binary_compress_batched if codec == "binary" else lib.cf_int2_compress_batched
+    rc = plain_compress(2, nv.ptr_array(xs), nv.ptr_array(bases), arr([None, None]),
+                                        arr([ref[t].data_ptr() for t in range(2)]),
+                                        arr([ref[t].data_ptr() + code_b for t in range(2)]),
+                                        arr([ref[t].data_ptr() + code_b + 2 * n for t in range(2)]), n, c,
+                                        ws.data_ptr(), ws.numel(), nv.stream_ptr())
+    nv.check(rc, "cf_*_compress_batched")
+    slots = torch.zeros(n_dst, 2, pn_pad, dtype=torch.uint8, device=dev)
+    flags = torch.zeros(n_dst, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    dst = arr([slots[q, t].data_ptr() for t in range(2) for q in range(n_dst)])
+    flg = arr([flags[q:q + 1].data_ptr() for q in range(n_dst)])
+    prev = 0
+    for it in range(2):
+        rc = lib.cf_sign_compress_put(cid, nv.PASS_ALL, 2, nv.ptr_array(xs), nv.ptr_array(bases), n_dst, 1, dst, flg,
+                                      count.data_ptr(), ticket.data_ptr(), n, c, ws.data_ptr(), ws.numel(), nv.stream_ptr())
+        nv.check(rc, "cf_sign_compress_put")
+        torch.cuda.synchronize()
+        # a flag counts the CTA arrivals of the publishing kernel; count is what "fully landed" looks like
+        assert count.item() > prev and ticket.item() == 0
+        assert flags.tolist() == [count.item()] * n_dst
+        prev = count.item()
+    for q in range(n_dst):
+        assert torch.equal(slots[q, :, :pn], ref[:, :pn]), f"slot {q} differs from the plain compress payload"
+    if (code_b // n) % 16 == 0:  # the flag-waiting decompress needs the pipelined kernel
+        recon = [torch.empty_like(b) for b in bases]
+        plain = [torch.empty_like(b) for b in bases]
+        q = n_dst - 1
+        pk = arr([slots[q, t].data_ptr() for t in range(2)])
+        us = arr([slots[q, t].data_ptr() + code_b for t in range(2)])
+        vs = arr([slots[q, t].data_ptr() + code_b + 2 * n for t in range(2)])
+        wf = arr([flags[q:q + 1].data_ptr()] * 2)
+        rc = lib.cf_sign_decompress_batched_wait(cid, 2, pk, us, vs, nv.ptr_array(bases), nv.ptr_array(recon), wf,
+                                                 count.data_ptr(), err.data_ptr(), n, c, nv.stream_ptr())
+        nv.check(rc, "cf_sign_decompress_batched_wait")
+        plain_decompress = lib.cf_binary_decompress_batched if codec == "binary" else lib.cf_int2_decompress_batched
+        rc = plain_decompress(2, pk, us, vs, nv.ptr_array(bases), nv.ptr_array(plain), n, c, nv.stream_ptr())
+        nv.check(rc, "cf_*_decompress_batched")
+        torch.cuda.synchronize()
+        assert err.item() == 0
+        for a, b in zip(recon, plain):
+            assert torch.equal(a, b)
+    # bad arguments are reported, not executed
+    rc = lib.cf_sign_compress_put(nv.CODEC_INT4, nv.PASS_ALL, 2, nv.ptr_array(xs), nv.ptr_array(bases), n_dst, 1, dst, flg,
+                                  count.data_ptr(), ticket.data_ptr(), n, c, ws.data_ptr(), ws.numel(), nv.stream_ptr())
+    assert rc == -1
+    rc = lib.cf_sign_compress_put(cid, nv.PASS_ALL, 2, nv.ptr_array(xs), nv.ptr_array(bases), 17, 1, dst, flg,
+                                  count.data_ptr(), ticket.data_ptr(), n, c, ws.data_ptr(), ws.numel(), nv.stream_ptr())
+    assert rc == -1
+
+
 def _two_gpu_worker_source():
     return r'''
 import os, sys

@@ -1,0 +1,8 @@
+OUT=gpurun_out; TAG=r1o; mkdir -p $OUT
+(time timeout 200 python -m pytest tests/test_gpu_engine.py -m gpu -x -q -k "fused or two_gpu") > $OUT/${TAG}_tests.log 2>&1 ; tail -15 $OUT/${TAG}_tests.log
+timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29502 \
+    bench.py --gpus 2 --steps 10 --warmup 3 --no-e2e --hang-dump 90 > $OUT/${TAG}_bench_n2.json 2> $OUT/${TAG}_bench_n2.err
+tail -c 300 $OUT/${TAG}_bench_n2.err
+timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29503 \
+    bench.py --gpus 2 --steps 10 --warmup 3 --no-e2e --codec int2 --hang-dump 90 > $OUT/${TAG}_bench_n2_int2.json 2> $OUT/${TAG}_bench_n2_int2.err
+tail -c 300 $OUT/${TAG}_bench_n2_int2.err
