@@ -53,6 +53,9 @@ SYMBOLS = {
     "cf_sign_compress_put": (c_int, [c_int, c_int, c_int, _VPP, _VPP, c_int, c_int, _VPP, _VPP, c_void_p, c_void_p, c_int64, c_int64,
                                      c_void_p, c_size_t, c_void_p]),
     "cf_sign_decompress_batched_wait": (c_int, [c_int, c_int] + [_VPP] * 6 + [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "cf_lse_merge": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
+    "cf_error_stats_workspace_bytes": (c_size_t, []),
+    "cf_error_stats": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cf_host_scratch_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "cf_host_compress": (c_int, [c_int] + [c_void_p] * 4 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "cf_host_decompress": (c_int, [c_int] + [c_void_p] * 3 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),

@@ -67,3 +67,27 @@ def update_out_and_lse(out, lse, block_out, block_lse):
     out = out - torch.sigmoid(block_lse - lse) * (out - block_out)
     lse = lse - F.logsigmoid(lse - block_lse)
     return out, lse
+
+
+def merge_out_and_lse(out, lse, block_out, block_lse):
+    """`update_out_and_lse` as ONE fused pass on the GPU (`cf_lse_merge`, csrc/cf_consumer.cu), in
+    flash-attn's own layouts: state `out` (b, s, h, d) fp32 is updated in place, `lse` stays
+    (b, h, s) fp32 (no transposes, no (b, s, h, 1) temporaries).  Returns the new (out, lse).
+    Used by engine.RingExchangeEngine; CUDA tensors only (the library has no CPU path)."""
+    from . import _native as nv
+    if out is None:
+        return block_out.to(torch.float32), block_lse.contiguous().to(torch.float32)
+    if not out.is_cuda:
+        raise nv.NativeError("merge_out_and_lse needs CUDA tensors: compactfusion_b200 has no CPU path")
+    b, s, h, d = out.shape
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    assert block_out.shape == out.shape and block_out.dtype == torch.half
+    block_out = block_out.contiguous()
+    block_lse = block_lse.contiguous()
+    assert lse.shape == (b, h, s) and block_lse.shape == (b, h, s)
+    assert lse.dtype == torch.float32 and block_lse.dtype == torch.float32 and lse.is_contiguous()
+    new_lse = torch.empty_like(lse)
+    rc = nv.lib().cf_lse_merge(out.data_ptr(), block_out.data_ptr(), lse.data_ptr(), block_lse.data_ptr(),
+                               new_lse.data_ptr(), b, s, h, d, nv.stream_ptr())
+    nv.check(rc, "cf_lse_merge")
+    return out, new_lse

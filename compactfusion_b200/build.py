@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcompactb200.so")
-SOURCES = ["cf_api.cu", "cf_sign_codecs.cu", "cf_minmax_codecs.cu", "cf_topk.cu", "cf_lowrank.cu", "cf_p2p.cu"]
+SOURCES = ["cf_api.cu", "cf_sign_codecs.cu", "cf_minmax_codecs.cu", "cf_topk.cu", "cf_lowrank.cu", "cf_p2p.cu",
+           "cf_consumer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -195,15 +195,16 @@ class PatchGatherEngine:
             self._ptr_cache[key] = args
         return args
 
-    def _decompress_args_p2p(self, layer, ctype, st):
-        key = ("dp", layer, ctype)
+    def _decompress_args_p2p(self, layer, ctype, st, origins=None):
+        origins = tuple(range(self.world)) if origins is None else tuple(origins)
+        key = ("dp", layer, ctype, origins)
         args = self._ptr_cache.get(key)
         if args is None:
             per_byte = 8 if ctype == T.BINARY else 4
             code_bytes = self.n * (self.c // per_byte)
             pn_bytes = self._numel(ctype) * 2
             packed, us, vs, bases, flags = [], [], [], [], []
-            for r in range(self.world):
+            for r in origins:
                 slot = self._slot(st, st["base"], layer, r)
                 for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
                     p0 = slot + j * pn_bytes
@@ -222,13 +223,14 @@ class PatchGatherEngine:
             self._ptr_cache[key] = args
         return args
 
-    def _decompress_args(self, layer, ctype):
-        key = ("d", layer, ctype)
+    def _decompress_args(self, layer, ctype, origins=None):
+        origins = tuple(range(self.world)) if origins is None else tuple(origins)
+        key = ("d", layer, ctype, origins)
         args = self._ptr_cache.get(key)
         if args is None:
             _, recv = self._buffers(ctype)
             packed, us, vs, bases = [], [], [], []
-            for r in range(self.world):
+            for r in origins:
                 for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
                     p, u, v = self._views(recv[r, j], ctype)
                     packed.append(p)
@@ -311,19 +313,20 @@ class PatchGatherEngine:
         nv.check(rc, "cf_p2p_put")
         self.kernel_launches += 1
 
-    def decompress(self, layer, ctype):
-        """All W origins x {K, V}: recon = base + dequant, in place in the global buffers."""
+    def decompress(self, layer, ctype, origins=None):
+        """Origins x {K, V} (default: all W): recon = base + dequant, in place in the global buffers.
+        With the one-sided transport the kernel first waits for the flags of exactly these origins."""
         st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
         if st:
             expected = st["count"][layer:layer + 1].data_ptr()
-            for cnt, pk, us, vs, bases, recon, flags in self._decompress_args_p2p(layer, ctype, st):
+            for cnt, pk, us, vs, bases, recon, flags in self._decompress_args_p2p(layer, ctype, st, origins):
                 rc = nv.lib().cf_sign_decompress_batched_wait(_CODEC[ctype] | self._flags, cnt, pk, us, vs, bases, recon, flags,
                                                               expected, st["error"].data_ptr(), self.n, self.c,
                                                               nv.stream_ptr())
                 nv.check(rc, "cf_sign_decompress_batched_wait")
                 self.kernel_launches += 1
             return
-        for cnt, pk, us, vs, bases, recon in self._decompress_args(layer, ctype):
+        for cnt, pk, us, vs, bases, recon in self._decompress_args(layer, ctype, origins):
             rc = nv.lib().cf_sign_decompress_batched_wait(_CODEC[ctype] | self._flags, cnt, pk, us, vs, bases, recon,
                                                           None, None, None, self.n, self.c, nv.stream_ptr())
             nv.check(rc, "cf_sign_decompress_batched_wait")
@@ -365,3 +368,81 @@ class PatchGatherEngine:
         self.launches_per_graph = self.kernel_launches - before
         self._ptr_cache.clear()
         return g
+
+
+class RingExchangeEngine(PatchGatherEngine):
+    """Compressed ring attention (`_compact_ring_fwd`, ring.py:120-275) on the engine's persistent buffers.
+
+    The reference relays each origin's compressed payload W-1 hops around a NCCL P2P ring
+    (ring.py:268-269) because a relay is what a ring of point-to-point links offers.  Behind an
+    NVSwitch every peer is one hop away, so here the sender's codec kernels store its payload into
+    ALL W receive slots at once (`cf_sign_compress_put`, or one all-gather on the NCCL transport)
+    and the "ring" is only the ORDER in which a rank consumes the origins: hop s reconstructs
+    origin (rank - s) mod W -- K and V in one launch that waits, on the device, for exactly that
+    origin's flag -- and hands the block to attention while later payloads are still in flight.
+    Hop 0 attends to the RAW local K/V (ring.py:197-208) while the own-shard cache receives the
+    error-feedback reconstruction, computed by the same kernel every receiver runs on the same
+    payload, so all W copies of an origin's base stay bit-identical.
+    Non-causal attention only (every hop is consumed, like the DiT callers of ring.py).
+    """
+
+    def hop_origin(self, hop: int) -> int:
+        return (self.rank - hop) % self.world
+
+    def begin(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
+        """Hop 0: compress this rank's K and V against the cached base, publish the payload to every
+        rank and update the own-shard cache (compact_compress(..., update_cache=True), ring.py:184-185)."""
+        if ctype == T.WARMUP:
+            self.warmup(layer, k, v)
+            return
+        assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
+        if self.fused(ctype):
+            self.compress_put(layer, k, v, ctype)
+        else:
+            self.compress(layer, k, v, ctype)
+            self.gather(ctype, layer)
+        self.decompress(layer, ctype, origins=(self.rank,))
+
+    def hop(self, layer: int, hop: int, ctype):
+        """Hop s >= 1: reconstruct origin (rank - s) mod W (cache update, ring.py:199-200); returns
+        that origin's (n_local, C) K and V blocks (views into the global buffers)."""
+        r = self.hop_origin(hop)
+        if ctype != T.WARMUP and hop != 0:
+            self.decompress(layer, ctype, origins=(r,))
+        return self._shard(self.global_k[layer], r), self._shard(self.global_v[layer], r)
+
+    def exchange(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
+        """The hot path of one layer without the attention blocks (what bench.py times)."""
+        self.begin(layer, k, v, ctype)
+        for s in range(1, self.world):
+            self.hop(layer, s, ctype)
+        return self.global_k[layer], self.global_v[layer]
+
+    def ring_forward(self, layer: int, q, k, v, ctype, softmax_scale=None, joint_tensor_key=None,
+                     joint_tensor_value=None, joint_strategy: str = "none"):
+        """q, k, v: (bs, s_local, h, d) fp16.  Returns (out (bs, s_local, h, d) fp16, lse (bs, h, s_local) fp32),
+        the values `_compact_ring_fwd(..., causal=False)` returns."""
+        from .attention import attn_forward, merge_out_and_lse
+        from .ring import _joint_flags
+        shape = k.shape
+        assert v.shape == shape and shape[0] * shape[1] == self.n and shape[2] * shape[3] == self.c
+        is_joint = _joint_flags(joint_tensor_key, joint_tensor_value, joint_strategy, ["front", "rear"])
+        if softmax_scale is None:
+            softmax_scale = q.shape[-1] ** (-0.5)
+        k, v = k.contiguous(), v.contiguous()
+        self.begin(layer, k, v, ctype)
+        out = lse = None
+        W = self.world
+        for s in range(W):
+            if s == 0:
+                kk, vv = k, v
+            else:
+                ks_, vs_ = self.hop(layer, s, ctype)
+                kk, vv = ks_.view(shape), vs_.view(shape)
+            if is_joint and joint_strategy == "rear" and s + 1 == W:
+                kk, vv = torch.cat([kk, joint_tensor_key], dim=1), torch.cat([vv, joint_tensor_value], dim=1)
+            elif is_joint and joint_strategy == "front" and s == 0:
+                kk, vv = torch.cat([joint_tensor_key, kk], dim=1), torch.cat([joint_tensor_value, vv], dim=1)
+            block_out, block_lse = attn_forward(q, kk, vv, 0.0, softmax_scale, causal=False)
+            out, lse = merge_out_and_lse(out, lse, block_out, block_lse)
+        return out.to(q.dtype), lse

@@ -242,6 +242,25 @@ CF_API int cf_sign_decompress_batched_wait(int codec, int batch, const void* con
                                     const void* const* wait_flag, const void* expected,
                                     void* error_word, int64_t N, int64_t C, cf_stream_t stream);
 
+/* ---- consumers right behind the codec kernels ------------------------------------------
+ * cf_lse_merge: the ring's per-hop online-softmax merge, replaces `update_out_and_lse` of
+ * yunchang.ring.utils (third party, pinned `yunchang>=0.6.0`, setup.py:35; call sites
+ * ring.py:193-195):  w = sigmoid(block_lse - lse);  out <- out - w (out - block_out);
+ * lse_out <- lse_in - logsigmoid(lse_in - block_lse).
+ * out (B,S,H,D) fp32, updated in place; block_out (B,S,H,D) fp16; lse_in / block_lse / lse_out
+ * (B,H,S) fp32 (flash-attn's layout), lse_out must not alias lse_in.  D % 4 == 0. */
+CF_API int cf_lse_merge(void* out, const void* block_out, const void* lse_in, const void* block_lse,
+                 void* lse_out, int64_t B, int64_t S, int64_t H, int64_t D, cf_stream_t stream);
+/* cf_error_stats: one pass over two fp16 tensors a (test) and b (reference) of `numel` elements
+ * (multiple of 8, 16-byte aligned): out4 (4 x fp32, device) = { sum (a-b)^2, sum b^2, max |a-b|,
+ * max |b| } -- the per-step max-abs / relative-L2 / PSNR inputs (replaces the eager torch
+ * reductions of stats.py:44-120).  Deterministic (fixed reduction order, fp64 partials).
+ * workspace: cf_error_stats_workspace_bytes() bytes, 256-byte aligned, ZERO-initialised once by
+ * the caller (the kernel leaves it ready for the next call). */
+CF_API size_t cf_error_stats_workspace_bytes(void);
+CF_API int cf_error_stats(const void* a, const void* b, int64_t numel, void* out4, void* workspace,
+                   size_t workspace_bytes, cf_stream_t stream);
+
 /* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside the call) ---------
  * x_host/base_host/recon_host are HOST (ideally pinned) buffers; payload_host receives /
  * supplies the flat fp16 wire payload [codes | U | V] (main.py:149-152).  dev_scratch is a
