@@ -12,6 +12,11 @@ global K/V buffers attention reads.  Synthetic AR(1) activations with per-channe
 scales (no network: no real weights / prompts); step 0 is the reference's uncompressed
 WARMUP step and is not timed.
 
+`--workload` selects the other BASELINE.json configs as extra bench lines (same metric, same
+kernels): cogvideox5b_ring (configs[2]: 42 layers, bs 2 x 17552 tokens, compressed ring attention --
+origins consumed hop by hop, engine.RingExchangeEngine), pixart_patch_parallel / sd3_patch_parallel
+(configs[3]: bs 2 x 4096 tokens, C = 1152 / 1536).
+
   python bench.py [--gpus N --steps K --warmup W]            (torchrun for N > 1)
   python bench.py --impl reference ...                        CPU arm (oracle port of the
                                                               reference's eager torch path)
@@ -38,6 +43,33 @@ import torch.distributed as dist  # noqa: E402
 LAYERS, SEQ, CH = 57, 4096 + 512, 3072
 METRIC = "compress+exchange GB/s (raw fp16 K/V bytes reconstructed per second, all ranks), FLUX 1024^2 patch parallel"
 UNIT = "GB/s"
+WORKLOAD, MODE = "flux1024_patch_parallel", "patch"
+# BASELINE.json configs.  rows = bs * tokens of the GLOBAL sequence; every rank owns rows / N.
+# The default (configs[1], the one `metric` is quoted on) is the headline; the others are extra bench lines.
+WORKLOADS = {
+    # FLUX.1-dev 1024^2: 57 layers, 4096 image + 512 text tokens, 24 x 128 channels, patch-parallel all-gather
+    "flux1024_patch_parallel": dict(layers=57, rows=4096 + 512, ch=3072, mode="patch",
+                                    what="FLUX 1024^2 patch parallel"),
+    # CogVideoX-5b 49 frames 720x480: 42 layers, bs 2 (CFG) x 17550 tokens (padded to 17552), 48 x 64 channels,
+    # compressed ring attention (configs[2])
+    "cogvideox5b_ring": dict(layers=42, rows=2 * 17552, ch=3072, mode="ring",
+                             what="CogVideoX-5b 49x720x480 compressed ring attention"),
+    # PixArt-alpha / SD3-medium 1024^2: bs 2 x 4096 tokens, 16 x 72 / 24 x 64 channels, patch parallel (configs[3])
+    "pixart_patch_parallel": dict(layers=28, rows=2 * 4096, ch=1152, mode="patch",
+                                  what="PixArt-alpha 1024^2 patch parallel"),
+    "sd3_patch_parallel": dict(layers=24, rows=2 * 4096, ch=1536, mode="patch",
+                               what="SD3-medium 1024^2 patch parallel"),
+}
+
+
+def select_workload(name, layers=None):
+    """Point the module-level shape constants at `name` (the default leaves them untouched)."""
+    global LAYERS, SEQ, CH, METRIC, WORKLOAD, MODE
+    w = WORKLOADS[name]
+    WORKLOAD, MODE = name, w["mode"]
+    LAYERS, SEQ, CH = w["layers"], w["rows"], w["ch"]
+    METRIC = ("compress+exchange GB/s (raw fp16 K/V bytes reconstructed per second, all ranks), " + w["what"])
+    return layers if layers is not None else LAYERS
 
 
 def parse():
@@ -47,7 +79,8 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--codec", default="binary", choices=["binary", "int2"])
-    p.add_argument("--layers", type=int, default=LAYERS)
+    p.add_argument("--workload", default="flux1024_patch_parallel", choices=sorted(WORKLOADS))
+    p.add_argument("--layers", type=int, default=None, help="default: the workload's layer count")
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     p.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                    help="payload exchange for N > 1: one-sided NVLink puts (p2p) or NCCL all-gather")
@@ -220,7 +253,7 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": args.layers, "seq": SEQ,
+        "config": {"workload": WORKLOAD, "codec": args.codec, "layers": args.layers, "seq": SEQ,
                    "channels": CH, "world": world, "shard_rows": SEQ // world, "launch_mode": "cpu (no GPU work)",
                    "transport": "in-process (all ranks' work on this host)", "l2": "n/a"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
@@ -248,6 +281,7 @@ def main():
         import faulthandler
         faulthandler.dump_traceback_later(args.hang_dump, exit=True)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.layers = select_workload(args.workload, args.layers)
     if args.impl == "reference":
         run_reference(args, max(world, args.gpus), rank)
         return
@@ -259,11 +293,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    from compactfusion_b200.engine import PatchGatherEngine
+    from compactfusion_b200.engine import PatchGatherEngine, RingExchangeEngine
     from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
     ctype = T.BINARY if args.codec == "binary" else T.INT2
     n_local, layers = SEQ // world, args.layers
-    eng = PatchGatherEngine(layers, n_local, CH, group=None, device=device, transport=args.transport)
+    # ring workloads consume the origins hop by hop (one flag-waiting decompress launch per origin);
+    # patch workloads reconstruct all origins in one launch
+    engine_cls = RingExchangeEngine if MODE == "ring" else PatchGatherEngine
+    eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport)
     transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
     note(rank, f"transport: {transport}")
     if transport == "nccl" and not args.no_graph:
@@ -400,8 +437,18 @@ def main():
         kernels[-1]["nvlink_gbs"] = (world - 1) * slot_bytes / kernels[-1]["avg_launch_us"] / 1e3
         kernels[-1]["nvlink_frac_of_770"] = kernels[-1]["nvlink_gbs"] / 770.0
     # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
-    n_launch_per_call = (2 * world + 15) // 16
-    time_kernel(apply_name, lambda l: eng.decompress(l, ctype),
+    if MODE == "ring":
+        n_launch_per_call = world
+
+        def dec(l):
+            for r in range(world):
+                eng.decompress(l, ctype, origins=(eng.hop_origin(r),))
+    else:
+        n_launch_per_call = (2 * world + 15) // 16
+
+        def dec(l):
+            eng.decompress(l, ctype)
+    time_kernel(apply_name, dec,
                 2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
     note(rank, "per-kernel timing done")
     kernels[-1]["avg_launch_us"] /= n_launch_per_call
@@ -491,10 +538,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "flux1024_patch_parallel", "codec": args.codec, "layers": layers, "seq": SEQ,
+            "config": {"workload": WORKLOAD, "exchange": MODE, "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
                        "transport": transport + (" (fused into the codec kernels)" if world > 1 and eng.fused(ctype) else ""),
-                       "l2": "inputs larger than L2 (each step streams > 6 GB of distinct K/V + cache)"},
+                       "l2": f"inputs larger than L2 (each step touches {(1 + world) * layers * 2 * n_local * CH * 2 / 1e9:.1f} GB "
+                             "of distinct K/V inputs + cached bases per rank)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
             "p2p_wait_timeouts": bool(eng.p2p_error()),
         }))
