@@ -78,7 +78,9 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--codec", default="binary", choices=["binary", "int2"])
+    p.add_argument("--codec", default="binary", choices=["binary", "int2", "raw"],
+                   help="raw = the uncompressed exchange of the same K/V (NCCL all-gather of fp16 shards, what "
+                        "xDiT does without the plugin): a comparison line, none of our kernels run")
     p.add_argument("--workload", default="flux1024_patch_parallel", choices=sorted(WORKLOADS))
     p.add_argument("--layers", type=int, default=None, help="default: the workload's layer count")
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
@@ -239,6 +241,7 @@ def cpu_baseline(codec, world, layers, sample_layers, budget_s=12.0):
 def run_reference(args, world, rank):
     if rank != 0:
         return
+    assert args.codec != "raw", "--codec raw is a GPU comparison line; the CPU arm runs the compressed path"
     per = []
     for _ in range(args.warmup):
         cpu_rank_step_seconds(args.codec, world, args.cpu_sample_layers)
@@ -295,13 +298,16 @@ def main():
 
     from compactfusion_b200.engine import PatchGatherEngine, RingExchangeEngine
     from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
-    ctype = T.BINARY if args.codec == "binary" else T.INT2
+    raw = args.codec == "raw"
+    ctype = {"binary": T.BINARY, "int2": T.INT2, "raw": T.WARMUP}[args.codec]
     n_local, layers = SEQ // world, args.layers
     # ring workloads consume the origins hop by hop (one flag-waiting decompress launch per origin);
     # patch workloads reconstruct all origins in one launch
     engine_cls = RingExchangeEngine if MODE == "ring" else PatchGatherEngine
     eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport)
     transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
+    if raw and world > 1:
+        transport = "nccl"  # all_gather_into_tensor of the raw fp16 shards (engine.warmup)
     note(rank, f"transport: {transport}")
     if transport == "nccl" and not args.no_graph:
         # NCCL collectives inside the captured step hang on replay on this stack (torch 2.11 / NCCL 2.28):
@@ -366,107 +372,109 @@ def main():
     ms_per_step = ms / args.steps
     value = job_bytes(layers, world) / (ms_per_step * 1e-3) / 1e9
 
-    # ---- per-kernel durations and the roofline of the dominant one ---------------------------
-    # Every kernel of the step is timed on its own: a CUDA graph holding that kernel's launch for
-    # ALL layers (distinct buffers per layer: `layers` x tens of MB >> 126 MB L2, so every launch
-    # is cold) is replayed between two CUDA events on the launching stream.  No per-launch events
-    # (they add a front-end round trip of several us to a 10-20 us kernel).
-    from compactfusion_b200 import _native as nv
-    e_tensor = n_local * CH
-    per_byte = 8 if args.codec == "binary" else 4
-    vsel = args.steps % versions
-    part_b = 148 // 2  # column/token partials written by pass 1 (one row block per CTA)
-    kernels = []
+    roofline = None
+    if not raw:
+        # ---- per-kernel durations and the roofline of the dominant one ---------------------------
+        # Every kernel of the step is timed on its own: a CUDA graph holding that kernel's launch for
+        # ALL layers (distinct buffers per layer: `layers` x tens of MB >> 126 MB L2, so every launch
+        # is cold) is replayed between two CUDA events on the launching stream.  No per-launch events
+        # (they add a front-end round trip of several us to a 10-20 us kernel).
+        from compactfusion_b200 import _native as nv
+        e_tensor = n_local * CH
+        per_byte = 8 if args.codec == "binary" else 4
+        vsel = args.steps % versions
+        part_b = 148 // 2  # column/token partials written by pass 1 (one row block per CTA)
+        kernels = []
 
-    def time_kernel(name, fn, algo_bytes, reps=3):
-        barrier()
-        for layer in range(layers):
-            fn(layer)
-        torch.cuda.synchronize()
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for layer in range(layers):
-                    fn(layer)
-            run = g.replay
-        except Exception:
+        def time_kernel(name, fn, algo_bytes, reps=3):
+            barrier()
+            for layer in range(layers):
+                fn(layer)
             torch.cuda.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for layer in range(layers):
+                        fn(layer)
+                run = g.replay
+            except Exception:
+                torch.cuda.synchronize()
 
-            def run():
-                for layer in range(layers):
-                    fn(layer)
-        run()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
+                def run():
+                    for layer in range(layers):
+                        fn(layer)
             run()
-        b.record()
-        torch.cuda.synchronize()
-        us = a.elapsed_time(b) * 1e3 / (reps * layers)
-        kernels.append({"kernel": name, "avg_launch_us": us, "algorithmic_bytes_per_launch": algo_bytes,
-                        "achieved": algo_bytes / us / 1e3})
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                run()
+            b.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / (reps * layers)
+            kernels.append({"kernel": name, "avg_launch_us": us, "algorithmic_bytes_per_launch": algo_bytes,
+                            "achieved": algo_bytes / us / 1e3})
 
-    stats_name = "k_delta_stats_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_delta_stats"
-    apply_name = "k_apply_codes_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_apply_codes"
-    fused = world > 1 and eng.fused(ctype)
-    comp = eng.compress_put if fused else eng.compress
-    fan = world if fused else 1  # fused put: codes and scales are stored to all W receive slots (W-1 over NVLink)
-    # pass 1 over K and V of this rank: read x and base, write sign bits (BINARY) + partial sums
-    time_kernel(stats_name, lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
-                2 * (4 * e_tensor + (fan * e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
-    time_kernel("k_finalize_scales", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
-                2 * (4 * part_b * CH + 2 * n_local + fan * 2 * (n_local + CH)))
-    if fused:
-        for k_ in kernels:
-            k_["fused_put"] = True
-            k_["nvlink_bytes_per_launch"] = (world - 1) * 2 * (
-                (e_tensor // 8 if args.codec == "binary" else 0) if k_["kernel"] == stats_name else 2 * (n_local + CH))
-    if args.codec == "int2":
-        time_kernel("k_int2_encode_tma", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
-                    2 * (4 * e_tensor + fan * e_tensor // 4 + 2 * (n_local + CH)))
+        stats_name = "k_delta_stats_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_delta_stats"
+        apply_name = "k_apply_codes_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_apply_codes"
+        fused = world > 1 and eng.fused(ctype)
+        comp = eng.compress_put if fused else eng.compress
+        fan = world if fused else 1  # fused put: codes and scales are stored to all W receive slots (W-1 over NVLink)
+        # pass 1 over K and V of this rank: read x and base, write sign bits (BINARY) + partial sums
+        time_kernel(stats_name, lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
+                    2 * (4 * e_tensor + (fan * e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
+        time_kernel("k_finalize_scales", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
+                    2 * (4 * part_b * CH + 2 * n_local + fan * 2 * (n_local + CH)))
         if fused:
-            kernels[-1]["fused_put"] = True
-            kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * 2 * (e_tensor // 4)
-    if transport == "p2p" and not fused:
-        # one-sided exchange: this rank's [K payload | V payload] stored into all W receive slots; W-1 of them
-        # cross NVLink (measured peer-copy peak 770 GB/s per direction, B200_PROFILING.md)
-        slot_bytes = 2 * (e_tensor // per_byte + 2 * (n_local + CH))
-        time_kernel("k_p2p_put", lambda l: eng.gather(ctype, l), (world + 1) * slot_bytes)
-        kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * slot_bytes
-        kernels[-1]["nvlink_gbs"] = (world - 1) * slot_bytes / kernels[-1]["avg_launch_us"] / 1e3
-        kernels[-1]["nvlink_frac_of_770"] = kernels[-1]["nvlink_gbs"] / 770.0
-    # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
-    if MODE == "ring":
-        n_launch_per_call = world
+            for k_ in kernels:
+                k_["fused_put"] = True
+                k_["nvlink_bytes_per_launch"] = (world - 1) * 2 * (
+                    (e_tensor // 8 if args.codec == "binary" else 0) if k_["kernel"] == stats_name else 2 * (n_local + CH))
+        if args.codec == "int2":
+            time_kernel("k_int2_encode_tma", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
+                        2 * (4 * e_tensor + fan * e_tensor // 4 + 2 * (n_local + CH)))
+            if fused:
+                kernels[-1]["fused_put"] = True
+                kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * 2 * (e_tensor // 4)
+        if transport == "p2p" and not fused:
+            # one-sided exchange: this rank's [K payload | V payload] stored into all W receive slots; W-1 of them
+            # cross NVLink (measured peer-copy peak 770 GB/s per direction, B200_PROFILING.md)
+            slot_bytes = 2 * (e_tensor // per_byte + 2 * (n_local + CH))
+            time_kernel("k_p2p_put", lambda l: eng.gather(ctype, l), (world + 1) * slot_bytes)
+            kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * slot_bytes
+            kernels[-1]["nvlink_gbs"] = (world - 1) * slot_bytes / kernels[-1]["avg_launch_us"] / 1e3
+            kernels[-1]["nvlink_frac_of_770"] = kernels[-1]["nvlink_gbs"] / 770.0
+        # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
+        if MODE == "ring":
+            n_launch_per_call = world
 
-        def dec(l):
-            for r in range(world):
-                eng.decompress(l, ctype, origins=(eng.hop_origin(r),))
-    else:
-        n_launch_per_call = (2 * world + 15) // 16
+            def dec(l):
+                for r in range(world):
+                    eng.decompress(l, ctype, origins=(eng.hop_origin(r),))
+        else:
+            n_launch_per_call = (2 * world + 15) // 16
 
-        def dec(l):
-            eng.decompress(l, ctype)
-    time_kernel(apply_name, dec,
-                2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
-    note(rank, "per-kernel timing done")
-    kernels[-1]["avg_launch_us"] /= n_launch_per_call
-    kernels[-1]["algorithmic_bytes_per_launch"] //= n_launch_per_call
-    peak, peak_src = measured_hbm_peak()
-    k_total = sum(k["avg_launch_us"] * (n_launch_per_call if k["kernel"] == apply_name else 1) for k in kernels)
-    for k in kernels:
-        mult = n_launch_per_call if k["kernel"] == apply_name else 1
-        k["frac"] = k["achieved"] / peak
-        k["share_of_kernel_time"] = k["avg_launch_us"] * mult / k_total
-    dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
-    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": ncu_traffic(dom["kernel"], args.codec, n_local, world), "kernel": dom["kernel"],
-                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
-                "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_kernel_time"],
-                "peak_source": peak_src, "kernels": kernels,
-                "method": "each kernel alone: one CUDA graph with its launch for all layers (cold buffers), "
-                          "replayed 3x between two CUDA events"}
+            def dec(l):
+                eng.decompress(l, ctype)
+        time_kernel(apply_name, dec,
+                    2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
+        note(rank, "per-kernel timing done")
+        kernels[-1]["avg_launch_us"] /= n_launch_per_call
+        kernels[-1]["algorithmic_bytes_per_launch"] //= n_launch_per_call
+        peak, peak_src = measured_hbm_peak()
+        k_total = sum(k["avg_launch_us"] * (n_launch_per_call if k["kernel"] == apply_name else 1) for k in kernels)
+        for k in kernels:
+            mult = n_launch_per_call if k["kernel"] == apply_name else 1
+            k["frac"] = k["achieved"] / peak
+            k["share_of_kernel_time"] = k["avg_launch_us"] * mult / k_total
+        dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
+        roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": ncu_traffic(dom["kernel"], args.codec, n_local, world), "kernel": dom["kernel"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                    "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_kernel_time"],
+                    "peak_source": peak_src, "kernels": kernels,
+                    "method": "each kernel alone: one CUDA graph with its launch for all layers (cold buffers), "
+                              "replayed 3x between two CUDA events"}
 
     # ---- e2e: pinned host activations -> H2D -> exchange -> D2H of the reconstructed K/V -------
     e2e = None
@@ -527,7 +535,7 @@ def main():
 
     note(rank, "e2e done")
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not raw:
         try:
             cpu = cpu_baseline(args.codec, world, layers, args.cpu_sample_layers)
         except Exception as e:
@@ -535,6 +543,7 @@ def main():
 
     if rank == 0:
         print(json.dumps({
+            **({"impl": "uncompressed_baseline"} if raw else {}),
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
