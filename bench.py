@@ -494,7 +494,6 @@ def main():
 
         def e2e_step():
             in_done = [None, None]
-            comp_done = None
             for layer in range(e2e_layers):
                 s = layer & 1
                 with torch.cuda.stream(copy_in):
@@ -503,8 +502,6 @@ def main():
                     in_done[s] = torch.cuda.Event()
                     in_done[s].record(copy_in)
                 main_s.wait_event(in_done[s])
-                if comp_done is not None:
-                    pass
                 gk, gv = eng.exchange(layer, dk[s], dv[s], ctype)
                 done = torch.cuda.Event()
                 done.record(main_s)
@@ -530,8 +527,8 @@ def main():
                "h2d_bytes_per_step": world * layers * 2 * n_local * CH * 2,
                "d2h_bytes_per_step": world * layers * 2 * world * n_local * CH * 2,
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "path": "pinned host K/V -> H2D -> PatchGatherEngine.exchange (C-ABI batched kernels + NCCL) -> "
-                       "D2H of reconstructed global K/V, double-buffered over 3 streams"}
+               "path": f"pinned host K/V -> H2D -> {engine_cls.__name__}.exchange (C-ABI batched kernels, transport "
+                       f"{transport}) -> D2H of reconstructed global K/V, double-buffered over 3 streams"}
 
     note(rank, "e2e done")
     cpu = None
