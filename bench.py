@@ -193,42 +193,47 @@ def ncu_traffic(kernel, codec, n_local, world):
 # --------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference's eager torch path
 # --------------------------------------------------------------------------------------------
-def cpu_rank_step_seconds(codec, world, sample_layers, reps=1):
-    """Time one rank's share of `sample_layers` layers on the host: compress own K and V shard
-    (no cache update) + decompress all `world` origins (cache update), main.py:390-420."""
-    from oracle.state import OracleCompact
-    n_local = SEQ // world
-    torch.set_num_threads(os.cpu_count() or 1)
-    g = torch.Generator().manual_seed(0)
-    ranks = OracleCompact(residual=1, ef=True, fastpath=True)
-    xs0, xs1 = [], []
-    for i in range(sample_layers * 2):
-        x0 = torch.randn(n_local, CH, generator=g)
-        xs0.append(x0.half())
-        xs1.append((0.97 * x0 + 0.243 * torch.randn(n_local, CH, generator=g)).half())
-    # warm-up step: bases for every origin (all origins carry the same synthetic shard)
-    for i, x in enumerate(xs0):
-        for r in range(world):
-            ranks.decompress(f"{i}-{r}", x, "warmup", x.shape, update_cache=True)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        for i, x in enumerate(xs1):
-            payload = ranks.compress(f"{i}-0", x, codec, update_cache=False)
+class CpuRankSample:
+    """One rank's share of `sample_layers` layers on the host (oracle port of the reference's eager
+    torch path): compress own K and V shard (no cache update) + decompress all `world` origins (cache
+    update), main.py:390-420.  Inputs and the warm-up step are prepared once; `step()` is the timed unit."""
+
+    def __init__(self, codec, world, sample_layers):
+        from oracle.state import OracleCompact
+        self.codec, self.world = codec, world
+        n_local = SEQ // world
+        torch.set_num_threads(os.cpu_count() or 1)
+        g = torch.Generator().manual_seed(0)
+        self.ranks = OracleCompact(residual=1, ef=True, fastpath=True)
+        self.cur, self.nxt = [], []
+        for _ in range(sample_layers * 2):
+            x0 = torch.randn(n_local, CH, generator=g)
+            self.cur.append(x0.half())
+            self.nxt.append((0.97 * x0 + 0.243 * torch.randn(n_local, CH, generator=g)).half())
+        # warm-up step: bases for every origin (all origins carry the same synthetic shard)
+        for i, x in enumerate(self.cur):
             for r in range(world):
-                ranks.decompress(f"{i}-{r}", payload, codec, x.shape, update_cache=True)
+                self.ranks.decompress(f"{i}-{r}", x, "warmup", x.shape, update_cache=True)
+
+    def step(self):
+        """Seconds for one compressed step of the sampled layers (inputs alternate between two versions)."""
+        t0 = time.perf_counter()
+        for i, x in enumerate(self.nxt):
+            payload = self.ranks.compress(f"{i}-0", x, self.codec, update_cache=False)
+            for r in range(self.world):
+                self.ranks.decompress(f"{i}-{r}", payload, self.codec, x.shape, update_cache=True)
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        xs0, xs1 = xs1, xs0
-    return best
+        self.cur, self.nxt = self.nxt, self.cur
+        return dt
 
 
 def cpu_baseline(codec, world, layers, sample_layers, budget_s=12.0):
-    """Bounded sample: repeat the sampled layers until ~budget_s of CPU work, keep the mean."""
-    cpu_rank_step_seconds(codec, world, sample_layers)  # page-in / thread-pool warm-up
-    t_all, times = time.perf_counter(), []
-    while time.perf_counter() - t_all < budget_s and len(times) < 200:
-        times.append(cpu_rank_step_seconds(codec, world, sample_layers))
+    """Bounded sample: repeat the sampled layers for ~budget_s of CPU work, keep the mean."""
+    sample = CpuRankSample(codec, world, sample_layers)
+    sample.step()  # page-in / thread-pool warm-up
+    times = []
+    while sum(times) < budget_s and len(times) < 500:
+        times.append(sample.step())
     dt = sum(times) / len(times)
     step_s = dt * layers / sample_layers * world  # all `world` ranks' work on this host's cores
     return {"value": job_bytes(layers, world) / step_s / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -242,11 +247,10 @@ def run_reference(args, world, rank):
     if rank != 0:
         return
     assert args.codec != "raw", "--codec raw is a GPU comparison line; the CPU arm runs the compressed path"
-    per = []
+    cpu = CpuRankSample(args.codec, world, args.cpu_sample_layers)
     for _ in range(args.warmup):
-        cpu_rank_step_seconds(args.codec, world, args.cpu_sample_layers)
-    for _ in range(args.steps):
-        per.append(cpu_rank_step_seconds(args.codec, world, args.cpu_sample_layers))
+        cpu.step()
+    per = [cpu.step() for _ in range(args.steps)]
     dt = sum(per) / len(per)
     step_s = dt * args.layers / args.cpu_sample_layers * world
     val = job_bytes(args.layers, world) / step_s / 1e9
