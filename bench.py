@@ -280,6 +280,33 @@ def note(rank, msg):
         print(f"[bench r{rank} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+def p2p_probe(engine_cls, n_local, ctype, device):
+    """N > 1: run a 2-layer WARMUP + compressed step over the one-sided transport and check that no
+    device-side flag wait timed out, BEFORE the 57-layer engine is built on it.  A transport that does
+    not deliver would otherwise spin ~2 s in every reconstruct launch of the timed region.  The verdict
+    is all-reduced (MIN), so every rank takes the same decision.  Returns (ok, reason)."""
+    from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+    ok, why = 1, ""
+    try:
+        probe = engine_cls(2, n_local, CH, group=None, device=device, transport="auto")
+        if probe.prepare(ctype) != "p2p":
+            ok, why = 0, "p2p setup failed (CUDA IPC)"
+        else:
+            g = torch.Generator(device=device).manual_seed(7 + dist.get_rank())
+            xs = [[torch.randn(n_local, CH, generator=g, device=device).half() for _ in range(2)] for _ in range(2)]
+            probe.step(xs[0], xs[0], T.WARMUP)
+            for _ in range(2):  # twice: the second step reuses every slot and flag
+                probe.step(xs[1], xs[1], ctype)
+            torch.cuda.synchronize()
+            if probe.p2p_error():
+                ok, why = 0, "a device-side flag wait timed out in the probe step"
+    except Exception as e:  # noqa: BLE001 -- any failure means: do not use this transport
+        ok, why = 0, f"{type(e).__name__}: {e}"
+    t = torch.tensor([ok], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item()), why
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -308,6 +335,12 @@ def main():
     # ring workloads consume the origins hop by hop (one flag-waiting decompress launch per origin);
     # patch workloads reconstruct all origins in one launch
     engine_cls = RingExchangeEngine if MODE == "ring" else PatchGatherEngine
+    probe_note = None
+    if world > 1 and args.transport == "auto" and not raw:
+        ok, why = p2p_probe(engine_cls, n_local, ctype, device)
+        if not ok:
+            args.transport, probe_note = "nccl", "one-sided transport rejected by the probe step: " + (why or "a peer failed")
+        note(rank, f"p2p probe: {'ok' if ok else probe_note}")
     eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport)
     transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
     if raw and world > 1:
@@ -551,6 +584,7 @@ def main():
             "config": {"workload": WORKLOAD, "exchange": MODE, "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
                        "transport": transport + (" (fused into the codec kernels)" if world > 1 and eng.fused(ctype) else ""),
+                       **({"transport_note": probe_note} if probe_note else {}),
                        "l2": f"inputs larger than L2 (each step touches {(1 + world) * layers * 2 * n_local * CH * 2 / 1e9:.1f} GB "
                              "of distinct K/V inputs + cached bases per rank)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
