@@ -149,7 +149,8 @@ def _payload_views(payload: torch.Tensor, n: int, c: int, compress_type, k: int 
 
 def _new_base_buffer(key, base):
     """Where the updated base goes: in place when allowed and the cache owns `base`."""
-    if _inplace and key in _owned and base is not None:
+    # (with log_stats the old base is still needed after the update: never alias it)
+    if _inplace and key in _owned and base is not None and not _config.log_compress_stats:
         return base
     return torch.empty_like(base)
 
@@ -245,7 +246,11 @@ def compact_compress(cache_key, x: torch.Tensor, compress_type: COMPACT_COMPRESS
         return _compact_compress_fastpath(cache_key, x, compress_type, update_cache, rank)
 
     if residual == 0:
-        return _compress_fn(x, compress_type, rank)
+        compressed = _compress_fn(x, compress_type, rank)
+        if _config.log_compress_stats:  # main.py:216-228
+            stats_log().log(cache_key, None, None, x, _decompress_fn(compressed, compress_type, x.shape, rank),
+                            compressed, 0)
+        return compressed
     if residual == 1:
         base = _cache.get_base(cache_key)
         fused = _residual1_fused(x, base, compress_type, rank)
@@ -260,6 +265,8 @@ def compact_compress(cache_key, x: torch.Tensor, compress_type: COMPACT_COMPRESS
                 _put(cache_key, reconstructed)
             else:
                 _put(cache_key, x, owned=False)  # main.py:233
+        if _config.log_compress_stats:  # main.py:234-245
+            stats_log().log(cache_key, base, None, x, reconstructed, compressed, 1)
         return compressed
     if residual == 2:
         base = _cache.get_base(cache_key)
@@ -267,8 +274,11 @@ def compact_compress(cache_key, x: torch.Tensor, compress_type: COMPACT_COMPRESS
         delta_delta = x - base - delta_base
         compressed = _compress_fn(delta_delta, compress_type, rank)
         recv_dd = _decompress_fn(compressed, compress_type, x.shape, rank)
+        new_base = base + delta_base + recv_dd
         if update_cache:
-            _put(cache_key, base + delta_base + recv_dd, _decay_delta_base(delta_base + recv_dd))
+            _put(cache_key, new_base, _decay_delta_base(delta_base + recv_dd))
+        if _config.log_compress_stats:  # main.py:257-268
+            stats_log().log(cache_key, base, delta_base, x, new_base, compressed, 2)
         return compressed
     raise ValueError("Invalid compress_residual value")
 

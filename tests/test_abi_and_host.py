@@ -259,3 +259,83 @@ def test_shim_installs_under_reference_module_path():
     finally:
         shim.uninstall()
     assert "xfuser.compact.main" not in sys.modules
+
+
+def test_stats_logger_host_logic(monkeypatch, tmp_path, capsys):
+    """StatsLogger bookkeeping (record fields, deferred read-back, similarity from norms, summaries, dump
+    formats of plot.py:413-560) with the device reduction replaced by torch-CPU IN THE TEST ONLY."""
+    from compactfusion_b200 import stats as st
+
+    def cpu_pair(self, a, b):
+        if not self._tables or self._used == st._CHUNK_ROWS:
+            self._tables.append(torch.zeros((st._CHUNK_ROWS, 4), dtype=torch.float32))
+            self._used = 0
+        d = a.double() - b.double()
+        self._tables[-1][self._used] = torch.tensor([float((d * d).sum()), float((b.double() ** 2).sum()),
+                                                     float(d.abs().max()), float(b.double().abs().max())])
+        self._used += 1
+        return (len(self._tables) - 1, self._used - 1)
+
+    monkeypatch.setattr(st.StatsLogger, "_pair", cpu_pair)
+    monkeypatch.setattr(st, "_CHUNK_ROWS", 5)  # several tables
+    st.stats_clear()
+    g = torch.Generator().manual_seed(3)
+    xs = {k: [torch.randn(16, 32, generator=g).half()] for k in ("0-0-k", "0-0-v")}
+    for k in xs:
+        for _ in range(3):
+            xs[k].append((0.9 * xs[k][-1].float() + 0.3 * torch.randn(16, 32, generator=g)).half())
+    want = {}
+    for k, seq in xs.items():
+        base = seq[0]
+        for t in range(1, 4):
+            x = seq[t]
+            recv = (base.float() + 0.5 * (x.float() - base.float())).half()
+            payload = torch.zeros(x.numel() // 8, dtype=torch.half)
+            st.log(k, base, None, x, recv, payload, 1)
+            want[(k, t - 1)] = dict(error=float(torch.norm(x.double() - recv.double())),
+                                    activation_norm=float(torch.norm(x.double())),
+                                    delta_norm=float(torch.norm(x.double() - base.double())),
+                                    prev=seq[t - 1] if t > 1 else None, x=x)
+            base = recv
+    logger = st.stats_log()
+    assert logger._dirty
+    stats = logger.stats
+    assert not logger._dirty and set(stats) == set(xs)
+    for (k, i), w in want.items():
+        r = stats[k][i]
+        for name in ("error", "activation_norm", "delta_norm"):
+            assert abs(r[name] - w[name]) <= 1e-5 * max(1.0, w[name]), (k, i, name)
+        assert r["residual"] == 1 and r["original_size_bytes"] == 16 * 32 * 2 and r["compressed_size_bytes"] == 128
+        assert r["total_error"] is None and r["delta_delta_norm"] is None
+        assert abs(r["rel_l2"] - w["error"] / w["activation_norm"]) < 1e-6
+        if w["prev"] is None:
+            assert r["activation_similarity"] is None and r["delta_before_feedback_norm"] is None
+        else:
+            cos = float(torch.nn.functional.cosine_similarity(w["x"].double().flatten(), w["prev"].double().flatten(), dim=0))
+            assert abs(r["activation_similarity"] - cos) < 1e-5
+            assert abs(r["delta_before_feedback_norm"] - float(torch.norm(w["x"].double() - w["prev"].double()))) < 1e-4
+    assert logger.total_original_volume == 6 * 1024 and logger.total_compressed_volume == 6 * 128
+    st.stats_verbose()
+    st.stats_verbose_steps(steps=[0, 7], keys=["0-0-k"])
+    out = capsys.readouterr().out
+    assert "Ratio 8.00x" in out and "avg comp error" in out and "Step 7 is out of range" in out and "=== Step 0 ===" in out
+    d = st.dump_err_vs_steps(str(tmp_path))
+    saved = torch.load(os.path.join(tmp_path, "average_error_vs_steps.pt"))
+    assert saved == d and saved["steps"] == [0, 1, 2] and saved["avg_total_errors"] == [None] * 3
+    assert abs(saved["avg_comp_errors"][1] - (want[("0-0-k", 1)]["error"] + want[("0-0-v", 1)]["error"]) / 2) < 1e-4
+    n = st.dump_norms_sim_vs_steps(str(tmp_path))
+    assert n["avg_act_similarities"][0] is None and n["avg_act_similarities"][1] is not None
+    assert os.path.exists(os.path.join(tmp_path, "average_norms_and_similarity_vs_steps.pt"))
+    # residual 2 adds the delta-delta norm; a None reconstruction leaves the error fields empty
+    st.stats_clear()
+    x, base, db = xs["0-0-k"][1], xs["0-0-k"][0], (0.1 * xs["0-0-v"][0].float()).half()
+    st.log("1-0-k", base, db, x, None, None, 2)
+    r = st.stats_log().stats["1-0-k"][0]
+    assert r["error"] is None and r["compressed_size_bytes"] == 0
+    assert abs(r["delta_delta_norm"] - float(torch.norm(x.double() - (base + db).double()))) < 1e-4
+    assert abs(r["activation_norm"] - float(torch.norm(x.double()))) < 1e-4
+    with pytest.raises(ValueError):
+        st.log("1-0-k", base, None, x, x, None, 3)
+    st.stats_clear()
+    st.stats_verbose()
+    assert "No statistics logged." in capsys.readouterr().out

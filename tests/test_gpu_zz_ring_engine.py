@@ -176,3 +176,60 @@ def test_two_gpu_ring_engine(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-4000:]
+
+
+@pytest.mark.parametrize("mode", ["fastpath_binary", "sim_int4_r1", "lowrank_r2"])
+def test_log_stats_through_the_plugin_api(mode, tmp_path, capsys):
+    """CompactConfig(log_stats=True): compact_compress records error / norm figures on the GPU without a
+    synchronisation per call; the read-back equals torch reductions of the same tensors (stats.py:107-328)."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200 import stats as st
+    T = cf.COMPACT_COMPRESS_TYPE
+    kw, ctype = {
+        "fastpath_binary": (dict(residual=1, ef=True, fastpath=True, comp_rank=-1), T.BINARY),
+        "sim_int4_r1": (dict(residual=1, ef=True, simulate=True, comp_rank=-1), T.INT4),
+        "lowrank_r2": (dict(residual=2, ef=True, comp_rank=8, delta_decay_factor=0.5), T.LOW_RANK),
+    }[mode]
+    n, c, steps = 256, 512, 5
+    shape = (1, n, 8, c // 8)
+    g = torch.Generator().manual_seed(11)
+    xs = [torch.randn(n, c, generator=g)]
+    for _ in range(steps - 1):
+        xs.append(0.95 * xs[-1] + 0.3 * torch.randn(n, c, generator=g))
+    xs = [x.half().view(shape).to(dev) for x in xs]
+    cf.compact_init(cf.CompactConfig(enabled=True, log_stats=True, compress_func=lambda l, s: ctype, **kw))
+    cf.compact_set_inplace(True)  # must not alias the old base while it is being logged
+    try:
+        want = []
+        warm = 2 if kw["residual"] == 2 else 1
+        for t, x in enumerate(xs):
+            cf.compact_set_step(t)
+            ct = ctype if t >= warm else T.WARMUP
+            base = cf.compact_cache().get_base("0-0-k")
+            base = None if base is None else base.clone()
+            comp = cf.compact_compress("0-0-k", x, ct, update_cache=True)
+            if ct != T.WARMUP:
+                new_base = cf.compact_cache().get_base("0-0-k")
+                x2 = x.view(n, c).double()
+                want.append(dict(error=float(torch.norm(x2 - new_base.double())), activation_norm=float(torch.norm(x2)),
+                                 delta_norm=float(torch.norm(x2 - base.double())), comp_bytes=comp.numel() * 2,
+                                 max_abs=float((x2 - new_base.double()).abs().max())))
+        recs = st.stats_log().stats["0-0-k"]
+        assert len(recs) == len(want) == steps - warm
+        for r, w in zip(recs, want):
+            for name in ("error", "activation_norm", "delta_norm"):
+                assert abs(r[name] - w[name]) <= 2e-5 * w[name], (mode, name, r[name], w[name])
+            assert abs(r["max_abs_error"] - w["max_abs"]) <= 1e-6 * max(w["max_abs"], 1e-3)
+            assert r["compressed_size_bytes"] == w["comp_bytes"] and r["original_size_bytes"] == n * c * 2
+            assert r["residual"] == kw["residual"] and (r["delta_delta_norm"] is not None) == (kw["residual"] == 2)
+        assert recs[0]["activation_similarity"] is None and 0.5 < recs[1]["activation_similarity"] < 1.0
+        cos = float(torch.nn.functional.cosine_similarity(xs[-1].double().flatten(), xs[-2].double().flatten(), dim=0))
+        assert abs(recs[-1]["activation_similarity"] - cos) < 1e-4
+        st.stats_verbose()
+        d = st.dump_err_vs_steps(str(tmp_path))
+        assert "avg comp error" in capsys.readouterr().out
+        assert len(d["avg_comp_errors"]) == steps - warm and abs(d["avg_comp_errors"][0] - want[0]["error"]) <= 2e-5 * want[0]["error"]
+    finally:
+        cf.compact_set_inplace(False)
+        st.stats_clear()
