@@ -86,6 +86,9 @@ def parse():
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     p.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                    help="payload exchange for N > 1: one-sided NVLink puts (p2p) or NCCL all-gather")
+    p.add_argument("--overlap", action="store_true",
+                   help="two-chain step: compress (+put) of layer l+1 runs beside the reconstruct of layer l "
+                        "(engine._step_overlapped; opt-in until measured)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-layers", type=int, default=2)
@@ -369,7 +372,7 @@ def main():
     mode = "eager"
     if not args.no_graph:
         try:
-            graphs = [eng.capture_step(ks[v], vs[v], ctype) for v in range(versions)]
+            graphs = [eng.capture_step(ks[v], vs[v], ctype, overlap=args.overlap) for v in range(versions)]
             mode = "cuda_graph"
         except Exception as e:  # capture can fail with NCCL inside: fall back to eager launches
             graphs, mode = None, f"eager (graph capture failed: {type(e).__name__})"
@@ -382,7 +385,7 @@ def main():
         if graphs is not None:
             graphs[v].replay()
         else:
-            eng.step(ks[v], vs[v], ctype)
+            eng.step(ks[v], vs[v], ctype, args.overlap)
 
     for i in range(max(args.warmup, 3)):
         run_step(i)
@@ -583,6 +586,7 @@ def main():
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "exchange": MODE, "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
+                       "schedule": "two chains (compress | reconstruct)" if (args.overlap and not raw and eng.can_overlap(ctype)) else "serial",
                        "transport": transport + (" (fused into the codec kernels)" if world > 1 and eng.fused(ctype) else ""),
                        **({"transport_note": probe_note} if probe_note else {}),
                        "l2": f"inputs larger than L2 (each step touches {(1 + world) * layers * 2 * n_local * CH * 2 / 1e9:.1f} GB "

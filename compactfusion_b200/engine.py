@@ -76,6 +76,8 @@ class PatchGatherEngine:
         # fused compress + put (cf_sign_compress_put): the codec kernels store the payload straight into every
         # rank's receive slot; CF_FUSED_PUT=0 keeps the separate put kernel (A/B)
         self.fused_put = os.environ.get("CF_FUSED_PUT", "1") != "0"
+        self._per_layer_send = False
+        self._side = None  # second stream of the overlapped step
 
     def prepare(self, ctype) -> str:
         """Set up the transport for `ctype` now (collective call); returns the transport in use."""
@@ -150,14 +152,18 @@ class PatchGatherEngine:
         per_byte = 8 if ctype == T.BINARY else 4
         return self.n * (self.c // per_byte) // 2 + self.n + self.c
 
-    def _buffers(self, ctype):
-        if ctype not in self._send:
+    def _buffers(self, ctype, layer: int = 0):
+        """(send, recv) payload buffers.  One pair serves all layers, except on a single GPU in overlap mode
+        (`_per_layer_send`): there recv aliases send, and the reconstruct of layer l runs while layer l+1 is
+        being compressed, so every layer gets its own buffer."""
+        key = (ctype, layer) if self._per_layer_send else ctype
+        if key not in self._send:
             pn = self._numel(ctype)
             self._payload_numel[ctype] = pn
-            self._send[ctype] = torch.empty((2, pn), dtype=torch.half, device=self.device)
-            self._recv[ctype] = (self._send[ctype].view(1, 2, pn) if self.world == 1 else
-                                 torch.empty((self.world, 2, pn), dtype=torch.half, device=self.device))
-        return self._send[ctype], self._recv[ctype]
+            self._send[key] = torch.empty((2, pn), dtype=torch.half, device=self.device)
+            self._recv[key] = (self._send[key].view(1, 2, pn) if self.world == 1 else
+                               torch.empty((self.world, 2, pn), dtype=torch.half, device=self.device))
+        return self._send[key], self._recv[key]
 
     def _views(self, flat, ctype):
         per_byte = 8 if ctype == T.BINARY else 4
@@ -184,7 +190,7 @@ class PatchGatherEngine:
         key = ("c", layer, k2.data_ptr(), v2.data_ptr(), ctype)
         args = self._ptr_cache.get(key)
         if args is None:
-            send, _ = self._buffers(ctype)
+            send, _ = self._buffers(ctype, layer)
             pk, uk, vk = self._views(send[0], ctype)
             pv, uv, vv = self._views(send[1], ctype)
             bases = [self._shard(self.global_k[layer], self.rank), self._shard(self.global_v[layer], self.rank)]
@@ -228,7 +234,7 @@ class PatchGatherEngine:
         key = ("d", layer, ctype, origins)
         args = self._ptr_cache.get(key)
         if args is None:
-            _, recv = self._buffers(ctype)
+            _, recv = self._buffers(ctype, layer)
             packed, us, vs, bases = [], [], [], []
             for r in origins:
                 for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
@@ -292,7 +298,7 @@ class PatchGatherEngine:
     def gather(self, ctype, layer: int = 0):
         """Move this rank's [K payload | V payload] to every rank: NCCL all-gather, or one put
         kernel writing all W receive slots (own included) over NVLink + flag publication."""
-        send, recv = self._buffers(ctype)
+        send, recv = self._buffers(ctype, layer)
         if self.world == 1:
             return
         st = self._p2p_region(ctype) if self.transport == "p2p" else None
@@ -346,25 +352,78 @@ class PatchGatherEngine:
         return self.global_k[layer], self.global_v[layer]
 
     # -- whole step ------------------------------------------------------------------------
-    def step(self, ks, vs, ctype):
+    OVERLAP_LAG = 2  # layers the compress chain may run ahead of the reconstruct chain
+
+    def can_overlap(self, ctype) -> bool:
+        """The two-chain step needs hazard-free buffers between the chains: per-layer receive slots (one-sided
+        transport) or per-layer send buffers (single GPU); the NCCL transport gathers every layer into one
+        buffer.  The slot-reuse argument below needs layers >= 2 * OVERLAP_LAG + 1."""
+        if ctype not in _CODEC or self.layers < 2 * self.OVERLAP_LAG + 1 or type(self).exchange is not PatchGatherEngine.exchange:
+            return False
+        return self.world == 1 or self.transport == "p2p"
+
+    def step(self, ks, vs, ctype, overlap: bool = False):
+        if overlap and self.can_overlap(ctype):
+            return self._step_overlapped(ks, vs, ctype)
         for layer in range(self.layers):
             self.exchange(layer, ks[layer], vs[layer], ctype)
 
-    def capture_step(self, ks, vs, ctype, warmup_iters: int = 1):
+    def _step_overlapped(self, ks, vs, ctype):
+        """One step as TWO chains: compress (+ put) of every layer on the current stream, reconstruct of every
+        layer on a side stream, joined per layer by an event.  The compress side of layer l+1 (a short
+        streaming pass plus a finalize kernel that mostly waits: partial sums, and at W > 1 a system-scope
+        fence and remote flag updates) then fills the bubbles of the bandwidth-bound reconstruct of layer l
+        instead of sitting in front of it.  Same kernels, same operands, bit-identical results.
+
+        Slot reuse stays safe at W > 1 because the compress chain is held to OVERLAP_LAG = d layers ahead
+        (put(l) waits for this rank's reconstruct(l - d)): a peer A overwrites slot (l, A) here in step t+1
+        only after (l >= d) its own reconstruct_{t+1}(l - d), which needed OUR put_{t+1}(l - d), issued after
+        our whole step t; or (l < d) after its step t, whose reconstruct_t(L-1) needed our put_t(L-1), issued
+        after our reconstruct_t(L-1-d) and hence -- the reconstruct chain runs in layer order -- after our
+        reconstruct_t(l), as l < d <= L-1-d."""
+        if self.world == 1 and not self._per_layer_send:
+            self._per_layer_send = True
+            self._ptr_cache.clear()
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side, lag = self._side, self.OVERLAP_LAG
+        side.wait_stream(main)  # fork (inside a capture this pulls the side stream into the graph)
+        done = []
+        for layer in range(self.layers):
+            if layer >= lag:
+                main.wait_event(done[layer - lag])
+            if self.fused(ctype):
+                self.compress_put(layer, ks[layer], vs[layer], ctype)
+            else:
+                self.compress(layer, ks[layer], vs[layer], ctype)
+                self.gather(ctype, layer)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                self.decompress(layer, ctype)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            done.append(ev)
+        main.wait_stream(side)  # join
+
+    def capture_step(self, ks, vs, ctype, warmup_iters: int = 1, overlap: bool = False):
         """Capture `step` (all layers, fixed input buffers) into a CUDA graph; returns the graph.
-        The caller replays it after refreshing ks / vs contents in place."""
+        The caller replays it after refreshing ks / vs contents in place.  `overlap`: the two-chain
+        step (`_step_overlapped`) where `can_overlap` allows it."""
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup_iters):
-                self.step(ks, vs, ctype)
+                self.step(ks, vs, ctype, overlap)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._ptr_cache.clear()  # workspaces are keyed by stream: rebuild inside the capture
         g = torch.cuda.CUDAGraph()
         before = self.kernel_launches
         with torch.cuda.graph(g):
-            self.step(ks, vs, ctype)
+            self.step(ks, vs, ctype, overlap)
         self.launches_per_graph = self.kernel_launches - before
         self._ptr_cache.clear()
         return g

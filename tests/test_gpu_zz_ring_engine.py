@@ -233,3 +233,105 @@ def test_log_stats_through_the_plugin_api(mode, tmp_path, capsys):
     finally:
         cf.compact_set_inplace(False)
         st.stats_clear()
+
+
+@pytest.mark.parametrize("codec", ["binary", "int2"])
+def test_overlapped_step_equals_serial_world1(codec):
+    """engine._step_overlapped (compress chain | reconstruct chain, per-layer events, lag 2): same kernels and
+    operands as the serial step -> bit-identical caches, eagerly and as a replayed CUDA graph."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200.engine import PatchGatherEngine
+    T = cf.COMPACT_COMPRESS_TYPE
+    ctype = T(codec)
+    n, c, layers, steps = 576, 3072, 7, 4
+    data = _kv(n, c, steps, layers, dev, seed=9)
+    serial, over, graph_eng = (PatchGatherEngine(layers, n, c, device=dev) for _ in range(3))
+    assert over.can_overlap(ctype) and not PatchGatherEngine(3, n, c, device=dev).can_overlap(ctype)
+    ks = [data[0][l][0].clone() for l in range(layers)]
+    vs = [data[0][l][1].clone() for l in range(layers)]
+    for e in (serial, over, graph_eng):
+        e.step(ks, vs, T.WARMUP, overlap=True)  # WARMUP ignores the flag
+    graph = None
+    for t in range(1, steps):
+        for l in range(layers):
+            ks[l].copy_(data[t][l][0])
+            vs[l].copy_(data[t][l][1])
+        serial.step(ks, vs, ctype)
+        over.step(ks, vs, ctype, overlap=True)
+        if graph is None:
+            snap = [(a.clone(), b.clone()) for a, b in zip(graph_eng.global_k, graph_eng.global_v)]
+            graph = graph_eng.capture_step(ks, vs, ctype, warmup_iters=1, overlap=True)
+            for l, (a, b) in enumerate(snap):  # the capture's warm-up run advanced the cache: restore it
+                graph_eng.global_k[l].copy_(a)
+                graph_eng.global_v[l].copy_(b)
+            assert graph_eng.launches_per_graph == layers * (3 if codec == "binary" else 4)
+        graph.replay()
+        torch.cuda.synchronize()
+        for l in range(layers):
+            assert torch.equal(over.global_k[l], serial.global_k[l]) and torch.equal(over.global_v[l], serial.global_v[l]), (t, l)
+            assert torch.equal(graph_eng.global_k[l], serial.global_k[l]), ("graph", t, l)
+            assert torch.equal(graph_eng.global_v[l], serial.global_v[l]), ("graph", t, l)
+
+
+OVERLAP_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["CF_ROOT"])
+import torch, torch.distributed as dist
+import compactfusion_b200 as cf
+from compactfusion_b200.engine import PatchGatherEngine
+T = cf.COMPACT_COMPRESS_TYPE
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+n, c, layers, steps = 288, 3072, 8, 6
+def shard(t, l, j):
+    g = torch.Generator().manual_seed(1000 * rank + 10 * l + j)
+    x0 = torch.randn(n, c, generator=g)
+    g2 = torch.Generator().manual_seed(77 + 1000 * rank + 10 * l + j + 100000 * t)
+    return (0.97 ** t * x0 + 0.2 * torch.randn(n, c, generator=g2)).half().to(dev)
+for codec in (T.BINARY, T.INT2):
+    serial = PatchGatherEngine(layers, n, c, device=dev, transport="nccl")
+    over = PatchGatherEngine(layers, n, c, device=dev, transport="p2p")
+    assert over.prepare(codec) == "p2p" and over.can_overlap(codec) and not serial.can_overlap(codec)
+    ks = [shard(0, l, 0) for l in range(layers)]
+    vs = [shard(0, l, 1) for l in range(layers)]
+    serial.step(ks, vs, T.WARMUP)
+    over.step(ks, vs, T.WARMUP)
+    graph = None
+    for t in range(1, steps):
+        for l in range(layers):
+            ks[l].copy_(shard(t, l, 0))
+            vs[l].copy_(shard(t, l, 1))
+        serial.step(ks, vs, codec)
+        if t < 3:
+            over.step(ks, vs, codec, overlap=True)       # eager two-chain steps
+        else:
+            if graph is None:
+                graph = over.capture_step(ks, vs, codec, warmup_iters=0, overlap=True)
+            for _ in range(1):
+                graph.replay()                           # the same step as one graph with two branches
+        torch.cuda.synchronize()
+        for l in range(layers):
+            assert torch.equal(over.global_k[l], serial.global_k[l]) and torch.equal(over.global_v[l], serial.global_v[l]), (codec, t, l)
+    assert not over.p2p_error(), "a device-side flag wait timed out"
+    dist.barrier()
+dist.destroy_process_group()
+print("WORKER_OK", rank)
+'''
+
+
+def test_two_gpu_overlapped_step(tmp_path):
+    """2 GPUs (skipped on a 1-GPU box): the two-chain step over the one-sided transport, eager and as a replayed
+    graph, against the serial NCCL engine."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "overlap2.py"
+    script.write_text(OVERLAP_WORKER)
+    env = dict(os.environ, CF_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29654", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-4000:]
