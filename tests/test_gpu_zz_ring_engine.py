@@ -235,6 +235,13 @@ def test_log_stats_through_the_plugin_api(mode, tmp_path, capsys):
         st.stats_clear()
 
 
+# The two-chain step is opt-in and has not run on a GPU yet: its tests are armed by CF_EXPERIMENTAL=1
+# (tools/gpu_round.sh and tools/gpu_multi.sh set it) until the schedule has been measured and made default.
+experimental = pytest.mark.skipif(os.environ.get("CF_EXPERIMENTAL", "0") != "1",
+                                  reason="opt-in feature, not yet measured: set CF_EXPERIMENTAL=1")
+
+
+@experimental
 @pytest.mark.parametrize("codec", ["binary", "int2"])
 def test_overlapped_step_equals_serial_world1(codec):
     """engine._step_overlapped (compress chain | reconstruct chain, per-layer events, lag 2): same kernels and
@@ -322,6 +329,7 @@ print("WORKER_OK", rank)
 '''
 
 
+@experimental
 def test_two_gpu_overlapped_step(tmp_path):
     """2 GPUs (skipped on a 1-GPU box): the two-chain step over the one-sided transport, eager and as a replayed
     graph, against the serial NCCL engine."""

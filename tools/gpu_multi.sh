@@ -6,6 +6,7 @@
 TAG=${1:-multi}
 N=${2:-2}
 OUT=gpurun_out
+export CF_EXPERIMENTAL=1  # arm the tests of opt-in features (two-chain step)
 mkdir -p $OUT
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $OUT/${TAG}_smi.txt 2>&1
 echo "== multi-rank tests"
@@ -22,6 +23,7 @@ run() {  # run <name> <timeout> [env VAR=..] -- bench args
 echo "== bench: fused put (default)" ; run fused 200 --steps 20 --warmup 3
 echo "== bench: separate put kernel" ; CF_FUSED_PUT=0 run putkernel 120 --steps 10 --warmup 3 --no-e2e
 echo "== bench: NCCL all-gather"     ; run nccl 120 --steps 10 --warmup 3 --no-e2e --transport nccl
+echo "== bench: two-chain step"      ; run overlap 120 --steps 10 --warmup 3 --no-e2e --overlap
 echo "== bench: INT2"                ; run int2 120 --steps 10 --warmup 3 --no-e2e --codec int2
 echo "== bench: uncompressed"        ; run raw 120 --steps 10 --warmup 3 --no-e2e --codec raw
 echo "== bench: CogVideoX ring"      ; run ring 200 --steps 5 --warmup 3 --no-e2e --workload cogvideox5b_ring

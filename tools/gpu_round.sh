@@ -6,6 +6,7 @@
 TAG=${1:-run}
 MODE=${2:-full}
 OUT=gpurun_out
+export CF_EXPERIMENTAL=1  # arm the tests of opt-in features (two-chain step)
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
 echo "== tests" ; (time timeout 600 python -m pytest tests -m gpu -x -q) > $OUT/${TAG}_tests.log 2>&1 ; tail -3 $OUT/${TAG}_tests.log
@@ -30,3 +31,5 @@ timeout 420 python sweep.py --sizes-mb 1,8,27,256,1024 --shapes 4608x3072,576x30
   --out $OUT/${TAG}_sweep.jsonl --md $OUT/${TAG}_sweep.md > $OUT/${TAG}_sweep.log 2>&1
 tail -5 $OUT/${TAG}_sweep.log
 ls -la $OUT | tail -20
+echo "== A/B: two-chain step (opt-in)"
+timeout 200 python bench.py --steps 10 --no-e2e --no-cpu-baseline --overlap > $OUT/${TAG}_bench_overlap.json 2>> $OUT/${TAG}_bench.err ; tail -c 600 $OUT/${TAG}_bench_overlap.json
