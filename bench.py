@@ -412,6 +412,19 @@ def main():
     ms_per_step = ms / args.steps
     value = job_bytes(layers, world) / (ms_per_step * 1e-3) / 1e9
 
+    # fidelity of what the timed steps produced (plumbing: plain torch reductions on one tensor)
+    fidelity = None
+    try:
+        x_last = ks[args.steps % versions][0].float()
+        d = eng._shard(eng.global_k[0], rank).float() - x_last
+        mse, peak = float((d * d).mean()), float(x_last.abs().max())
+        fidelity = {"tensor": "layer 0 K, this rank's shard: reconstruction after the last timed step vs its raw input",
+                    "rel_l2": float(d.norm() / x_last.norm()), "max_abs": float(d.abs().max()),
+                    "psnr_db": (10.0 * __import__("math").log10(peak * peak / mse)) if mse > 0 else None}
+        del x_last, d
+    except Exception as e:  # noqa: BLE001
+        fidelity = {"error": f"{type(e).__name__}: {e}"}
+
     roofline = None
     if not raw:
         # ---- per-kernel durations and the roofline of the dominant one ---------------------------
@@ -592,6 +605,7 @@ def main():
                        "l2": f"inputs larger than L2 (each step touches {(1 + world) * layers * 2 * n_local * CH * 2 / 1e9:.1f} GB "
                              "of distinct K/V inputs + cached bases per rank)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+            "fidelity": fidelity,
             "p2p_wait_timeouts": bool(eng.p2p_error()),
         }))
     if world > 1:
