@@ -26,6 +26,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 echo "== ncu full"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_delta_stats|k_finalize|k_apply|k_int2' -s 12 -c 9 \
   -f -o $OUT/${TAG}_full python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --layers 8 --no-graph > $OUT/${TAG}_ncu_full.log 2>&1
+echo "== kernel times (CUPTI)"
+for args in "lowrank --rank 32" "lowrank --rank 8" "codec --codec int4" "step --codec binary" "step --codec binary --overlap"; do
+  echo "-- $args" >> $OUT/${TAG}_kernel_times.md; timeout 120 python tools/kernel_times.py $args >> $OUT/${TAG}_kernel_times.md 2>&1
+done
 echo "== sweep"
 timeout 420 python sweep.py --sizes-mb 1,8,27,256,1024 --shapes 4608x3072,576x3072,4388x3072,8192x1152 --reps 5 \
   --out $OUT/${TAG}_sweep.jsonl --md $OUT/${TAG}_sweep.md > $OUT/${TAG}_sweep.log 2>&1
