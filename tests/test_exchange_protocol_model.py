@@ -28,44 +28,52 @@ class Violation(Exception):
     pass
 
 
-def _schedule(rank, world, layers, steps, mode, lag):
-    """Ops of one rank: list of dicts {id, kind, t, l, origins, stream, deps}.  ids are (rank, t, kind, l, hop)."""
-    ops, prev_step_tail = [], []
+def template_for(mode, rank, world, layers, lag):
+    """One step of one rank as a list of entries {kind, l, origins, stream, deps (indices of earlier entries)}.
+    Stream order is implicit: an entry also depends on the previous entry of its stream."""
+    tpl, applies = [], {}
+
+    def add(kind, l, stream, deps, origins=None):
+        tpl.append(dict(kind=kind, l=l, stream=stream, deps=list(deps), origins=origins))
+        return len(tpl) - 1
+
+    for l in range(layers):
+        if mode == "serial":
+            p = add("put", l, "main", [])
+            applies[l] = add("apply", l, "main", [p], origins=tuple(range(world)))
+        elif mode == "ring":
+            p = add("put", l, "main", [])
+            for hop in range(world):
+                applies[l] = add("apply", l, "main", [p], origins=((rank - hop) % world,))
+        else:  # two chains
+            p = add("put", l, "main", [applies[l - lag]] if l >= lag else [])
+            applies[l] = add("apply", l, "side", [p], origins=tuple(range(world)))
+    return tpl
+
+
+def instantiate(rank, template, steps):
+    """Ops of one rank over `steps` graph launches: ids (rank, t, index); the first entry of every stream
+    depends on the tail of every stream of the previous step (a graph launch starts after the previous one
+    has finished)."""
+    ops, prev_tail = [], []
     for t in range(steps):
-        step_ops, last_on = [], {}
-
-        def add(kind, l, stream, deps, origins=None, hop=0):
-            op = dict(id=(rank, t, kind, l, hop), kind=kind, t=t, l=l, stream=stream, origins=origins,
-                      deps=set(deps) | ({last_on[stream]} if stream in last_on else set(prev_step_tail)))
-            if stream not in last_on:
-                op["deps"] |= set(prev_step_tail)  # a graph launch starts after the previous one has finished
-            last_on[stream] = op["id"]
-            step_ops.append(op)
-            return op["id"]
-
-        applies = {}
-        for l in range(layers):
-            if mode == "serial":
-                p = add("put", l, "main", [])
-                applies[l] = add("apply", l, "main", [p], origins=tuple(range(world)))
-            elif mode == "ring":
-                p = add("put", l, "main", [])
-                for hop in range(world):
-                    applies[l] = add("apply", l, "main", [p], origins=((rank - hop) % world,), hop=hop)
-            else:  # two chains
-                deps = [applies[l - lag]] if l >= lag else []
-                p = add("put", l, "main", deps)
-                applies[l] = add("apply", l, "side", [p], origins=tuple(range(world)))
-        prev_step_tail = list(last_on.values())
-        ops += step_ops
+        last_on = {}
+        for idx, e in enumerate(template):
+            deps = {(rank, t, d) for d in e["deps"]}
+            deps |= {last_on[e["stream"]]} if e["stream"] in last_on else set(prev_tail)
+            last_on[e["stream"]] = (rank, t, idx)
+            ops.append(dict(id=(rank, t, idx), kind=e["kind"], t=t, l=e["l"], origins=e["origins"], deps=deps))
+        prev_tail = list(last_on.values())
     return ops
 
 
-def simulate(world, layers, steps, mode, lag, seed):
+def simulate(world, layers, steps, mode, lag, seed, templates=None):
+    """`templates`: per-rank step templates (e.g. recorded from the engine); default: `template_for(mode, ...)`."""
     rng = random.Random(seed)
     ops = {}
     for r in range(world):
-        for op in _schedule(r, world, layers, steps, mode, lag):
+        tpl = templates[r] if templates is not None else template_for(mode, r, world, layers, lag)
+        for op in instantiate(r, tpl, steps):
             ops[op["id"]] = op
     # slot[b][(l, a)] = step whose payload it holds (-1: the warm-up state); flag counts completed puts
     version = [{(l, a): -1 for l in range(layers) for a in range(world)} for _ in range(world)]
