@@ -1,0 +1,196 @@
+"""Dry run of bench.py's GPU arm on the CPU: CUDA streams / events / graphs, the native library and (for the
+N = 2 case) torch.distributed are replaced by recording stand-ins (TEST ONLY: nothing is computed, times are
+made up), so that every line of the host code that produces the round's JSON line executes here -- argument
+handling, the transport probe, engine setup, graph capture, per-kernel timing legs, fidelity, e2e staging,
+JSON assembly -- and a typo cannot first show up on the GPU box."""
+import contextlib
+import ctypes
+import json
+import sys
+import types
+
+import pytest
+import torch
+
+from test_engine_schedule_fake_cuda import FakeCuda, FakeEvent, FakeLib, FakeStream
+
+
+class TimedEvent(FakeEvent):
+    def __init__(self, enable_timing=False, **k):
+        super().__init__()
+
+    def elapsed_time(self, other):
+        return 1.0  # ms
+
+
+class FakeGraph:
+    def replay(self):
+        return None
+
+
+@contextlib.contextmanager
+def fake_graph_ctx(g, *a, **k):
+    yield
+
+
+class IpcLib(FakeLib):
+    """FakeLib whose cf_ipc_alloc / cf_ipc_open hand out made-up pointers."""
+    next_ptr = 0x7000000000
+
+    def __getattr__(self, name):
+        if name in ("cf_ipc_alloc", "cf_ipc_open"):
+            def alloc(*args):
+                out = args[1]
+                IpcLib.next_ptr += 0x100000000
+                ctypes.cast(out, ctypes.POINTER(ctypes.c_void_p))[0] = IpcLib.next_ptr
+                return 0
+            return alloc
+        if name == "cf_last_error":
+            return lambda: b""
+        return super().__getattr__(name)
+
+
+class FakeDist:
+    """torch.distributed for ONE process that believes it is rank 0 of `world`."""
+
+    class ReduceOp:
+        MAX, MIN, SUM = "max", "min", "sum"
+
+    def __init__(self, world):
+        self.world, self.up = world, False
+
+    def init_process_group(self, *a, **k):
+        self.up = True
+
+    def is_initialized(self):
+        return self.up
+
+    def get_world_size(self, group=None):
+        return self.world
+
+    def get_rank(self, group=None):
+        return 0
+
+    def barrier(self, *a, **k):
+        return None
+
+    def all_reduce(self, t, *a, **k):
+        return None
+
+    def all_gather_object(self, out, obj, group=None):
+        for i in range(len(out)):
+            out[i] = obj
+
+    def all_gather_into_tensor(self, out, inp, group=None):
+        out.view(self.world, -1).copy_(inp.reshape(1, -1).expand(self.world, -1))
+
+    def destroy_process_group(self):
+        self.up = False
+
+
+def _run_bench(monkeypatch, capsys, argv, world=1):
+    import bench
+    from compactfusion_b200 import _native as nv
+    from compactfusion_b200 import engine as eng_mod
+    FakeCuda.reset()
+    lib = IpcLib({})
+    monkeypatch.setattr(nv, "lib", lambda: lib)
+    monkeypatch.setattr(nv, "stream_ptr", lambda: FakeCuda.current().cuda_stream)
+    monkeypatch.setattr(nv, "workspace", lambda nbytes, device: torch.empty(max(int(nbytes), 16), dtype=torch.uint8))
+    monkeypatch.setattr(nv, "workspace_bytes", lambda *a, **k: 4096)
+    for name, val in dict(current_stream=lambda *a, **k: FakeCuda.current(), Stream=FakeStream, Event=TimedEvent,
+                          stream=FakeCuda.stream_ctx, is_available=lambda: True, set_device=lambda d: None,
+                          synchronize=lambda *a, **k: None, CUDAGraph=FakeGraph, graph=fake_graph_ctx,
+                          current_device=lambda: 0).items():
+        monkeypatch.setattr(torch.cuda, name, val)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    # inside bench.py, "cuda" devices are the CPU
+    real_device = torch.device
+    proxy = types.SimpleNamespace(**{k: getattr(torch, k) for k in dir(torch) if not k.startswith("__")})
+    proxy.device = lambda *a, **k: real_device("cpu")
+    monkeypatch.setattr(bench, "torch", proxy)
+    if world > 1:
+        fd = FakeDist(world)
+        monkeypatch.setattr(bench, "dist", fd)
+        monkeypatch.setattr(eng_mod, "dist", fd)
+        monkeypatch.setenv("WORLD_SIZE", str(world))
+        monkeypatch.setenv("RANK", "0")
+        monkeypatch.setenv("LOCAL_RANK", "0")
+    else:
+        for v in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+            monkeypatch.delenv(v, raising=False)
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    # restore the module-level workload constants afterwards
+    saved = {k: getattr(bench, k) for k in ("LAYERS", "SEQ", "CH", "METRIC", "WORKLOAD", "MODE")}
+    try:
+        bench.main()
+    finally:
+        for k, v in saved.items():
+            setattr(bench, k, v)
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, "bench.py must print exactly ONE JSON line"
+    return json.loads(lines[0])
+
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"}
+
+
+@pytest.mark.parametrize("argv", [
+    ["--layers", "2", "--steps", "4", "--no-cpu-baseline"],
+    ["--layers", "6", "--steps", "3", "--no-cpu-baseline", "--overlap", "--codec", "int2"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-graph", "--no-e2e"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--codec", "raw"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--workload", "pixart_patch_parallel"],
+])
+def test_bench_gpu_arm_single_gpu_dry_run(monkeypatch, capsys, argv):
+    line = _run_bench(monkeypatch, capsys, argv)
+    assert BASE_KEYS <= set(line), BASE_KEYS - set(line)
+    assert line["n_gpus"] == 1 and line["unit"] == "GB/s" and line["higher_is_better"] is True
+    assert line["steps"] == int(argv[argv.index("--steps") + 1]) and line["warmup"] >= 3
+    cfg = line["config"]
+    assert cfg["workload"] and "model" not in cfg and cfg["layers"] == int(argv[argv.index("--layers") + 1])
+    raw = "raw" in argv
+    if raw:
+        assert line["impl"] == "uncompressed_baseline" and line["roofline"] is None
+    else:
+        r = line["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernels"} <= set(r)
+        names = [k["kernel"] for k in r["kernels"]]
+        assert names[0].startswith("k_delta_stats") and names[-1].startswith("k_apply_codes")
+        assert ("k_int2_encode_tma" in names) == ("int2" in argv)
+        assert line["gpu_launches"] > 0
+    assert cfg["schedule"] == ("two chains (compress | reconstruct)" if "--overlap" in argv else "serial")
+    assert (line["e2e"] is None) == ("--no-e2e" in argv)
+    if line["e2e"]:
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert "rel_l2" in line["fidelity"] or "error" in line["fidelity"]
+    assert "error" not in line["fidelity"], line["fidelity"]
+
+
+@pytest.mark.parametrize("argv", [
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline"],
+    ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--overlap"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--transport", "nccl"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--workload", "cogvideox5b_ring",
+     "--codec", "int2"],
+])
+def test_bench_gpu_arm_two_rank_dry_run(monkeypatch, capsys, argv):
+    """Rank 0 of a pretended 2-rank job: the transport probe, CUDA-IPC region setup, fused put, flag-waiting
+    reconstruct and the per-kernel legs of the one-sided path."""
+    if "cogvideox5b_ring" in argv:
+        import bench
+        monkeypatch.setitem(bench.WORKLOADS, "cogvideox5b_ring", dict(bench.WORKLOADS["cogvideox5b_ring"], rows=2 * 1024))
+    line = _run_bench(monkeypatch, capsys, argv, world=2)
+    assert BASE_KEYS <= set(line) and line["n_gpus"] == 2
+    cfg = line["config"]
+    nccl = "nccl" in argv
+    assert cfg["transport"].startswith("nccl" if nccl else "p2p"), cfg["transport"]
+    assert cfg["launch_mode"] == ("eager" if nccl else "cuda_graph")
+    assert line["cpu_baseline"] is None and line["p2p_wait_timeouts"] is False
+    names = [k["kernel"] for k in line["roofline"]["kernels"]]
+    if not nccl:
+        assert all(k.get("fused_put") for k in line["roofline"]["kernels"][:2])
+        assert "k_p2p_put" not in names
+    if "cogvideox5b_ring" in argv:
+        assert cfg["exchange"] == "ring"
