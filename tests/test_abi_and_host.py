@@ -33,6 +33,55 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert lib.cf_abi_version() == 1
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype in include/compactb200.h against the ctypes binding: same arity, and per parameter the
+    same class (int / int64_t / size_t / pointer / pointer-to-pointer / float pointer); same return type."""
+    import ctypes
+    from compactfusion_b200 import _native as nv
+    hdr = open(os.path.join(ROOT, "include", "compactb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"CF_API\s+([\w\s\*]+?)\b(cf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert {name for _, name, _ in protos} == set(nv.SYMBOLS)
+
+    def classify_c(decl):
+        decl = " ".join(decl.replace("const", " ").split())
+        if decl in ("void", ""):
+            return None
+        stars = decl.count("*")
+        base = decl.replace("*", " ").split()
+        base = " ".join(base[:-1]) if len(base) > 1 else base[0]  # drop the parameter name
+        if stars >= 2:
+            return "pp"
+        if stars == 1:
+            return "p"
+        return {"int": "int", "int64_t": "i64", "size_t": "size", "cf_stream_t": "p", "unsigned": "int"}[base]
+
+    def classify_py(t):
+        if t is ctypes.c_int:
+            return "int"
+        if t is ctypes.c_int64:
+            return "i64"
+        if t is ctypes.c_size_t:
+            return "size"
+        if t in (ctypes.c_void_p, ctypes.c_char_p):
+            return "p"
+        if t is nv._VPP:
+            return "pp"
+        if isinstance(t, type) and issubclass(t, ctypes._Pointer):
+            return "p" if t._type_ is not ctypes.c_void_p else "pp"
+        raise AssertionError(f"unclassified ctypes type {t}")
+
+    for ret, name, params in protos:
+        res, args = nv.SYMBOLS[name]
+        c_args = [classify_c(p) for p in params.split(",")]
+        c_args = [a for a in c_args if a is not None]
+        py_args = [classify_py(a) for a in args]
+        # a void** OUT parameter (cf_ipc_alloc / cf_ipc_open) is bound as POINTER(c_void_p): both "pp"
+        assert c_args == py_args, f"{name}: header {c_args} vs ctypes {py_args}"
+        c_ret = classify_c(ret.strip() + " _") or "void"
+        assert c_ret == classify_py(res), f"{name}: return {c_ret} vs {classify_py(res)}"
+
+
 def test_workspace_sizes_without_gpu(built_lib):
     from compactfusion_b200 import _native as nv
     for codec in (nv.CODEC_BINARY, nv.CODEC_INT2, nv.CODEC_INT4, nv.CODEC_INT8):
