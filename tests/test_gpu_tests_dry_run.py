@@ -25,6 +25,15 @@ def fake_gpu(monkeypatch):
                           graph=fake_graph_ctx, current_device=lambda: 0).items():
         monkeypatch.setattr(torch.cuda, name, val)
     monkeypatch.setattr(zz, "_cuda", lambda: torch.device("cpu"))
+    # the product's fused LSE merge refuses CPU tensors: the dry run merges with the eager restatement
+    from compactfusion_b200 import attention
+
+    def eager_merge(out, lse, block_out, block_lse):
+        if out is None:
+            return block_out.to(torch.float32), block_lse.contiguous().to(torch.float32)
+        o, l = attention.update_out_and_lse(out, lse.transpose(1, 2).unsqueeze(-1), block_out, block_lse)
+        return o, l.squeeze(-1).transpose(1, 2).contiguous()
+    monkeypatch.setattr(attention, "merge_out_and_lse", eager_merge)
 
 
 @pytest.mark.parametrize("codec", ["binary", "int2"])
@@ -35,3 +44,28 @@ def test_dry_run_ring_engine_world1(fake_gpu, codec):
 @pytest.mark.parametrize("codec", ["binary", "int2"])
 def test_dry_run_overlapped_step_world1(fake_gpu, codec):
     zz.test_overlapped_step_equals_serial_world1(codec)  # (a direct call ignores the CF_EXPERIMENTAL skip mark)
+
+
+@pytest.mark.parametrize("worker", ["WORKER", "OVERLAP_WORKER"])
+def test_dry_run_two_gpu_workers_as_rank0(fake_gpu, monkeypatch, worker):
+    """The 2-GPU worker scripts of test_gpu_zz_ring_engine, executed in-process as rank 0 of a pretended
+    2-rank job (fake process group, fake CUDA IPC): transports, fused put, per-hop reconstruct, graph capture
+    and the launch-count assertions."""
+    import torch.distributed as dist
+    from compactfusion_b200 import _native as nv
+    from test_bench_dry_run import FakeDist, IpcLib
+    lib = IpcLib({})
+    monkeypatch.setattr(nv, "lib", lambda: lib)
+    fd = FakeDist(2)
+    for name in ("init_process_group", "is_initialized", "get_world_size", "get_rank", "barrier", "all_reduce",
+                 "all_gather_object", "all_gather_into_tensor", "destroy_process_group"):
+        monkeypatch.setattr(dist, name, getattr(fd, name))
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("CF_ROOT", zz.ROOT)
+    src = getattr(zz, worker).replace('torch.device("cuda", rank)', 'torch.device("cpu")')
+    src = src.replace('device_id=dev', 'device_id=None')
+    out = {}
+    exec(compile(src, worker, "exec"), {"__name__": "__worker__", "print": lambda *a: out.setdefault("printed", a)})
+    assert out["printed"] == ("WORKER_OK", 0)
