@@ -5,7 +5,7 @@
  * The reference has no FFI of its own: its boundary is the Python module API
  * `xfuser.compact.*`.  Each entry point below replaces the tensor
  * work of one reference function (cited as file:line under /root/reference); the Python
- * mirror `compactfusion_b200/*.py` keeps the reference's names and signatures and binds
+ * mirror (the `compactfusion_b200` modules) keeps the reference's names and signatures and binds
  * these symbols with ctypes (see INTEGRATION.md for the stub a maintainer would add).
  *
  * Conventions

@@ -388,3 +388,15 @@ def test_stats_logger_host_logic(monkeypatch, tmp_path, capsys):
     st.stats_clear()
     st.stats_verbose()
     assert "No statistics logged." in capsys.readouterr().out
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/compactb200.h is the drop-in boundary: it must compile as C99 and as C++ with no warnings and
+    without CUDA or torch headers on the include path."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "compactb200.h"\nint main(void) { return cf_abi_version() != CF_ABI_VERSION; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99"], ["g++", "-x", "c++", "-std=c++17"]):
+        r = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
+                                  str(tmp_path / "t.o")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
