@@ -400,3 +400,53 @@ def test_header_is_plain_c(tmp_path):
         r = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
                                   str(tmp_path / "t.o")], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def _build_c_client(tmp_path, built_lib):
+    exe = str(tmp_path / "c_client")
+    libdir = os.path.dirname(built_lib)
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           "-I", "/usr/local/cuda/include", os.path.join(ROOT, "examples", "c_client.c"), "-o", exe,
+           "-L", libdir, "-lcompactb200", f"-Wl,-rpath,{libdir}", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_client_links_and_its_checker_agrees_with_the_oracle(tmp_path, built_lib):
+    """examples/c_client.c (C99, no torch): links against the shared library, the device-free calls work, and
+    its bit-exact property checker accepts the ORACLE's BINARY round trip and rejects corrupted ones -- so the
+    GPU run of the same program (tests/test_gpu_zz_ring_engine.py) is judged by a checked checker."""
+    from oracle import codecs as oc
+    exe = _build_c_client(tmp_path, built_lib)
+    r = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True)
+    assert r.returncode == 0 and "C_NO_GPU_OK abi=1" in r.stdout, r.stdout + r.stderr
+    n, c = 48, 256
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(n, c, generator=g) * 3).half()
+    base = (x.float() + 0.4 * torch.randn(n, c, generator=g)).half()
+    base[0, :8] = x[0, :8]                      # zero deltas: sign bit 1
+    x[1, 0], base[1, 0] = 6.0e-8, 1.2e-7        # subnormal operands
+    packed, u, v, _ = oc.binary_quant(x, base, False)
+    recon = oc.binary_dequant(packed, u, v, base)
+    payload = packed.tobytes() + u.numpy().tobytes() + v.numpy().tobytes()
+
+    def dump(path, recon_t, payload_b):
+        with open(path, "wb") as f:
+            f.write(np.array([n, c], dtype=np.int64).tobytes())
+            f.write(x.numpy().tobytes() + base.numpy().tobytes() + payload_b + recon_t.numpy().tobytes())
+
+    good = str(tmp_path / "good.bin")
+    dump(good, recon, payload)
+    r = subprocess.run([exe, "--check", good], capture_output=True, text=True)
+    assert r.returncode == 0 and "C_CHECK_OK" in r.stdout, r.stdout + r.stderr
+    bad_recon = recon.clone()
+    bad_recon.view(torch.int16)[5, 7] ^= 1      # one ulp off
+    dump(str(tmp_path / "bad1.bin"), bad_recon, payload)
+    r = subprocess.run([exe, "--check", str(tmp_path / "bad1.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "recon (5,7)" in r.stderr
+    flipped = bytearray(payload)
+    flipped[3 * (c // 8) + 2] ^= 0x10           # sign bit of element (3, 20)
+    dump(str(tmp_path / "bad2.bin"), recon, bytes(flipped))
+    r = subprocess.run([exe, "--check", str(tmp_path / "bad2.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "sign bit (3,20)" in r.stderr

@@ -344,3 +344,21 @@ def test_two_gpu_overlapped_step(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-4000:]
+
+
+def test_plain_c_client_round_trip(tmp_path):
+    """examples/c_client.c: a C99 program (no torch) drives one BINARY residual round trip through the C ABI on
+    host buffers and checks sign bits, reconstruction and the sender/receiver identity bit for bit with its own
+    fp16 arithmetic (the checker is pinned against the oracle in tests/test_abi_and_host.py)."""
+    _cuda()
+    from compactfusion_b200 import build as cf_build
+    lib = cf_build.build()
+    libdir = os.path.dirname(lib)
+    exe = str(tmp_path / "c_client")
+    cmd = ["gcc", "-std=c99", "-O2", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(ROOT, "examples", "c_client.c"), "-o", exe, "-L", libdir, "-lcompactb200",
+           f"-Wl,-rpath,{libdir}", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C_CLIENT_OK 544x3072" in r.stdout, r.stdout + r.stderr
