@@ -351,9 +351,9 @@ def test_plain_c_client_round_trip(tmp_path):
     host buffers and checks sign bits, reconstruction and the sender/receiver identity bit for bit with its own
     fp16 arithmetic (the checker is pinned against the oracle in tests/test_abi_and_host.py)."""
     _cuda()
-    from compactfusion_b200 import build as cf_build
-    lib = cf_build.build()
-    libdir = os.path.dirname(lib)
+    from compactfusion_b200 import _native as nv
+    nv.lib()  # the library this process already uses (never rebuild a mapped .so)
+    libdir = os.path.dirname(nv.LIB_PATH)
     exe = str(tmp_path / "c_client")
     cmd = ["gcc", "-std=c99", "-O2", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
            os.path.join(ROOT, "examples", "c_client.c"), "-o", exe, "-L", libdir, "-lcompactb200",
