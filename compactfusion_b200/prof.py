@@ -1,15 +1,21 @@
-"""CUDA-event scope profiler with the reference's scope names (xfuser/prof.py:5-202).
+"""Scope profiler with the reference's API and scope names (mirror of xfuser/prof.py:5-203).
 
-Disabled by default (the reference's is enabled by default and creates CUDA events on every
-scope); `Profiler.instance().enable()` turns it on.  Scope names on the hot path are kept
-(`compact.compact_compress`, `compact.all_gather`, `compact.ring.wait`, ...) so latency
-breakdowns are comparable.
+Same calls as the reference -- `Profiler.instance()`, `start/stop(name, stream=None, cpu=False)`,
+`elapsed_time(name) -> (total_ms, avg_ms)`, `get_all_elapsed_times() -> (totals, avgs)`, `sync()`,
+`reset()`, `Profiler.scope(...)`, `@Profiler.prof_func(...)`, `prof_summary(profiler, rank) -> lines`,
+`set_torch_profiler` / `torch_profiler_step` -- so xDiT's hooks, the example scripts and latency
+breakdowns keyed by scope name (`compact.compact_compress`, `compact.all_gather`, `compact.ring.wait`,
+...) work unchanged.
+
+One deliberate difference: the profiler is DISABLED until `enable()` is called.  The reference's is
+enabled from the start and records two CUDA events around every scope of every call, which cannot be
+captured in a CUDA graph and fails on a host without CUDA; a run that wants the breakdown enables it
+(the example scripts do so explicitly around their timed region).
 """
 from __future__ import annotations
 
-import contextlib
 import functools
-from collections import defaultdict
+import time
 
 import torch
 
@@ -18,86 +24,154 @@ class Profiler:
     _instance = None
 
     def __init__(self):
+        self.events = {}      # name -> {'start': [...], 'end': [...], 'elapsed': ms, 'count': n, 'cpu': bool}
         self.enabled = False
-        self._open = {}
-        self._pairs = defaultdict(list)
-        self._totals = defaultdict(float)
-        self._counts = defaultdict(int)
 
-    @classmethod
-    def instance(cls):
-        if cls._instance is None:
-            cls._instance = cls()
-        return cls._instance
+    @staticmethod
+    def instance() -> "Profiler":
+        if Profiler._instance is None:
+            Profiler._instance = Profiler()
+        return Profiler._instance
 
     def enable(self):
+        """All subsequent start / stop calls are recorded."""
         self.enabled = True
 
     def disable(self):
+        """All subsequent start / stop calls are ignored."""
         self.enabled = False
 
-    def reset(self):
-        self._open.clear()
-        self._pairs.clear()
-        self._totals.clear()
-        self._counts.clear()
+    # -- recording ---------------------------------------------------------------------------
+    @staticmethod
+    def _mark(stream, cpu):
+        if cpu:
+            return time.time()
+        ev = torch.cuda.Event(enable_timing=True)
+        if stream is not None:
+            ev.record(stream)
+        else:
+            ev.record()
+        return ev
 
-    def start(self, name):
+    def start(self, name, stream=None, cpu=False):
+        """Open section `name` (a section may be opened and closed many times; times accumulate)."""
         if not self.enabled:
             return
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        self._open[name] = ev
+        rec = self.events.setdefault(name, {"start": [], "end": [], "elapsed": 0.0, "count": 0, "cpu": cpu})
+        assert len(rec["start"]) == len(rec["end"]), f"Cannot start '{name}' as there are more starts than stops"
+        rec["start"].append(self._mark(stream, cpu))
 
-    def stop(self, name):
-        if not self.enabled or name not in self._open:
+    def stop(self, name, stream=None, cpu=False):
+        if not self.enabled:
             return
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        self._pairs[name].append((self._open.pop(name), ev))
+        assert name in self.events, f"No events recorded for '{name}'"
+        rec = self.events[name]
+        assert len(rec["start"]) - 1 == len(rec["end"]), f"Cannot stop '{name}' as there are more stops than starts"
+        rec["end"].append(self._mark(stream, cpu))
 
+    # -- read-out ----------------------------------------------------------------------------
     def elapsed_time(self, name):
-        """Accumulated milliseconds and call count of a scope (synchronises)."""
-        for s, e in self._pairs.pop(name, []):
-            e.synchronize()
-            self._totals[name] += s.elapsed_time(e)
-            self._counts[name] += 1
-        return self._totals[name], self._counts[name]
+        """(total_ms, avg_ms) of section `name`; folds the pending start / stop pairs into the total
+        (synchronising the device for CUDA-event sections)."""
+        if name not in self.events:
+            raise ValueError(f"No events recorded for '{name}'")
+        rec = self.events[name]
+        pairs = list(zip(rec["start"], rec["end"]))
+        if pairs:
+            if rec["cpu"]:
+                rec["elapsed"] += sum((e - s) * 1000.0 for s, e in pairs)
+            else:
+                torch.cuda.synchronize()
+                rec["elapsed"] += sum(s.elapsed_time(e) for s, e in pairs)
+            rec["count"] += len(pairs)
+            # an open section (start without stop) stays open
+            rec["start"], rec["end"] = rec["start"][len(pairs):], []
+        return rec["elapsed"], (rec["elapsed"] / rec["count"] if rec["count"] else 0.0)
+
+    def get_all_elapsed_times(self):
+        totals, avgs = {}, {}
+        for name in self.events:
+            totals[name], avgs[name] = self.elapsed_time(name)
+        return totals, avgs
+
+    def sync(self):
+        """Fold every pending event pair into the totals."""
+        if any(not r["cpu"] and r["start"] for r in self.events.values()):
+            torch.cuda.synchronize()
+        self.get_all_elapsed_times()
+
+    def reset(self):
+        self.events = {}
 
     def summary(self):
-        names = set(self._pairs) | set(self._totals)
-        return {n: self.elapsed_time(n) for n in sorted(names)}
+        """name -> (total_ms, calls)."""
+        out = {}
+        for name in sorted(self.events):
+            total, _ = self.elapsed_time(name)
+            out[name] = (total, self.events[name]["count"])
+        return out
 
-    @classmethod
-    @contextlib.contextmanager
-    def scope(cls, name):
-        inst = cls.instance()
-        inst.start(name)
-        try:
-            yield
-        finally:
-            inst.stop(name)
+    # -- scopes ------------------------------------------------------------------------------
+    class _Scope:
+        def __init__(self, profiler, name, stream=None, cpu=False):
+            self.profiler, self.name, self.stream, self.cpu = profiler, name, stream, cpu
 
-    @classmethod
-    def prof_func(cls, name):
-        def deco(fn):
-            @functools.wraps(fn)
-            def wrapper(*a, **kw):
-                inst = cls.instance()
+        def __enter__(self):
+            self.profiler.start(self.name, self.stream, self.cpu)
+            return self
+
+        def __exit__(self, exc_type, exc_val, exc_tb):
+            self.profiler.stop(self.name, self.stream, self.cpu)
+            return False
+
+    @staticmethod
+    def scope(name, stream=None, cpu=False):
+        """`with Profiler.scope("compact.ring.wait"): ...`"""
+        return Profiler._Scope(Profiler.instance(), name, stream, cpu)
+
+    @staticmethod
+    def prof_func(name, cpu=False):
+        """Decorator: time every call of the function as section `name`."""
+        def decorator(func):
+            @functools.wraps(func)
+            def wrapper(*args, **kwargs):
+                inst = Profiler.instance()
                 if not inst.enabled:
-                    return fn(*a, **kw)
-                with cls.scope(name):
-                    return fn(*a, **kw)
+                    return func(*args, **kwargs)
+                inst.start(name, cpu=cpu)
+                try:
+                    return func(*args, **kwargs)
+                finally:
+                    inst.stop(name, cpu=cpu)
             return wrapper
-        return deco
+        return decorator
 
 
-def prof_summary(profiler: Profiler | None = None, rank=None) -> str:
+def prof_summary(profiler: Profiler | None = None, rank=None):
+    """Breakdown as a list of text lines, largest section first; shares are relative to the section
+    named 'total' when one was recorded (xfuser/prof.py:172-189)."""
     p = profiler or Profiler.instance()
-    rows = p.summary()
-    total = rows.get("total", (0.0, 0))[0]
-    lines = []
-    for name, (ms, cnt) in rows.items():
-        share = f" {100.0 * ms / total:5.1f}%" if total > 0 else ""
-        lines.append(f"{name:48s} total {ms:10.3f} ms  calls {cnt:6d}  avg {ms / max(cnt, 1):8.4f} ms{share}")
-    return "\n".join(lines)
+    rank = "N/A" if rank is None else rank
+    totals, avgs = p.get_all_elapsed_times()
+    whole = totals.get("total", 0.0)
+    split = "-" * 20
+    lines = [split, f"Profiling Summary for Rank {rank}"]
+    for name, ms in sorted(totals.items(), key=lambda kv: kv[1], reverse=True):
+        share = f" {ms / whole:.2%}" if whole > 0 else ""
+        lines.append(f"[Rank {rank}] [{name}] {ms / 1000:.2f}s{share} avg={avgs[name]:.2f}ms")
+    lines.append(split)
+    return lines
+
+
+_torch_profiler = None
+
+
+def torch_profiler_step():
+    """Advance the torch.profiler schedule installed with `set_torch_profiler`, if any."""
+    if _torch_profiler is not None:
+        _torch_profiler.step()
+
+
+def set_torch_profiler(profiler):
+    global _torch_profiler
+    _torch_profiler = profiler
