@@ -561,3 +561,42 @@ def test_profiler_api_matches_the_reference_semantics():
     set_torch_profiler(None)
     torch_profiler_step()
     assert s.n == 1
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/examples/configs.py"), reason="reference tree not mounted (GPU box)")
+def test_reference_example_presets_construct_against_this_package(capsys):
+    """Execute the reference's own examples/configs.py (the presets its example scripts and benchmarks use:
+    binary, int2, lowrank*, distrifusion, patch, int2patch ...) on top of the shim: every preset must build a
+    valid CompactConfig from THIS package, and init / compress-type selection must work as the pipelines use
+    them (compact_init -> compress_func(layer, step) -> get_compress_type)."""
+    import compactfusion_b200 as cf
+    import compactfusion_b200.shim as shim
+    shim.install()
+    try:
+        ns = {"__name__": "ref_configs"}
+        exec(compile(open("/root/reference/examples/configs.py").read(), "configs.py", "exec"), ns)
+        methods = ["binary", "int2", "lowrank12", "lowrank8", "lowrankq32", "df", "pipe", "ring", "ulysses", "int2patch"]
+        built = {}
+        for model in ("Flux", "Pixart-alpha", "CogVideoX"):
+            for method in methods:
+                cfg = ns["get_config"](model, method)
+                assert isinstance(cfg, cf.CompactConfig), (model, method)
+                built[(model, method)] = cfg
+                cf.compact_init(cfg)
+                assert cf.compact_config() is cfg and cf.compact_get_step() is None
+                if cfg.enabled and cfg.compress_func is not None:
+                    warm = 2 if model == "CogVideoX" else 1
+                    assert cfg.compress_func(0, 0) == cf.COMPACT_COMPRESS_TYPE.WARMUP
+                    assert cfg.compress_func(3, warm) != cf.COMPACT_COMPRESS_TYPE.WARMUP
+                    assert isinstance(cfg.get_compress_type(), str)
+                cf.compact_reset()
+        assert built[("Flux", "binary")].fastpath and built[("Flux", "binary")].compress_func(0, 5) == cf.COMPACT_COMPRESS_TYPE.BINARY
+        assert built[("CogVideoX", "lowrankq32")].comp_rank == 32
+        assert built[("Flux", "int2patch")].override_with_patch_gather_fwd
+        assert built[("Flux", "int2patch")].patch_gather_fwd_config.use_compact
+        assert not built[("Flux", "ring")].enabled
+        with pytest.raises(ValueError):
+            ns["get_config"]("SDXL", "binary")
+    finally:
+        shim.uninstall()
+    capsys.readouterr()
