@@ -330,6 +330,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    from compactfusion_b200 import build as cf_build
+    if not os.path.exists(cf_build.OUT) and local_rank == 0:
+        cf_build.build()  # a checkout without the build artefact: compile it (no fallback: failure is fatal)
+    if world > 1:
+        dist.barrier()
     from compactfusion_b200.engine import PatchGatherEngine, RingExchangeEngine
     from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
     raw = args.codec == "raw"
