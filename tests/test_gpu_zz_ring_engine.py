@@ -179,7 +179,7 @@ def test_two_gpu_ring_engine(tmp_path):
         assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-4000:]
 
 
-@pytest.mark.parametrize("mode", ["fastpath_binary", "sim_int4_r1", "lowrank_r2"])
+@pytest.mark.parametrize("mode", ["fastpath_binary", "sim_int4_r1", "sim_int2_r2"])
 def test_log_stats_through_the_plugin_api(mode, tmp_path, capsys):
     """CompactConfig(log_stats=True): compact_compress records error / norm figures on the GPU without a
     synchronisation per call; the read-back equals torch reductions of the same tensors (stats.py:107-328)."""
@@ -190,7 +190,7 @@ def test_log_stats_through_the_plugin_api(mode, tmp_path, capsys):
     kw, ctype = {
         "fastpath_binary": (dict(residual=1, ef=True, fastpath=True, comp_rank=-1), T.BINARY),
         "sim_int4_r1": (dict(residual=1, ef=True, simulate=True, comp_rank=-1), T.INT4),
-        "lowrank_r2": (dict(residual=2, ef=True, comp_rank=8, delta_decay_factor=0.5), T.LOW_RANK),
+        "sim_int2_r2": (dict(residual=2, ef=True, simulate=True, comp_rank=-1, delta_decay_factor=0.5), T.INT2),
     }[mode]
     n, c, steps = 256, 512, 5
     shape = (1, n, 8, c // 8)
