@@ -1,6 +1,8 @@
 """Low-rank projector (mirror of xfuser/compact/compress_lowrank.py)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _native as nv
@@ -15,11 +17,16 @@ def svd(input_tensor: torch.Tensor, rank: int):
     return (u[:, :rank] @ torch.diag(s[:rank])).to(input_tensor.dtype), vh[:rank, :].to(input_tensor.dtype)
 
 
-def _init_q(n: int, rank: int, device) -> torch.Tensor:
-    """The reference's random start: qr(randn(n, rank)) in fp32 from the global torch RNG
-    (compress_lowrank.py:40-42).  Data independent; drawn with torch, like the reference."""
+def _init_q(n: int, rank: int, device, orthonormalise: bool) -> torch.Tensor:
+    """The reference's random start, randn(n, rank) in fp32 from the global torch RNG (same draw, same RNG
+    consumption, compress_lowrank.py:40-42).  The reference then orthonormalises it with a library QR; that
+    step only changes the BASIS of span(Q0): Z = A^T A Q0 spans the same subspace for Q0 and for Q0 R^-1, and
+    every later step re-orthonormalises, so U V (the only thing the codec ships or anyone compares) is the
+    same.  The library QR of a (C, r) matrix costs ~1 ms on the GPU -- twice the whole projector -- so it is
+    only run when no iteration follows (num_iters == 0 returns Q0 itself) or with CF_LR_ORTHO_INIT=1."""
     q = torch.randn(n, rank, device=device, dtype=torch.float)
-    q, _ = torch.linalg.qr(q)
+    if orthonormalise or os.environ.get("CF_LR_ORTHO_INIT", "0") == "1":
+        q, _ = torch.linalg.qr(q)
     return q.contiguous()
 
 
@@ -31,7 +38,7 @@ def lowrank_project(x: torch.Tensor, base: torch.Tensor | None, rank: int, num_i
     assert 1 <= rank <= MAX_RANK, f"rank must be in [1, {MAX_RANK}]"
     x = x.contiguous()
     n, c = x.shape
-    q0 = _init_q(c, rank, x.device) if init_q is None else init_q.float().contiguous()
+    q0 = _init_q(c, rank, x.device, num_iters == 0) if init_q is None else init_q.float().contiguous()
     assert q0.shape == (c, rank)
     u = torch.empty((n, rank), dtype=torch.half, device=x.device) if u_out is None else u_out
     v = torch.empty((rank, c), dtype=torch.half, device=x.device) if v_out is None else v_out

@@ -159,3 +159,20 @@ def test_state_machine_matches_reference(golden_state, name):
     if kw.get("ef"):
         # error-feedback invariant: sender and receiver caches are bit-identical
         assert_bits_equal(sender.base["0-0-k"], receiver.base["0-0-k"], "EF invariant")
+
+
+def test_lowrank_product_does_not_depend_on_orthonormalising_the_random_start():
+    """compactfusion_b200.compress_lowrank._init_q skips the reference's library QR of the random start
+    (compress_lowrank.py:40-42): with the reference's own algorithm (the oracle restatement) U V from a raw
+    Gaussian Q0 equals U V from qr(Q0) to fp16 output rounding, with and without low-rank structure."""
+    from oracle import codecs
+    g = torch.Generator().manual_seed(0)
+    n, c, r = 272, 384, 8
+    low = torch.randn(n, r, generator=g) @ torch.randn(r, c, generator=g)
+    for a in ((low + 0.3 * torch.randn(n, c, generator=g)).half(), torch.randn(n, c, generator=g).half()):
+        q0 = torch.randn(c, r, generator=g)
+        qo, _ = torch.linalg.qr(q0)
+        u1, v1, _ = codecs.subspace_iter(a, r, 2, init_q=q0)
+        u2, v2, _ = codecs.subspace_iter(a, r, 2, init_q=qo)
+        p1, p2 = u1.float() @ v1.float(), u2.float() @ v2.float()
+        assert float((p1 - p2).norm() / p2.norm()) < 2e-4
