@@ -7,14 +7,18 @@ Same calls as the reference -- `Profiler.instance()`, `start/stop(name, stream=N
 breakdowns keyed by scope name (`compact.compact_compress`, `compact.all_gather`, `compact.ring.wait`,
 ...) work unchanged.
 
-One deliberate difference: the profiler is DISABLED until `enable()` is called.  The reference's is
-enabled from the start and records two CUDA events around every scope of every call, which cannot be
-captured in a CUDA graph and fails on a host without CUDA; a run that wants the breakdown enables it
-(the example scripts do so explicitly around their timed region).
+Like the reference's, the profiler is ENABLED from the start (its example scripts rely on that:
+`Profiler.instance().reset(); with Profiler.instance().scope("total"): ...; prof_summary(...)` without ever
+calling `enable()`), and every scope records two CUDA events.  Two things differ, so that the same code also
+runs where the reference's cannot: on a host without CUDA a section is timed with the wall clock instead of
+raising, and while the current stream is being captured into a CUDA graph a section records nothing
+(timing events cannot be read back from a capture).  `COMPACT_PROFILER=0` in the environment, or
+`Profiler.instance().disable()`, switches the ~2 us per event off; the engines (engine.py) never use it.
 """
 from __future__ import annotations
 
 import functools
+import os
 import time
 
 import torch
@@ -25,7 +29,7 @@ class Profiler:
 
     def __init__(self):
         self.events = {}      # name -> {'start': [...], 'end': [...], 'elapsed': ms, 'count': n, 'cpu': bool}
-        self.enabled = False
+        self.enabled = os.environ.get("COMPACT_PROFILER", "1") != "0"
 
     @staticmethod
     def instance() -> "Profiler":
@@ -44,8 +48,12 @@ class Profiler:
     # -- recording ---------------------------------------------------------------------------
     @staticmethod
     def _mark(stream, cpu):
-        if cpu:
+        """A time stamp: wall clock (cpu sections, or no CUDA on this host), a recorded CUDA event, or None
+        while the stream is being captured into a graph."""
+        if cpu or not torch.cuda.is_available():
             return time.time()
+        if torch.cuda.is_current_stream_capturing():
+            return None
         ev = torch.cuda.Event(enable_timing=True)
         if stream is not None:
             ev.record(stream)
@@ -78,12 +86,12 @@ class Profiler:
         rec = self.events[name]
         pairs = list(zip(rec["start"], rec["end"]))
         if pairs:
-            if rec["cpu"]:
-                rec["elapsed"] += sum((e - s) * 1000.0 for s, e in pairs)
-            else:
+            timed = [(s, e) for s, e in pairs if s is not None and e is not None]  # None: inside a graph capture
+            if any(not isinstance(s, float) for s, _ in timed):
                 torch.cuda.synchronize()
-                rec["elapsed"] += sum(s.elapsed_time(e) for s, e in pairs)
-            rec["count"] += len(pairs)
+            for s, e in timed:
+                rec["elapsed"] += (e - s) * 1000.0 if isinstance(s, float) else s.elapsed_time(e)
+            rec["count"] += len(timed)
             # an open section (start without stop) stays open
             rec["start"], rec["end"] = rec["start"][len(pairs):], []
         return rec["elapsed"], (rec["elapsed"] / rec["count"] if rec["count"] else 0.0)
@@ -96,8 +104,6 @@ class Profiler:
 
     def sync(self):
         """Fold every pending event pair into the totals."""
-        if any(not r["cpu"] and r["start"] for r in self.events.values()):
-            torch.cuda.synchronize()
         self.get_all_elapsed_times()
 
     def reset(self):
@@ -153,7 +159,7 @@ def prof_summary(profiler: Profiler | None = None, rank=None):
     p = profiler or Profiler.instance()
     rank = "N/A" if rank is None else rank
     totals, avgs = p.get_all_elapsed_times()
-    whole = totals.get("total", 0.0)
+    whole = totals.get("total", 0.0)  # (the reference raises without a 'total' section; here shares are omitted)
     split = "-" * 20
     lines = [split, f"Profiling Summary for Rank {rank}"]
     for name, ms in sorted(totals.items(), key=lambda kv: kv[1], reverse=True):

@@ -507,12 +507,17 @@ def test_profiler_api_matches_the_reference_semantics():
     p = Profiler.instance()
     assert p is Profiler.instance()
     p.reset()
-    assert p.enabled is False
+    assert Profiler().enabled is True           # like the reference's: recording from the start
+    p.disable()
     p.start("ignored", cpu=True)
     p.stop("ignored", cpu=True)
     assert p.events == {}                       # disabled: nothing is recorded
     p.enable()
     try:
+        with Profiler.scope("no_cuda_here"):    # a CUDA section on a host without CUDA: wall clock, no raise
+            time.sleep(0.001)
+        assert p.elapsed_time("no_cuda_here")[0] >= 1.0
+        p.reset()
         for _ in range(3):
             with Profiler.scope("total", cpu=True):
                 with Profiler.scope("inner", cpu=True):
@@ -545,7 +550,7 @@ def test_profiler_api_matches_the_reference_semantics():
         work(5)
         assert p.elapsed_time("decorated")[0] == totals["decorated"]
     finally:
-        p.disable()
+        p.enable()
         p.reset()
 
     class Stepper:

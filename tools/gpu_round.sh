@@ -37,3 +37,5 @@ tail -5 $OUT/${TAG}_sweep.log
 ls -la $OUT | tail -20
 echo "== A/B: two-chain step (opt-in)"
 timeout 200 python bench.py --steps 10 --no-e2e --no-cpu-baseline --overlap > $OUT/${TAG}_bench_overlap.json 2>> $OUT/${TAG}_bench.err ; tail -c 600 $OUT/${TAG}_bench_overlap.json
+echo "== the reference's own tests against this library (needs tools/stage_reference.sh run in the build container)"
+[ -d baseline/_ref/tests/compact ] && (timeout 600 python tools/run_reference_tests.py -x > $OUT/${TAG}_reference_tests.log 2>&1; tail -3 $OUT/${TAG}_reference_tests.log)

@@ -11,3 +11,9 @@ cp "$REF"/xfuser/compact/*.py "$DST/xfuser/compact/"
 cp -r "$REF/xfuser/compact/patchpara" "$DST/xfuser/compact/"
 cp "$REF"/xfuser/collector/*.py "$DST/xfuser/collector/"
 echo "staged reference files under $DST"
+# the reference's own unit tests of the plugin (run against THIS library by tools/run_reference_tests.py)
+mkdir -p "$DST/tests/compact"
+cp "$REF"/tests/compact/*.py "$DST/tests/compact/"
+# regular packages, so that `from tests.compact... import` finds THIS tree and not some installed `tests`
+touch "$DST/tests/__init__.py" "$DST/tests/compact/__init__.py"
+echo "staged the reference's tests/compact under $DST/tests/compact"
