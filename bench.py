@@ -310,6 +310,184 @@ def p2p_probe(engine_cls, n_local, ctype, device):
     return bool(t.item()), why
 
 
+def measure_fidelity(eng, x_last, rank):
+    """Fidelity of what the timed steps produced (plumbing: plain torch reductions on one tensor): layer 0 K,
+    this rank's shard -- the reconstruction after the last timed step against its raw input `x_last`."""
+    import math
+    try:
+        x = x_last.float()
+        d = eng._shard(eng.global_k[0], rank).float() - x
+        mse, peak = float((d * d).mean()), float(x.abs().max())
+        return {"tensor": "layer 0 K, this rank's shard: reconstruction after the last timed step vs its raw input",
+                "rel_l2": float(d.norm() / x.norm()), "max_abs": float(d.abs().max()),
+                "psnr_db": (10.0 * math.log10(peak * peak / mse)) if mse > 0 else None}
+    except Exception as e:  # noqa: BLE001 -- never lose the bench line over a side figure
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def measure_kernels(args, eng, ks, vs, ctype, world, rank, n_local, layers, transport, barrier):
+    """Per-kernel durations and the roofline of the dominant one.
+
+    Every kernel of the step is timed on its own: a CUDA graph holding that kernel's launch for ALL
+    layers (distinct buffers per layer: `layers` x tens of MB >> 126 MB L2, so every launch is cold) is
+    replayed between two CUDA events on the launching stream.  No per-launch events (they add a front-end
+    round trip of several us to a 10-20 us kernel)."""
+    versions = len(ks)
+    from compactfusion_b200 import _native as nv
+    e_tensor = n_local * CH
+    per_byte = 8 if args.codec == "binary" else 4
+    vsel = args.steps % versions
+    part_b = 148 // 2  # column/token partials written by pass 1 (one row block per CTA)
+    kernels = []
+
+    def time_kernel(name, fn, algo_bytes, reps=3):
+        barrier()
+        for layer in range(layers):
+            fn(layer)
+        torch.cuda.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for layer in range(layers):
+                    fn(layer)
+            run = g.replay
+        except Exception:
+            torch.cuda.synchronize()
+
+            def run():
+                for layer in range(layers):
+                    fn(layer)
+        run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            run()
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / (reps * layers)
+        kernels.append({"kernel": name, "avg_launch_us": us, "algorithmic_bytes_per_launch": algo_bytes,
+                        "achieved": algo_bytes / us / 1e3})
+
+    stats_name = "k_delta_stats_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_delta_stats"
+    apply_name = "k_apply_codes_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_apply_codes"
+    fused = world > 1 and eng.fused(ctype)
+    comp = eng.compress_put if fused else eng.compress
+    fan = world if fused else 1  # fused put: codes and scales are stored to all W receive slots (W-1 over NVLink)
+    # pass 1 over K and V of this rank: read x and base, write sign bits (BINARY) + partial sums
+    time_kernel(stats_name, lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
+                2 * (4 * e_tensor + (fan * e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
+    time_kernel("k_finalize_scales", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
+                2 * (4 * part_b * CH + 2 * n_local + fan * 2 * (n_local + CH)))
+    if fused:
+        for k_ in kernels:
+            k_["fused_put"] = True
+            k_["nvlink_bytes_per_launch"] = (world - 1) * 2 * (
+                (e_tensor // 8 if args.codec == "binary" else 0) if k_["kernel"] == stats_name else 2 * (n_local + CH))
+    if args.codec == "int2":
+        time_kernel("k_int2_encode_tma", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
+                    2 * (4 * e_tensor + fan * e_tensor // 4 + 2 * (n_local + CH)))
+        if fused:
+            kernels[-1]["fused_put"] = True
+            kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * 2 * (e_tensor // 4)
+    if transport == "p2p" and not fused:
+        # one-sided exchange: this rank's [K payload | V payload] stored into all W receive slots; W-1 of them
+        # cross NVLink (measured peer-copy peak 770 GB/s per direction, B200_PROFILING.md)
+        slot_bytes = 2 * (e_tensor // per_byte + 2 * (n_local + CH))
+        time_kernel("k_p2p_put", lambda l: eng.gather(ctype, l), (world + 1) * slot_bytes)
+        kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * slot_bytes
+        kernels[-1]["nvlink_gbs"] = (world - 1) * slot_bytes / kernels[-1]["avg_launch_us"] / 1e3
+        kernels[-1]["nvlink_frac_of_770"] = kernels[-1]["nvlink_gbs"] / 770.0
+    # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
+    if MODE == "ring":
+        n_launch_per_call = world
+
+        def dec(l):
+            for r in range(world):
+                eng.decompress(l, ctype, origins=(eng.hop_origin(r),))
+    else:
+        n_launch_per_call = (2 * world + 15) // 16
+
+        def dec(l):
+            eng.decompress(l, ctype)
+    time_kernel(apply_name, dec,
+                2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
+    note(rank, "per-kernel timing done")
+    kernels[-1]["avg_launch_us"] /= n_launch_per_call
+    kernels[-1]["algorithmic_bytes_per_launch"] //= n_launch_per_call
+    peak, peak_src = measured_hbm_peak()
+    k_total = sum(k["avg_launch_us"] * (n_launch_per_call if k["kernel"] == apply_name else 1) for k in kernels)
+    for k in kernels:
+        mult = n_launch_per_call if k["kernel"] == apply_name else 1
+        k["frac"] = k["achieved"] / peak
+        k["share_of_kernel_time"] = k["avg_launch_us"] * mult / k_total
+    dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
+    roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": ncu_traffic(dom["kernel"], args.codec, n_local, world), "kernel": dom["kernel"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_kernel_time"],
+                "peak_source": peak_src, "kernels": kernels,
+                "method": "each kernel alone: one CUDA graph with its launch for all layers (cold buffers), "
+                          "replayed 3x between two CUDA events"}
+    return roofline
+
+
+def measure_e2e(args, eng, sample, ctype, world, n_local, layers, device, transport, barrier):
+    """The same step with K/V in pinned host memory: H2D -> exchange -> D2H of the reconstructed global K/V,
+    double-buffered over three streams (copy in, compute, copy out).  Wall clock, max over ranks."""
+    e2e_layers = layers
+    hk = [torch.empty((n_local, CH), dtype=torch.half).pin_memory() for _ in range(2)]
+    hv = [torch.empty((n_local, CH), dtype=torch.half).pin_memory() for _ in range(2)]
+    for b_ in hk + hv:
+        b_.copy_(sample.cpu())
+    out_k = torch.empty((world * n_local, CH), dtype=torch.half).pin_memory()
+    out_v = torch.empty((world * n_local, CH), dtype=torch.half).pin_memory()
+    dk = [torch.empty((n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
+    dv = [torch.empty((n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
+    copy_in, copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    main_s = torch.cuda.current_stream()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        in_done = [None, None]
+        for layer in range(e2e_layers):
+            s = layer & 1
+            with torch.cuda.stream(copy_in):
+                dk[s].copy_(hk[s], non_blocking=True)
+                dv[s].copy_(hv[s], non_blocking=True)
+                in_done[s] = torch.cuda.Event()
+                in_done[s].record(copy_in)
+            main_s.wait_event(in_done[s])
+            gk, gv = eng.exchange(layer, dk[s], dv[s], ctype)
+            done = torch.cuda.Event()
+            done.record(main_s)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(done)
+                out_k.copy_(gk, non_blocking=True)
+                out_v.copy_(gv, non_blocking=True)
+            copy_in.wait_event(done)  # the staging buffer may be refilled only after its exchange
+        main_s.wait_stream(copy_out)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": job_bytes(layers, world) / e2e_s / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": world * layers * 2 * n_local * CH * 2,
+           "d2h_bytes_per_step": world * layers * 2 * world * n_local * CH * 2,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "path": f"pinned host K/V -> H2D -> {type(eng).__name__}.exchange (C-ABI batched kernels, transport "
+                   f"{transport}) -> D2H of reconstructed global K/V, double-buffered over 3 streams"}
+    return e2e
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -417,177 +595,11 @@ def main():
     ms_per_step = ms / args.steps
     value = job_bytes(layers, world) / (ms_per_step * 1e-3) / 1e9
 
-    # fidelity of what the timed steps produced (plumbing: plain torch reductions on one tensor)
-    fidelity = None
-    try:
-        x_last = ks[args.steps % versions][0].float()
-        d = eng._shard(eng.global_k[0], rank).float() - x_last
-        mse, peak = float((d * d).mean()), float(x_last.abs().max())
-        fidelity = {"tensor": "layer 0 K, this rank's shard: reconstruction after the last timed step vs its raw input",
-                    "rel_l2": float(d.norm() / x_last.norm()), "max_abs": float(d.abs().max()),
-                    "psnr_db": (10.0 * __import__("math").log10(peak * peak / mse)) if mse > 0 else None}
-        del x_last, d
-    except Exception as e:  # noqa: BLE001
-        fidelity = {"error": f"{type(e).__name__}: {e}"}
-
-    roofline = None
-    if not raw:
-        # ---- per-kernel durations and the roofline of the dominant one ---------------------------
-        # Every kernel of the step is timed on its own: a CUDA graph holding that kernel's launch for
-        # ALL layers (distinct buffers per layer: `layers` x tens of MB >> 126 MB L2, so every launch
-        # is cold) is replayed between two CUDA events on the launching stream.  No per-launch events
-        # (they add a front-end round trip of several us to a 10-20 us kernel).
-        from compactfusion_b200 import _native as nv
-        e_tensor = n_local * CH
-        per_byte = 8 if args.codec == "binary" else 4
-        vsel = args.steps % versions
-        part_b = 148 // 2  # column/token partials written by pass 1 (one row block per CTA)
-        kernels = []
-
-        def time_kernel(name, fn, algo_bytes, reps=3):
-            barrier()
-            for layer in range(layers):
-                fn(layer)
-            torch.cuda.synchronize()
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    for layer in range(layers):
-                        fn(layer)
-                run = g.replay
-            except Exception:
-                torch.cuda.synchronize()
-
-                def run():
-                    for layer in range(layers):
-                        fn(layer)
-            run()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                run()
-            b.record()
-            torch.cuda.synchronize()
-            us = a.elapsed_time(b) * 1e3 / (reps * layers)
-            kernels.append({"kernel": name, "avg_launch_us": us, "algorithmic_bytes_per_launch": algo_bytes,
-                            "achieved": algo_bytes / us / 1e3})
-
-        stats_name = "k_delta_stats_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_delta_stats"
-        apply_name = "k_apply_codes_tma" if os.environ.get("CF_LEGACY_KERNELS", "0") != "1" else "k_apply_codes"
-        fused = world > 1 and eng.fused(ctype)
-        comp = eng.compress_put if fused else eng.compress
-        fan = world if fused else 1  # fused put: codes and scales are stored to all W receive slots (W-1 over NVLink)
-        # pass 1 over K and V of this rank: read x and base, write sign bits (BINARY) + partial sums
-        time_kernel(stats_name, lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_STATS),
-                    2 * (4 * e_tensor + (fan * e_tensor // 8 if args.codec == "binary" else 0) + 2 * n_local + 4 * part_b * CH))
-        time_kernel("k_finalize_scales", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_FINALIZE),
-                    2 * (4 * part_b * CH + 2 * n_local + fan * 2 * (n_local + CH)))
-        if fused:
-            for k_ in kernels:
-                k_["fused_put"] = True
-                k_["nvlink_bytes_per_launch"] = (world - 1) * 2 * (
-                    (e_tensor // 8 if args.codec == "binary" else 0) if k_["kernel"] == stats_name else 2 * (n_local + CH))
-        if args.codec == "int2":
-            time_kernel("k_int2_encode_tma", lambda l: comp(l, ks[vsel][l], vs[vsel][l], ctype, nv.PASS_ENCODE),
-                        2 * (4 * e_tensor + fan * e_tensor // 4 + 2 * (n_local + CH)))
-            if fused:
-                kernels[-1]["fused_put"] = True
-                kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * 2 * (e_tensor // 4)
-        if transport == "p2p" and not fused:
-            # one-sided exchange: this rank's [K payload | V payload] stored into all W receive slots; W-1 of them
-            # cross NVLink (measured peer-copy peak 770 GB/s per direction, B200_PROFILING.md)
-            slot_bytes = 2 * (e_tensor // per_byte + 2 * (n_local + CH))
-            time_kernel("k_p2p_put", lambda l: eng.gather(ctype, l), (world + 1) * slot_bytes)
-            kernels[-1]["nvlink_bytes_per_launch"] = (world - 1) * slot_bytes
-            kernels[-1]["nvlink_gbs"] = (world - 1) * slot_bytes / kernels[-1]["avg_launch_us"] / 1e3
-            kernels[-1]["nvlink_frac_of_770"] = kernels[-1]["nvlink_gbs"] / 770.0
-        # reconstruct K and V of all W origins in place: read base + codes + scales, write recon
-        if MODE == "ring":
-            n_launch_per_call = world
-
-            def dec(l):
-                for r in range(world):
-                    eng.decompress(l, ctype, origins=(eng.hop_origin(r),))
-        else:
-            n_launch_per_call = (2 * world + 15) // 16
-
-            def dec(l):
-                eng.decompress(l, ctype)
-        time_kernel(apply_name, dec,
-                    2 * world * (2 * e_tensor + e_tensor // per_byte + 2 * (n_local + CH) + 2 * e_tensor))
-        note(rank, "per-kernel timing done")
-        kernels[-1]["avg_launch_us"] /= n_launch_per_call
-        kernels[-1]["algorithmic_bytes_per_launch"] //= n_launch_per_call
-        peak, peak_src = measured_hbm_peak()
-        k_total = sum(k["avg_launch_us"] * (n_launch_per_call if k["kernel"] == apply_name else 1) for k in kernels)
-        for k in kernels:
-            mult = n_launch_per_call if k["kernel"] == apply_name else 1
-            k["frac"] = k["achieved"] / peak
-            k["share_of_kernel_time"] = k["avg_launch_us"] * mult / k_total
-        dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
-        roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                    "traffic": ncu_traffic(dom["kernel"], args.codec, n_local, world), "kernel": dom["kernel"],
-                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
-                    "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_kernel_time"],
-                    "peak_source": peak_src, "kernels": kernels,
-                    "method": "each kernel alone: one CUDA graph with its launch for all layers (cold buffers), "
-                              "replayed 3x between two CUDA events"}
-
-    # ---- e2e: pinned host activations -> H2D -> exchange -> D2H of the reconstructed K/V -------
-    e2e = None
-    if not args.no_e2e:
-        e2e_layers = layers
-        hk = [torch.empty((n_local, CH), dtype=torch.half).pin_memory() for _ in range(2)]
-        hv = [torch.empty((n_local, CH), dtype=torch.half).pin_memory() for _ in range(2)]
-        for b_ in hk + hv:
-            b_.copy_(acts[0][0][0].cpu())
-        out_k = torch.empty((world * n_local, CH), dtype=torch.half).pin_memory()
-        out_v = torch.empty((world * n_local, CH), dtype=torch.half).pin_memory()
-        dk = [torch.empty((n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
-        dv = [torch.empty((n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
-        copy_in, copy_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-        main_s = torch.cuda.current_stream()
-        e2e_steps = max(2, min(args.steps, 5))
-
-        def e2e_step():
-            in_done = [None, None]
-            for layer in range(e2e_layers):
-                s = layer & 1
-                with torch.cuda.stream(copy_in):
-                    dk[s].copy_(hk[s], non_blocking=True)
-                    dv[s].copy_(hv[s], non_blocking=True)
-                    in_done[s] = torch.cuda.Event()
-                    in_done[s].record(copy_in)
-                main_s.wait_event(in_done[s])
-                gk, gv = eng.exchange(layer, dk[s], dv[s], ctype)
-                done = torch.cuda.Event()
-                done.record(main_s)
-                with torch.cuda.stream(copy_out):
-                    copy_out.wait_event(done)
-                    out_k.copy_(gk, non_blocking=True)
-                    out_v.copy_(gv, non_blocking=True)
-                copy_in.wait_event(done)  # the staging buffer may be refilled only after its exchange
-            main_s.wait_stream(copy_out)
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_s], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": job_bytes(layers, world) / e2e_s / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": world * layers * 2 * n_local * CH * 2,
-               "d2h_bytes_per_step": world * layers * 2 * world * n_local * CH * 2,
-               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-               "path": f"pinned host K/V -> H2D -> {engine_cls.__name__}.exchange (C-ABI batched kernels, transport "
-                       f"{transport}) -> D2H of reconstructed global K/V, double-buffered over 3 streams"}
-
+    fidelity = measure_fidelity(eng, ks[args.steps % versions][0], rank)
+    roofline = None if raw else measure_kernels(args, eng, ks, vs, ctype, world, rank, n_local, layers, transport,
+                                                barrier)
+    e2e = None if args.no_e2e else measure_e2e(args, eng, acts[0][0][0], ctype, world, n_local, layers, device,
+                                               transport, barrier)
     note(rank, "e2e done")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not raw:
