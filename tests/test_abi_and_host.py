@@ -605,3 +605,24 @@ def test_reference_example_presets_construct_against_this_package(capsys):
     finally:
         shim.uninstall()
     capsys.readouterr()
+
+
+def test_integration_md_stub_binds_against_the_library(built_lib):
+    """The ctypes stub INTEGRATION.md shows a reference maintainer is real code: it loads this library, its
+    prototypes agree with the binding the package itself uses, and it defines the reference's entry points."""
+    from compactfusion_b200 import _native as nv
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
+    stub = next(b for b in blocks if "_compactb200.py" in b)
+    stub = stub.replace('ctypes.CDLL("libcompactb200.so")', f'ctypes.CDLL({built_lib!r})')
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md:_compactb200.py", "exec"), ns)
+    for fn in ("binary_quant_fastpath", "binary_dequant_fastpath"):
+        assert callable(ns[fn])
+    lib = ns["_lib"]
+    for name in ("cf_binary_compress", "cf_int2_compress", "cf_binary_decompress", "cf_int2_decompress",
+                 "cf_workspace_bytes"):
+        res, args = nv.SYMBOLS[name]
+        assert list(getattr(lib, name).argtypes) == list(args), name
+        assert getattr(lib, name).restype is res, name
+    assert ns["_lib"].cf_workspace_bytes(1, 4608, 3072, 0, 1) == nv.workspace_bytes(nv.CODEC_BINARY, 4608, 3072)
