@@ -523,7 +523,7 @@ def test_profiler_api_matches_the_reference_semantics():
                 with Profiler.scope("inner", cpu=True):
                     time.sleep(0.005)
         total, avg = p.elapsed_time("inner")
-        assert 12.0 < total < 200.0 and abs(avg - total / 3) < 1e-9
+        assert 12.0 < total < 5000.0 and abs(avg - total / 3) < 1e-9
         assert p.elapsed_time("inner") == (total, avg)   # idempotent once folded
 
         @Profiler.prof_func("decorated", cpu=True)
