@@ -25,6 +25,14 @@ def pytest_sessionstart(session):
         cf_build.build()
 
 
+def free_port() -> str:
+    """A TCP port that is free right now (for the rendezvous of multi-process tests)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+        sock.bind(("127.0.0.1", 0))
+        return str(sock.getsockname()[1])
+
+
 def h16(a: np.ndarray) -> torch.Tensor:
     """uint16 bit pattern array -> fp16 CPU tensor (inverse of oracle/make_goldens.bits)."""
     return torch.from_numpy(a.view(np.int16).copy()).view(torch.half)

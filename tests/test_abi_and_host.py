@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import free_port
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -264,7 +266,7 @@ print("WORKER_OK", rank)
 def test_exchange_host_logic_gloo_world2(tmp_path, built_lib):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", OMP_NUM_THREADS="2")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=free_port(), OMP_NUM_THREADS="2")
     procs = []
     for r in range(2):
         e = dict(env, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r))

@@ -4,7 +4,7 @@ import os
 import pytest
 import torch
 
-from conftest import rel_l2
+from conftest import free_port, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -335,7 +335,7 @@ def test_two_gpu_all_gather_and_ring(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "w2.py"
     script.write_text(_two_gpu_worker_source())
-    env = dict(os.environ, CF_ROOT=root, MASTER_ADDR="127.0.0.1", MASTER_PORT="29641", WORLD_SIZE="2")
+    env = dict(os.environ, CF_ROOT=root, MASTER_ADDR="127.0.0.1", MASTER_PORT=free_port(), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]

@@ -8,6 +8,8 @@ import sys
 import pytest
 import torch
 
+from conftest import free_port
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -171,7 +173,7 @@ def test_two_gpu_ring_engine(tmp_path):
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "ring2.py"
     script.write_text(WORKER)
-    env = dict(os.environ, CF_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29653", WORLD_SIZE="2")
+    env = dict(os.environ, CF_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT=free_port(), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
@@ -338,7 +340,7 @@ def test_two_gpu_overlapped_step(tmp_path):
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "overlap2.py"
     script.write_text(OVERLAP_WORKER)
-    env = dict(os.environ, CF_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29654", WORLD_SIZE="2")
+    env = dict(os.environ, CF_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT=free_port(), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
