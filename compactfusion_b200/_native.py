@@ -38,6 +38,7 @@ SYMBOLS = {
     "cf_int2_encode_with_scales": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p]),
     "cf_sign_compress_passes": (c_int, [c_int, c_int, c_int] + [_VPP] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "cf_int4_compress": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "cf_int2mm_compress": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "cf_int4_decompress": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_void_p]),
     "cf_int8_compress": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "cf_int8_decompress": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_void_p]),

@@ -118,8 +118,19 @@ def sim_int2(input_tensor: torch.Tensor) -> torch.Tensor:
     return _sign_compress(nv.CODEC_INT2, x, None, True)[3]
 
 
+def sim_int2_minmax(input_tensor: torch.Tensor) -> torch.Tensor:
+    """Channel-wise 4-level min/max quantise-dequantise (simulation only).  compress_quantize.py:386-426.
+    As for sim_int4, a constant column (zero scale) reconstructs to its value instead of NaN."""
+    x = _check2d(input_tensor)
+    n = x.shape[0]
+    if n % 2:  # the nibble packing needs an even N; pad with a copy of the last row (min/max unchanged)
+        xp = torch.cat([x, x[-1:]], dim=0).contiguous()
+        return _minmax_compress(nv.CODEC_INT4, xp, None, want_recon=True, levels=3)[3][:n].contiguous()
+    return _minmax_compress(nv.CODEC_INT4, x, None, want_recon=True, levels=3)[3]
+
+
 # ------------------------------------------------------------------------------------ INT4 / INT8
-def _minmax_compress(codec, x, base, want_codes=True, want_recon=False):
+def _minmax_compress(codec, x, base, want_codes=True, want_recon=False, levels=15):
     nv.require_cuda_half(x, "x")
     n, c = x.shape
     dev = x.device
@@ -128,6 +139,8 @@ def _minmax_compress(codec, x, base, want_codes=True, want_recon=False):
         codes = torch.empty((n // 2, c), dtype=torch.uint8, device=dev)
         second = torch.empty((1, c), dtype=torch.half, device=dev)
         fn, name = nv.lib().cf_int4_compress, "cf_int4_compress"
+        if levels == 3:  # the 4-level simulation-only variant (sim_int2_minmax)
+            fn, name = nv.lib().cf_int2mm_compress, "cf_int2mm_compress"
     else:
         codes = torch.empty((n, c), dtype=torch.int8, device=dev)
         second = torch.empty((1, c), dtype=torch.int16, device=dev)

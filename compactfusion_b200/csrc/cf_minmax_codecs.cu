@@ -14,7 +14,10 @@
 
 namespace cf {
 
-enum { MODE_INT4 = 0, MODE_INT8 = 1 };
+// MODE_INT2MM: the reference's simulation-only 4-level min/max quantiser (sim_int2_minmax,
+// compress_quantize.py:386-426) -- the INT4 arithmetic with qmax = 3 instead of 15; codes travel in nibbles
+enum { MODE_INT4 = 0, MODE_INT8 = 1, MODE_INT2MM = 2 };
+template <int MODE> struct MmLevels { static constexpr int value = (MODE == MODE_INT2MM) ? 3 : 15; };
 __host__ __device__ constexpr int mm_unroll_for(int G) { return G == 1 ? 4 : (G == 2 ? 2 : 1); }
 
 __device__ __forceinline__ __half hdiv_exact(__half a, __half b) {
@@ -119,9 +122,10 @@ template <int MODE>
 __device__ __forceinline__ void finalize_column(__half mn, __half mx, int c, __half* __restrict__ scale_out,
                                                 void* __restrict__ second_out, __half* __restrict__ min_ws) {
   const __half diff = __hsub_rn(mx, mn);  // (max_val - min_val) in fp16
-  if (MODE == MODE_INT4) {
+  if (MODE == MODE_INT4 || MODE == MODE_INT2MM) {
     // scale = (max - min) / (15 + 1e-6): fp16 tensor / python scalar = fp32 divide by float(15.000001)
-    const __half s = __float2half_rn(__fdiv_rn(__half2float(diff), 15.000001f));  // compress_quantize.py:556
+    // (INT2MM: qmax - qmin + 1e-6 = 3.000001, compress_quantize.py:411)
+    const __half s = __float2half_rn(__fdiv_rn(__half2float(diff), MODE == MODE_INT4 ? 15.000001f : 3.000001f));  // compress_quantize.py:556
     scale_out[c] = s;
     static_cast<__half*>(second_out)[c] = mn;
   } else {
@@ -230,12 +234,13 @@ __device__ __forceinline__ __half hi_h(uint32_t w) { return __ushort_as_half(sta
 // [1024, 2048) where the fp16 spacing is 1, so the addition itself rounds half-to-even and the code is the
 // low mantissa bits.  NaN -> 0 (hmax2 returns the non-NaN operand).
 // ---------------------------------------------------------------------------------------
+template <int LEVELS = 15>
 __device__ __forceinline__ uint32_t int4_codes2(uint32_t d2, uint32_t mn2, uint32_t s2, float rcp0, float rcp1) {
   const float2 a = __half22float2(__hsub2_rn(u2h2(d2), u2h2(mn2)));  // (input - min_val)  :561
   const float t0 = quot_for_rn16(a.x, rcp0, lo_h(s2));
   const float t1 = quot_for_rn16(a.y, rcp1, hi_h(s2));
   __half2 h = __floats2half2_rn(t0, t1);                             // fp16(. / scale)
-  h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(15.f));
+  h = __hmin2(__hmax2(h, __float2half2_rn(0.f)), __float2half2_rn(static_cast<float>(LEVELS)));
   return h22u(__hadd2_rn(h, __float2half2_rn(1024.f)));              // 0x6400 + code per half
 }
 // biased (1024 + code) pair -> fp16(code * scale) + min
@@ -244,7 +249,7 @@ __device__ __forceinline__ __half2 int4_values2(uint32_t r2, uint32_t mn2, uint3
   return __hadd2_rn(__hmul2_rn(q, u2h2(s2)), u2h2(mn2));
 }
 
-template <int G, bool ENCODE>
+template <int G, bool ENCODE, int LEVELS = 15>
 __global__ void __launch_bounds__(512) k_int4_codec(const __half* __restrict__ x, const __half* __restrict__ base,
                                                     const __half* __restrict__ scale, const __half* __restrict__ minv,
                                                     uint8_t* __restrict__ packed, __half* __restrict__ out,
@@ -287,8 +292,8 @@ __global__ void __launch_bounds__(512) k_int4_codec(const __half* __restrict__ x
         uint32_t m[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          r0[i] = int4_codes2(d0.w[i], mfrag[j][i], sfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
-          r1[i] = int4_codes2(d1.w[i], mfrag[j][i], sfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
+          r0[i] = int4_codes2<LEVELS>(d0.w[i], mfrag[j][i], sfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
+          r1[i] = int4_codes2<LEVELS>(d1.w[i], mfrag[j][i], sfrag[j][i], rfrag[j][2 * i], rfrag[j][2 * i + 1]);
           m[i] = (r0[i] & 0x000F000Fu) | ((r1[i] & 0x000F000Fu) << 4);  // low nibble = even row  :573
         }
         // byte of column 2i sits in bits 0-7 of m[i], column 2i+1 in bits 16-23
@@ -410,10 +415,11 @@ __global__ void __launch_bounds__(512) k_int8_codec(const __half* __restrict__ x
 }
 
 // scalar forms for the generic (C % 8 != 0) path
+template <int LEVELS = 15>
 __device__ __forceinline__ uint32_t int4_code(__half d, __half mn, __half s) {
   const __half a = __hsub_rn(d, mn);                     // (input - min_val)          :561
   const float q = rintf(__half2float(hdiv_exact(a, s))); // round(. / scale), half-even :561
-  return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), 15.f));  // clamp; NaN -> 0         :564
+  return static_cast<uint32_t>(fminf(fmaxf(q, 0.f), static_cast<float>(LEVELS)));  // clamp; NaN -> 0 :564
 }
 __device__ __forceinline__ __half int4_value(uint32_t q, __half mn, __half s) {
   return __hadd_rn(__hmul_rn(__ushort2half_rn(static_cast<unsigned short>(q)), s), mn);  // q*scale + min :636
@@ -431,7 +437,7 @@ __device__ __forceinline__ __half int8_value(int q, __half s, __half zp_h) {
 }
 
 // ---- generic element-per-thread codecs for C % 8 != 0 --------------------------------------
-template <bool ENCODE>
+template <bool ENCODE, int LEVELS = 15>
 __global__ void __launch_bounds__(256) k_int4_codec_generic(const __half* __restrict__ x, const __half* __restrict__ base,
                                                             const __half* __restrict__ scale, const __half* __restrict__ minv,
                                                             uint8_t* __restrict__ packed, __half* __restrict__ out,
@@ -446,8 +452,8 @@ __global__ void __launch_bounds__(256) k_int4_codec_generic(const __half* __rest
     const __half b0 = base ? base[o0] : zero, b1 = base ? base[o1] : zero;
     uint32_t q0, q1;
     if (ENCODE) {
-      q0 = int4_code(base ? __hsub_rn(x[o0], b0) : x[o0], mn, s);
-      q1 = int4_code(base ? __hsub_rn(x[o1], b1) : x[o1], mn, s);
+      q0 = int4_code<LEVELS>(base ? __hsub_rn(x[o0], b0) : x[o0], mn, s);
+      q1 = int4_code<LEVELS>(base ? __hsub_rn(x[o1], b1) : x[o1], mn, s);
       packed[i] = static_cast<uint8_t>(q0 | (q1 << 4));
     } else {
       const uint32_t byte = packed[i];
@@ -544,8 +550,8 @@ static int minmax_compress_generic(const __half* xh, const __half* bh, void* new
                                    void* second, int n, int c, cudaStream_t st) {
   k_minmax_column_generic<MODE><<<c, 256, 0, st>>>(xh, bh, n, c, static_cast<__half*>(scale), second);
   CF_CHECK_LAUNCH();
-  if (MODE == MODE_INT4)
-    k_int4_codec_generic<true><<<generic_grid(static_cast<size_t>(n / 2) * c), 256, 0, st>>>(
+  if (MODE != MODE_INT8)
+    k_int4_codec_generic<true, MmLevels<MODE>::value><<<generic_grid(static_cast<size_t>(n / 2) * c), 256, 0, st>>>(
         xh, bh, static_cast<const __half*>(scale), static_cast<const __half*>(second), static_cast<uint8_t*>(codes),
         static_cast<__half*>(new_base), n, c);
   else
@@ -560,10 +566,9 @@ template <int MODE>
 static int minmax_compress(const void* x, const void* base, void* new_base, void* codes, void* scale,
                            void* second, int64_t N, int64_t C, void* workspace, size_t workspace_bytes,
                            cudaStream_t st) {
-  if (int rc = check_mm_shape(N, C, MODE == MODE_INT4)) return rc;
+  if (int rc = check_mm_shape(N, C, MODE != MODE_INT8)) return rc;
   CF_CHECK_ARG(x && codes && scale && second, "null pointer");
   CF_CHECK_ARG(aligned2(scale) && aligned2(second), "scale vectors must be 2-byte aligned");
-  if (int rc0 = check_mm_shape(N, C, MODE == MODE_INT4)) return rc0;
   if (C % 8 != 0)
     return minmax_compress_generic<MODE>(static_cast<const __half*>(x), static_cast<const __half*>(base), new_base,
                                          codes, scale, second, static_cast<int>(N), static_cast<int>(C), st);
@@ -599,11 +604,11 @@ static int minmax_compress(const void* x, const void* base, void* new_base, void
   CF_CHECK_LAUNCH();
   k_minmax_finalize<MODE><<<(c + 31) / 32, 256, 0, st>>>(pmin, pmax, pl.B, c, static_cast<__half*>(scale), second, min_ws);
   CF_CHECK_LAUNCH();
-  if (MODE == MODE_INT4) {
+  if (MODE != MODE_INT8) {
     dim3 grid(grid_rows(pl.geom, N / 2));
 #define CF_I4(GG)                                                                               \
   case GG:                                                                                      \
-    k_int4_codec<GG, true><<<grid, block, 0, st>>>(xh, bh, static_cast<const __half*>(scale),   \
+    k_int4_codec<GG, true, MmLevels<MODE>::value><<<grid, block, 0, st>>>(xh, bh, static_cast<const __half*>(scale),   \
                                                    static_cast<const __half*>(second),          \
                                                    static_cast<uint8_t*>(codes),                \
                                                    static_cast<__half*>(new_base), n, c);       \
@@ -685,6 +690,11 @@ int cf_int4_compress(const void* x, const void* base, void* new_base, void* pack
                      int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
   return cf::minmax_compress<cf::MODE_INT4>(x, base, new_base, packed, scale, minv, N, C, workspace,
                                             workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int cf_int2mm_compress(const void* x, const void* base, void* new_base, void* packed, void* scale, void* minv,
+                       int64_t N, int64_t C, void* workspace, size_t workspace_bytes, cf_stream_t stream) {
+  return cf::minmax_compress<cf::MODE_INT2MM>(x, base, new_base, packed, scale, minv, N, C, workspace,
+                                              workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 int cf_int4_decompress(const void* packed, const void* scale, const void* minv, const void* base, void* recon,
                        int64_t N, int64_t C, cf_stream_t stream) {

@@ -9,7 +9,7 @@ import torch
 
 from .compress_lowrank import lowrank_reconstruct, subspace_iter
 from .compress_quantize import (dequantize_1bit, dequantize_int2, dequantize_int4, quantize_1bit, quantize_int2,
-                                quantize_int4, sim_binary, sim_int2, sim_int4)
+                                quantize_int4, sim_binary, sim_int2, sim_int2_minmax, sim_int4)
 from .compress_topk import SPARSE_LAST_DIM_SIZE, sim_topk, topk_compress, topk_decompress
 from .utils import COMPACT_COMPRESS_TYPE
 
@@ -119,7 +119,8 @@ def sim_compress(x: torch.Tensor, compress_type: COMPACT_COMPRESS_TYPE, sparse_r
         assert rank is not None
         u, v, _ = subspace_iter(x, rank, 2)
         return lowrank_reconstruct(sim_int4(u, dim=0), sim_int4(v, dim=1))
-    if compress_type in (T.INT2_MINMAX, T.LOW_RANK_AWL):
-        raise ValueError(f"{compress_type} is a deprecated / simulation-only experiment of the reference "
-                         "and is not provided")
+    if compress_type == T.INT2_MINMAX:
+        return sim_int2_minmax(x)
+    if compress_type == T.LOW_RANK_AWL:
+        raise ValueError(f"{compress_type} is a deprecated experiment of the reference and is not provided")
     raise ValueError("Invalid compress_type value")

@@ -157,6 +157,14 @@ CF_API int cf_int4_compress(const void* x, const void* base, void* new_base, voi
 CF_API int cf_int4_decompress(const void* packed, const void* scale, const void* minv,
                        const void* base, void* recon, int64_t N, int64_t C,
                        cf_stream_t stream);
+/* The reference's simulation-only 4-level min/max quantiser, sim_int2_minmax (compress_quantize.py:386-426;
+ * COMPACT_COMPRESS_TYPE.INT2_MINMAX in sim_compress, slowpath.py:203-204): the INT4 arithmetic with
+ * qmax = 3 -- scale = fp16((max-min)/(3+1e-6)), q = clamp(rne((v-min)/scale),0,3).  Same arguments as
+ * cf_int4_compress (workspace of CF_CODEC_INT4 size); the codes are written as nibbles (0..3) and are not a
+ * wire format -- the result is new_base = base + (q*scale + min). */
+CF_API int cf_int2mm_compress(const void* x, const void* base, void* new_base, void* packed,
+                       void* scale, void* minv, int64_t N, int64_t C, void* workspace,
+                       size_t workspace_bytes, cf_stream_t stream);
 /* INT8 replaces quantize_int8 / dequantize_int8 (compress_quantize.py:428-484):
  * outputs: q (N,C) i8, scale (1,C) fp16, zero_point (1,C) i16. */
 CF_API int cf_int8_compress(const void* x, const void* base, void* new_base, void* q, void* scale,

@@ -364,3 +364,24 @@ def test_plain_c_client_round_trip(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "C_CLIENT_OK 544x3072" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", ["rand_64x256", "rand_48x1152", "rand_130x64", "flux_k_96x512"])
+def test_sim_int2_minmax_matches_reference_golden(name):
+    """The 4-level min/max simulation codec (cf_int2mm_compress: the INT4 kernels at qmax = 3) against what
+    the reference's sim_int2_minmax produced on the committed inputs: bit-exact (min/max are exact)."""
+    dev = _cuda()
+    import numpy as np
+    from conftest import GOLDEN, assert_bits_equal, h16
+    from compactfusion_b200.compress_quantize import sim_int2_minmax
+    from compactfusion_b200.slowpath import sim_compress
+    from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+    from oracle import codecs as oc
+    g = np.load(os.path.join(GOLDEN, "codecs.npz"))
+    d = h16(g[f"{name}/x"]) - h16(g[f"{name}/base"])
+    got = sim_int2_minmax(d.to(dev))
+    assert_bits_equal(got, h16(g[f"{name}/sim_int2_minmax"]), "sim_int2_minmax")
+    assert torch.equal(sim_compress(d.to(dev), T.INT2_MINMAX), got)
+    assert all(len(torch.unique(got[:, c])) <= 4 for c in range(0, got.shape[1], 17))  # 4 levels per channel
+    odd = d[:-1].contiguous()  # odd N: padded with a copy of the last row inside the wrapper
+    assert_bits_equal(sim_int2_minmax(odd.to(dev)), oc.sim_int2_minmax(odd), "sim_int2_minmax, odd N")
