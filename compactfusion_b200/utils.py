@@ -78,9 +78,8 @@ class CompactConfig:
             assert not simulate, "Fastpath does not support simulation."
             assert residual == 1, "Fastpath requires 1st order residual."
         if quantized_cache:
-            # int8 cache storage is deprecated in the reference (utils.py:128-129) and not provided here
+            # int8 cache storage: deprecated in the reference, gated the same way (utils.py:128-129)
             assert ALLOW_DEPRECATED, "quantized_cache is deprecated"
-            raise NotImplementedError("quantized_cache (deprecated int8 cache storage) is not supported")
         if override_with_patch_gather_fwd:
             assert enabled, "Compact must be enabled if override_with_patch_gather_fwd is True"
             assert patch_gather_fwd_config is not None, \
@@ -108,18 +107,29 @@ class CompactCache:
     """
 
     def __init__(self, quantize=False):
-        assert not quantize, "quantized cache is not supported"
-        self.quantize = False
+        self.quantize = quantize
         self.base = {}
         self.delta_base = {}
+        if quantize:
+            assert ALLOW_DEPRECATED  # utils.py:128-129
         self.passed_count = 0
 
     def put(self, key, base, delta_base):
+        """With `quantize` the base is stored as per-channel int8 (q, scale, zero_point) and dequantised on
+        every read (utils.py:134-136, :151-155: quantize_int8 / dequantize_int8, here the sm_100a codec)."""
+        if self.quantize:
+            from .compress_quantize import quantize_int8
+            base = quantize_int8(base.reshape(-1, base.shape[-1]) if base.dim() != 2 else base) + (base.shape,)
         self.base[key] = base
         self.delta_base[key] = delta_base
 
     def get_base(self, key):
-        return self.base.get(key, None)
+        base = self.base.get(key, None)
+        if self.quantize and base is not None:
+            from .compress_quantize import dequantize_int8
+            q, scale, zp, shape = base
+            base = dequantize_int8(q, scale, zp).view(shape)
+        return base
 
     def get_delta_base(self, key):
         return self.delta_base.get(key, None)

@@ -628,3 +628,34 @@ def test_integration_md_stub_binds_against_the_library(built_lib):
         assert list(getattr(lib, name).argtypes) == list(args), name
         assert getattr(lib, name).restype is res, name
     assert ns["_lib"].cf_workspace_bytes(1, 4608, 3072, 0, 1) == nv.workspace_bytes(nv.CODEC_BINARY, 4608, 3072)
+
+
+def test_quantized_cache_host_logic(monkeypatch):
+    """CompactCache(quantize=True): deprecated gate, int8 storage tuple, dequantise-on-read -- with the codec
+    calls replaced by the oracle IN THE TEST ONLY."""
+    from compactfusion_b200 import compress_quantize as cq
+    from compactfusion_b200 import utils
+    from oracle import codecs as oc
+    monkeypatch.setattr(utils, "ALLOW_DEPRECATED", False)
+    with pytest.raises(AssertionError):
+        utils.CompactCache(quantize=True)
+    with pytest.raises(AssertionError):
+        utils.CompactConfig(enabled=True, residual=1, ef=True, quantized_cache=True)
+    monkeypatch.setattr(utils, "ALLOW_DEPRECATED", True)
+    assert utils.CompactConfig(enabled=True, residual=1, ef=True, quantized_cache=True).quantized_cache
+    monkeypatch.setattr(cq, "quantize_int8", lambda t: tuple(oc.int8_quantize(t)))
+    monkeypatch.setattr(cq, "dequantize_int8", lambda q, s, z: oc.int8_dequantize(q, s, z))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(64, 128, generator=g).half()
+    cache = utils.CompactCache(quantize=True)
+    cache.put("0-0-k", x, x * 0)
+    stored = cache.base["0-0-k"]
+    assert isinstance(stored, tuple) and len(stored) == 4 and stored[3] == x.shape
+    got = cache.get_base("0-0-k")
+    assert got.shape == x.shape and got.dtype == torch.half
+    assert torch.equal(got, oc.int8_dequantize(*oc.int8_quantize(x)))
+    assert float((got.float() - x.float()).norm() / x.float().norm()) < 2e-2
+    assert cache.get_delta_base("0-0-k") is not None and cache.get_base("nope") is None
+    plain = utils.CompactCache()
+    plain.put("k", x, None)
+    assert plain.get_base("k") is x

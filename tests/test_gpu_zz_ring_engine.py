@@ -385,3 +385,45 @@ def test_sim_int2_minmax_matches_reference_golden(name):
     assert all(len(torch.unique(got[:, c])) <= 4 for c in range(0, got.shape[1], 17))  # 4 levels per channel
     odd = d[:-1].contiguous()  # odd N: padded with a copy of the last row inside the wrapper
     assert_bits_equal(sim_int2_minmax(odd.to(dev)), oc.sim_int2_minmax(odd), "sim_int2_minmax, odd N")
+
+
+def test_quantized_cache_stores_int8_and_keeps_sender_and_receiver_identical(monkeypatch):
+    """CompactConfig(quantized_cache=True) (deprecated in the reference, gated by COMPACT_ALLOW_DEPRECATED like
+    there): bases are stored as per-channel int8 and dequantised on every read (utils.py:123-160)."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200 import utils
+    from compactfusion_b200.compress_quantize import dequantize_int8, quantize_int8
+    from conftest import rel_l2
+    monkeypatch.setattr(utils, "ALLOW_DEPRECATED", False)
+    with pytest.raises(AssertionError):
+        utils.CompactCache(quantize=True)
+    with pytest.raises(AssertionError):
+        cf.CompactConfig(enabled=True, residual=1, ef=True, quantized_cache=True)
+    monkeypatch.setattr(utils, "ALLOW_DEPRECATED", True)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(256, 512, generator=g).half().to(dev)
+    cache = utils.CompactCache(quantize=True)
+    cache.put("0-0-k", x, None)
+    q, scale, zp, shape = cache.base["0-0-k"]
+    assert q.dtype == torch.int8 and shape == x.shape
+    got = cache.get_base("0-0-k")
+    assert torch.equal(got, dequantize_int8(*quantize_int8(x))) and got.shape == x.shape
+    assert cache.get_delta_base("0-0-k") is None and cache.get_base("missing") is None
+    assert rel_l2(got, x) < 2e-2
+    # through the plugin: residual 1 + EF on a quantised cache; both sides cache the same reconstruction
+    T = cf.COMPACT_COMPRESS_TYPE
+    cfg = cf.CompactConfig(enabled=True, residual=1, ef=True, simulate=True, quantized_cache=True, comp_rank=-1,
+                           compress_func=lambda l, s: T.INT4 if s >= 1 else T.WARMUP)
+    cf.compact_init(cfg)
+    shape4 = (1, 256, 8, 64)
+    xs = [x.view(shape4)]
+    for t in range(1, 4):
+        xs.append((0.97 * xs[-1].float() + 0.2 * torch.randn(shape4, generator=g).to(dev)).half())
+    for t, xt in enumerate(xs):
+        ct = cfg.compress_func(0, t)
+        comp = cf.compact_compress("0-0-k", xt, ct, update_cache=True)
+        rec = cf.compact_decompress("1-0-k", comp, ct, shape4, update_cache=True)
+        assert isinstance(cf.compact_cache().base["0-0-k"], tuple)
+        assert torch.equal(cf.compact_cache().get_base("0-0-k"), cf.compact_cache().get_base("1-0-k"))
+        assert rel_l2(rec.reshape(-1), xt.reshape(-1)) < 0.3
