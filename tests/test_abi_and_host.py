@@ -418,7 +418,7 @@ def _build_c_client(tmp_path, built_lib):
 def test_plain_c_client_links_and_its_checker_agrees_with_the_oracle(tmp_path, built_lib):
     """examples/c_client.c (C99, no torch): links against the shared library, the device-free calls work, and
     its bit-exact property checker accepts the ORACLE's BINARY round trip and rejects corrupted ones -- so the
-    GPU run of the same program (tests/test_gpu_zz_ring_engine.py) is judged by a checked checker."""
+    GPU run of the same program (tests/test_gpu_zy_consumers_stats_abi.py) is judged by a checked checker."""
     from oracle import codecs as oc
     exe = _build_c_client(tmp_path, built_lib)
     r = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True)
