@@ -139,12 +139,16 @@ static inline uint4 ldg_stream(const void* p) { return *static_cast<const uint4*
 static inline void stg_stream(void* p, const uint4& v) { *static_cast<uint4*>(p) = v; }
 static inline void stg_stream_pol(void* p, const uint4& v, uint64_t) { *static_cast<uint4*>(p) = v; }
 
+#ifndef EMU_LAUNCH_HOOK
+#define EMU_LAUNCH_HOOK
+#endif
 template <class F> static void launch(unsigned gx, unsigned gy, unsigned bx, unsigned by, F body) {
   gridDim.x = gx; gridDim.y = gy; blockDim.x = bx; blockDim.y = by;
   const unsigned nthreads = bx * by;
   for (unsigned cy = 0; cy < gy; ++cy)
     for (unsigned cx = 0; cx < gx; ++cx) {
       pthread_barrier_init(&cta_bar, nullptr, nthreads);
+      EMU_LAUNCH_HOOK
       for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_init(&warp_bar[w], nullptr, 32);
       std::vector<std::thread> ts;
       for (unsigned ty = 0; ty < by; ++ty)
@@ -184,6 +188,67 @@ static inline __half __ushort2half_rn(unsigned short v) { return __float2half_rn
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 '''
 
+
+PIPE_SHIM = r'''
+// ---- stand-ins for csrc/cf_pipe.cuh (all inline PTX there): mbarriers, bulk copies, shared-window loads ----
+#include <atomic>
+#include <mutex>
+#include <sched.h>
+static unsigned char* const emu_smem_bytes = reinterpret_cast<unsigned char*>(emu_smem);
+static pthread_barrier_t compute_bar;
+static int emu_ncompute = 0;   // set by the runner before a launch of a pipelined kernel
+struct EmuMbar { std::mutex m; uint32_t init = 0, pending = 0; int64_t tx = 0; uint32_t phase = 0; };
+static EmuMbar emu_mbars[64];
+static inline EmuMbar& mbar_of(const uint64_t* bar) {
+  // barriers live in the shared-memory image; the side table is indexed by their slot in it
+  const size_t off = reinterpret_cast<const unsigned char*>(bar) - emu_smem_bytes;
+  return emu_mbars[(off / 8) % 64];
+}
+static inline void mbar_complete_locked(EmuMbar& b) {
+  if (b.pending == 0 && b.tx == 0) { b.phase += 1; b.pending = b.init; }
+}
+static inline uint32_t smem_addr(const void* p) { return (uint32_t)(static_cast<const unsigned char*>(p) - emu_smem_bytes); }
+static inline void mbar_init(uint64_t* bar, uint32_t count) {
+  EmuMbar& b = mbar_of(bar); std::lock_guard<std::mutex> g(b.m); b.init = b.pending = count; b.tx = 0; b.phase = 0;
+}
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  EmuMbar& b = mbar_of(bar); std::lock_guard<std::mutex> g(b.m); b.tx += bytes; b.pending -= 1; mbar_complete_locked(b);
+}
+static inline void mbar_arrive(uint64_t* bar) {
+  EmuMbar& b = mbar_of(bar); std::lock_guard<std::mutex> g(b.m); b.pending -= 1; mbar_complete_locked(b);
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  EmuMbar& b = mbar_of(bar);
+  for (;;) {
+    { std::lock_guard<std::mutex> g(b.m); if ((b.phase & 1u) != parity) return; }
+    sched_yield();
+  }
+}
+static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  // the rules of cp.async.bulk: 16-byte aligned addresses, size a multiple of 16
+  if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15u) { fprintf(stderr, "misaligned bulk copy\n"); abort(); }
+  memcpy(dst, src, bytes);
+  EmuMbar& b = mbar_of(bar); std::lock_guard<std::mutex> g(b.m); b.tx -= bytes; mbar_complete_locked(b);
+}
+static inline void bulk_g2s_hint(void* d, const void* s, uint32_t n, uint64_t* bar, uint64_t) { bulk_g2s(d, s, n, bar); }
+static inline void bulk_g2s_pol(void* d, const void* s, uint32_t n, uint64_t* bar, uint64_t) { bulk_g2s(d, s, n, bar); }
+static inline uint64_t make_policy_evict_first() { return 1; }
+static inline uint64_t make_policy_evict_last() { return 2; }
+static inline void compute_sync(int) { pthread_barrier_wait(&compute_bar); }
+static inline void __syncwarp() {
+  const unsigned lin = threadIdx.y * blockDim.x + threadIdx.x;
+  pthread_barrier_wait(&warp_bar[lin >> 5]);
+}
+static inline uint4 lds128a(uint32_t a) { uint4 r; memcpy(&r, emu_smem_bytes + a, 16); return r; }
+static inline uint4 lds128(const void* p) { uint4 r; memcpy(&r, p, 16); return r; }
+static inline uint32_t lds8a(uint32_t a) { return emu_smem_bytes[a]; }
+static inline uint32_t lds16a(uint32_t a) { uint16_t r; memcpy(&r, emu_smem_bytes + a, 2); return r; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+'''
 
 SLURP = r'''
 static std::vector<unsigned char> slurp(const char* path) {
