@@ -36,11 +36,32 @@ static int run(const __half* x, int N, int C, int rows_per_cta) {
   return 0;
 }
 
-int main(int argc, char** argv) {  // <int4|int2mm> x.bin N C rows_per_cta
+static int run_int8(const __half* x, int N, int C, int rows_per_cta) {
+  using namespace cf;
+  const RowGeom g = make_row_geom(C);
+  if (g.G != 1) return 3;
+  const int B = (N + rows_per_cta - 1) / rows_per_cta;
+  std::vector<__half> pmin((size_t)B * C), pmax((size_t)B * C), scale(C), min_ws(C), recon((size_t)N * C), deq((size_t)N * C);
+  std::vector<int16_t> zp(C);
+  std::vector<int8_t> q((size_t)N * C, 77);
+  launch(B, 1, g.TX, g.TY, [&] { k_minmax_stats<1>(x, nullptr, pmin.data(), pmax.data(), N, C, rows_per_cta); });
+  launch((C + 31) / 32, 1, 256, 1, [&] { k_minmax_finalize<MODE_INT8>(pmin.data(), pmax.data(), B, C, scale.data(), zp.data(), min_ws.data()); });
+  launch(2, 1, g.TX, g.TY, [&] { k_int8_codec<1, true>(x, nullptr, scale.data(), zp.data(), q.data(), recon.data(), N, C); });
+  launch(3, 1, g.TX, g.TY, [&] { k_int8_codec<1, false>(nullptr, nullptr, scale.data(), zp.data(), q.data(), deq.data(), N, C); });
+  fwrite(q.data(), 1, q.size(), stdout);
+  fwrite(scale.data(), 2, C, stdout);
+  fwrite(zp.data(), 2, C, stdout);
+  fwrite(recon.data(), 2, recon.size(), stdout);
+  fwrite(deq.data(), 2, deq.size(), stdout);
+  return 0;
+}
+
+int main(int argc, char** argv) {  // <int4|int2mm|int8> x.bin N C rows_per_cta
   const std::string mode = argv[1];
   auto x = slurp(argv[2]);
   const int N = atoi(argv[3]), C = atoi(argv[4]), rpc = atoi(argv[5]);
   const __half* xh = reinterpret_cast<const __half*>(x.data());
+  if (mode == "int8") return run_int8(xh, N, C, rpc);
   return mode == "int4" ? run<cf::MODE_INT4>(xh, N, C, rpc) : run<cf::MODE_INT2MM>(xh, N, C, rpc);
 }
 '''
@@ -62,14 +83,14 @@ def _run(emulator, mode, d16, rows_per_cta):
     (d / "x.bin").write_bytes(d16.numpy().tobytes())
     r = subprocess.run([exe, mode, str(d / "x.bin"), str(n), str(c), str(rows_per_cta)], capture_output=True, timeout=900)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
-    sizes = [n // 2 * c, 2 * c, 2 * c, 2 * n * c, 2 * n * c]
+    sizes = [(n if mode == "int8" else n // 2) * c, 2 * c, 2 * c, 2 * n * c, 2 * n * c]
     assert len(r.stdout) == sum(sizes)
     parts, o = [], 0
     for s in sizes:
         parts.append(r.stdout[o:o + s])
         o += s
     u16 = lambda b, shape: np.frombuffer(b, dtype=np.uint16).reshape(shape)  # noqa: E731
-    return (np.frombuffer(parts[0], dtype=np.uint8).reshape(n // 2, c), u16(parts[1], (1, c)), u16(parts[2], (1, c)),
+    return (np.frombuffer(parts[0], dtype=np.uint8).reshape(-1, c), u16(parts[1], (1, c)), u16(parts[2], (1, c)),
             u16(parts[3], (n, c)), u16(parts[4], (n, c)))
 
 
@@ -89,3 +110,9 @@ def test_int4_and_int2_minmax_kernel_source_match_the_reference_goldens(emulator
     assert np.array_equal(recon2, bits16(h16(g[f"{name}/sim_int2_minmax"])).reshape(recon2.shape)), "sim_int2_minmax differs"
     assert np.array_equal(recon2, deq2) and np.array_equal(mn2, mn)
     assert int((packed2 & 0x0F).max()) <= 3 and int((packed2 >> 4).max()) <= 3
+    # INT8 (per-channel affine, int16 zero point)
+    q8, s8, zp8, recon8, deq8 = _run(emulator, "int8", d16, rows_per_cta)
+    assert np.array_equal(q8.view(np.int8), g[f"{name}/int8_q"]), "INT8 codes differ from the reference"
+    assert np.array_equal(s8, bits16(h16(g[f"{name}/int8_scale"])).reshape(s8.shape))
+    assert np.array_equal(zp8.view(np.int16), g[f"{name}/int8_zp"].reshape(zp8.shape))
+    assert np.array_equal(deq8, bits16(h16(g[f"{name}/int8_deq"])).reshape(deq8.shape)) and np.array_equal(recon8, deq8)
