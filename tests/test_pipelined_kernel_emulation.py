@@ -110,7 +110,10 @@ int main(int argc, char** argv) {  // <binary|int2> x.bin base.bin N C stats_cta
   const __half* bh = reinterpret_cast<const __half*>(b.data());
   const cf::PipeGeom g = cf::make_pipe_geom(C, 2, 0, false);
   if (!g.ok) { fprintf(stderr, "no pipelined geometry for C=%d\n", C); return 3; }
-  if (g.G != 1) { fprintf(stderr, "this runner instantiates G = 1 only\n"); return 3; }
+  if (g.G == 2) {   // C > 4096: two column groups per thread, one CTA per SM
+    if (g.ctas_per_sm != 1) { fprintf(stderr, "unexpected G = 2 geometry\n"); return 3; }
+    return mode == "binary" ? run<cf::MODE_BINARY, 2, 1>(xh, bh, N, C, sc, ac) : run<cf::MODE_INT2, 2, 1>(xh, bh, N, C, sc, ac);
+  }
   if (mode == "binary") return g.ctas_per_sm == 2 ? run<cf::MODE_BINARY, 1, 2>(xh, bh, N, C, sc, ac) : run<cf::MODE_BINARY, 1, 1>(xh, bh, N, C, sc, ac);
   return g.ctas_per_sm == 2 ? run<cf::MODE_INT2, 1, 2>(xh, bh, N, C, sc, ac) : run<cf::MODE_INT2, 1, 1>(xh, bh, N, C, sc, ac);
 }
@@ -184,10 +187,11 @@ def test_pipelined_int2_kernel_source_matches_the_oracle(emulator, n, c, stats_c
 
 
 # edge shapes: fewer rows than one tile / one quad, a single row, the smallest C (8 column groups: 24 idle
-# lanes per warp), the widest single-group C, row counts one past a tile boundary
+# lanes per warp), the widest single-group C, row counts one past a tile boundary, and C > 4096 (two column
+# groups per thread, one CTA per SM; 6144 leaves the second group partly idle)
 @pytest.mark.parametrize("mode", ["binary", "int2"])
 @pytest.mark.parametrize("n,c,stats_ctas,apply_ctas", [(3, 256, 1, 1), (1, 64, 1, 1), (129, 64, 2, 3), (5, 4096, 1, 2),
-                                                       (65, 128, 4, 4), (64, 256, 1, 1)])
+                                                       (65, 128, 4, 4), (64, 256, 1, 1), (6, 6144, 1, 1)])
 def test_pipelined_kernel_source_edge_shapes(emulator, mode, n, c, stats_ctas, apply_ctas):
     if (c // (8 if mode == "binary" else 4)) % 16:
         pytest.skip("the host dispatch (launch_apply) sends code rows that are not a multiple of 16 bytes to the "
