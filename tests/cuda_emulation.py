@@ -143,19 +143,28 @@ static inline void stg_stream_pol(void* p, const uint4& v, uint64_t) { *static_c
 #define EMU_LAUNCH_HOOK
 #endif
 template <class F> static void launch(unsigned gx, unsigned gy, unsigned bx, unsigned by, F body) {
+  // one set of OS threads per launch; they walk the CTAs together (a barrier between CTAs: shared memory and
+  // the __shared__ statics belong to one CTA at a time)
   gridDim.x = gx; gridDim.y = gy; blockDim.x = bx; blockDim.y = by;
   const unsigned nthreads = bx * by;
-  for (unsigned cy = 0; cy < gy; ++cy)
-    for (unsigned cx = 0; cx < gx; ++cx) {
-      pthread_barrier_init(&cta_bar, nullptr, nthreads);
-      EMU_LAUNCH_HOOK
-      for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_init(&warp_bar[w], nullptr, 32);
-      std::vector<std::thread> ts;
-      for (unsigned ty = 0; ty < by; ++ty)
-        for (unsigned tx = 0; tx < bx; ++tx)
-          ts.emplace_back([=] { threadIdx.x = tx; threadIdx.y = ty; blockIdx.x = cx; blockIdx.y = cy; body(); });
-      for (auto& t : ts) t.join();
-    }
+  static pthread_barrier_t between;
+  pthread_barrier_init(&cta_bar, nullptr, nthreads);
+  pthread_barrier_init(&between, nullptr, nthreads);
+  for (unsigned w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_init(&warp_bar[w], nullptr, 32);
+  EMU_LAUNCH_HOOK
+  std::vector<std::thread> ts;
+  for (unsigned ty = 0; ty < by; ++ty)
+    for (unsigned tx = 0; tx < bx; ++tx)
+      ts.emplace_back([=] {
+        threadIdx.x = tx; threadIdx.y = ty;
+        for (unsigned cy = 0; cy < gy; ++cy)
+          for (unsigned cx = 0; cx < gx; ++cx) {
+            blockIdx.x = cx; blockIdx.y = cy;
+            body();
+            pthread_barrier_wait(&between);
+          }
+      });
+  for (auto& t : ts) t.join();
 }
 
 // ---- more fp16 / fp32 intrinsics (min/max codecs) ----
