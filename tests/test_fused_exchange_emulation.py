@@ -189,3 +189,80 @@ def test_fused_put_and_flag_waiting_reconstruct_on_cpu(emulator, mode, world, n,
     r = subprocess.run([exe, mode, str(d / "x.bin"), str(d / "b.bin"), str(world), str(n), str(c)],
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and f"FUSED_EXCHANGE_OK W={world}" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
+WAIT_RUNNER = r'''
+#include <chrono>
+// A late sender: the receiver's flag-waiting reconstruct is launched FIRST; another thread then writes the
+// payload into the slot and only afterwards raises the flag.  The kernel must not read the slot early.
+int main(int argc, char** argv) {   // x.bin base.bin N C
+  using namespace cf;
+  auto x = slurp(argv[1]), b = slurp(argv[2]);
+  const int N = atoi(argv[3]), C = atoi(argv[4]);
+  const size_t E = (size_t)N * C, code_bytes = E / 8;
+  const __half* xh = reinterpret_cast<const __half*>(x.data());
+  const __half* bh = reinterpret_cast<const __half*>(b.data());
+  // the payload the sender will deliver (plain pipelined compress)
+  std::vector<unsigned char> pay(code_bytes + 2 * (size_t)N + 2 * (size_t)C);
+  const PipeGeom g1 = make_pipe_geom(C, 2, 0, false), g3 = make_pipe_geom(C, 1, C / 8, true);
+  auto args = [](const PipeGeom& g, int rpc) { PipeArgs a{}; a.TX = g.TX; a.TY = g.TY; a.R = g.R; a.stages = g.stages;
+    a.chunk_rows = g.chunk_rows; a.u_cap = g.u_cap; a.tile_bytes = g.tile_bytes; a.stage_bytes = g.stage_bytes;
+    a.rows_per_cta = rpc; a.early_load = 1; return a; };
+  int64_t rpc = (N + g1.R - 1) / g1.R * g1.R;
+  std::vector<__half> rowmean(N); std::vector<float> tokpart(1), colpart(C);
+  StatsParams sp{}; sp.x[0] = xh; sp.base[0] = bh; sp.packed[0] = pay.data(); sp.rowmean[0] = rowmean.data();
+  sp.tokpart[0] = tokpart.data(); sp.colpart[0] = colpart.data(); sp.N = N; sp.C = C; sp.rows_per_cta = (int)rpc;
+  const PipeArgs a1 = args(g1, (int)rpc);
+  emu_ncompute = g1.TX * g1.TY;
+  launch(1, 1, g1.TX * g1.TY + 32, 1, [&] { k_delta_stats_tma<MODE_BINARY, 1, 2, false>(sp, a1, FanOut{}); });
+  FinalizeParams fp{}; fp.rowmean[0] = rowmean.data(); fp.tokpart[0] = tokpart.data(); fp.colpart[0] = colpart.data();
+  fp.scale_u[0] = reinterpret_cast<__half*>(pay.data() + code_bytes);
+  fp.scale_v[0] = reinterpret_cast<__half*>(pay.data() + code_bytes + 2 * (size_t)N); fp.N = N; fp.C = C; fp.B = 1;
+  launch((C + 31) / 32, 1, 1024, 1, [&] { k_finalize_scales<MODE_BINARY, false>(fp, FanOut{}, 0); });
+  // receiver: slot full of garbage, flag behind the expected count
+  std::vector<unsigned char> slot_mem(pay.size() + 32, 0x5A);
+  unsigned char* slot = slot_mem.data() + ((16 - (reinterpret_cast<uintptr_t>(slot_mem.data()) & 15u)) & 15u);
+  uint32_t flag = 6, expected = 7, err = 0;
+  std::vector<__half> got(E), want(E);
+  ApplyParams ap{}; ap.N = N; ap.C = C; ap.K = 1; ap.packed[0] = slot;
+  ap.scale_u[0] = reinterpret_cast<const __half*>(slot + code_bytes);
+  ap.scale_v[0] = reinterpret_cast<const __half*>(slot + code_bytes + 2 * (size_t)N);
+  ap.base[0] = bh; ap.recon[0] = got.data(); ap.wait_flag[0] = &flag; ap.expected = &expected; ap.error = &err;
+  const PipeArgs a3 = args(g3, 0);
+  TileSched ts{}; ts.tiles_per_tensor = (N + g3.R - 1) / g3.R; ts.total_tiles = ts.tiles_per_tensor; ts.tiles_per_cta = ts.total_tiles;
+  std::thread sender([&] {
+    std::this_thread::sleep_for(std::chrono::milliseconds(150));
+    memcpy(slot, pay.data(), pay.size());
+    __sync_synchronize();
+    __atomic_store_n(&flag, 7u, __ATOMIC_SEQ_CST);
+  });
+  emu_ncompute = g3.TX * g3.TY;
+  launch(1, 1, g3.TX * g3.TY + 32, 1, [&] { k_apply_codes_tma<MODE_BINARY, 1, 2>(ap, a3, ts); });
+  sender.join();
+  ApplyParams rf = ap; rf.packed[0] = pay.data(); rf.scale_u[0] = fp.scale_u[0]; rf.scale_v[0] = fp.scale_v[0];
+  rf.recon[0] = want.data(); rf.expected = nullptr; rf.wait_flag[0] = nullptr;
+  launch(1, 1, g3.TX * g3.TY + 32, 1, [&] { k_apply_codes_tma<MODE_BINARY, 1, 2>(rf, a3, ts); });
+  if (err != 0 || memcmp(got.data(), want.data(), E * 2) != 0) { fprintf(stderr, "waited reconstruct differs (err=%u)\n", err); return 1; }
+  printf("WAIT_OK\n");
+  return 0;
+}
+'''
+
+
+def test_flag_waiting_reconstruct_does_not_read_the_slot_before_the_flag(emulator, tmp_path_factory):
+    """A late sender (payload written 150 ms after the receiver's kernel started, flag raised last): warp 0
+    polls, the row scales / column fragments / code tiles are only fetched behind the wait, the result equals
+    the plain reconstruct.  (Early base-tile prefetch before the wait is allowed: bases are local.)"""
+    _, d0 = emulator
+    src = (d0 / "emu.cpp").read_text()
+    src = src[:src.index("using namespace cf;\nstatic PipeArgs args_of")] + WAIT_RUNNER   # same prelude, other main
+    d = tmp_path_factory.mktemp("wait_emu")
+    exe = emu.build(d, src, name="wait")
+    g = torch.Generator().manual_seed(5)
+    n, c = 150, 256
+    x = torch.randn(n, c, generator=g).half()
+    base = (0.97 * x.float() + 0.2 * torch.randn(n, c, generator=g)).half()
+    (d / "x.bin").write_bytes(x.numpy().tobytes())
+    (d / "b.bin").write_bytes(base.numpy().tobytes())
+    r = subprocess.run([exe, str(d / "x.bin"), str(d / "b.bin"), str(n), str(c)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "WAIT_OK" in r.stdout, r.stdout + r.stderr[-2000:]
