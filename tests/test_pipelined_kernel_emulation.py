@@ -188,10 +188,12 @@ def test_pipelined_int2_kernel_source_matches_the_oracle(emulator, n, c, stats_c
 
 # edge shapes: fewer rows than one tile / one quad, a single row, the smallest C (8 column groups: 24 idle
 # lanes per warp), the widest single-group C, row counts one past a tile boundary, and C > 4096 (two column
-# groups per thread, one CTA per SM; 6144 leaves the second group partly idle)
+# groups per thread, one CTA per SM; 6144 leaves the second group partly idle); C = 3072 is the FLUX / CogVideoX
+# geometry itself (384 compute threads, 4-row tiles, 2 stages, 2 CTAs per SM)
 @pytest.mark.parametrize("mode", ["binary", "int2"])
 @pytest.mark.parametrize("n,c,stats_ctas,apply_ctas", [(3, 256, 1, 1), (1, 64, 1, 1), (129, 64, 2, 3), (5, 4096, 1, 2),
-                                                       (65, 128, 4, 4), (64, 256, 1, 1), (6, 6144, 1, 1)])
+                                                       (65, 128, 4, 4), (64, 256, 1, 1), (6, 6144, 1, 1),
+                                                       (37, 3072, 2, 3)])
 def test_pipelined_kernel_source_edge_shapes(emulator, mode, n, c, stats_ctas, apply_ctas):
     if (c // (8 if mode == "binary" else 4)) % 16:
         pytest.skip("the host dispatch (launch_apply) sends code rows that are not a multiple of 16 bytes to the "
