@@ -56,12 +56,29 @@ static int run_int8(const __half* x, int N, int C, int rows_per_cta) {
   return 0;
 }
 
-int main(int argc, char** argv) {  // <int4|int2mm|int8> x.bin N C rows_per_cta
+// the generic path (C % 8 != 0: the tall-skinny low-rank factors of LOW_RANK_Q, slowpath.py:69-70)
+static int run_int4_generic(const __half* x, int N, int C) {
+  using namespace cf;
+  std::vector<__half> scale(C), minv(C), recon((size_t)N * C), deq((size_t)N * C);
+  std::vector<uint8_t> packed((size_t)(N / 2) * C, 0xEE);
+  launch(C, 1, 256, 1, [&] { k_minmax_column_generic<MODE_INT4>(x, nullptr, N, C, scale.data(), minv.data()); });
+  launch(2, 1, 256, 1, [&] { k_int4_codec_generic<true>(x, nullptr, scale.data(), minv.data(), packed.data(), recon.data(), N, C); });
+  launch(3, 1, 256, 1, [&] { k_int4_codec_generic<false>(nullptr, nullptr, scale.data(), minv.data(), packed.data(), deq.data(), N, C); });
+  fwrite(packed.data(), 1, packed.size(), stdout);
+  fwrite(scale.data(), 2, C, stdout);
+  fwrite(minv.data(), 2, C, stdout);
+  fwrite(recon.data(), 2, recon.size(), stdout);
+  fwrite(deq.data(), 2, deq.size(), stdout);
+  return 0;
+}
+
+int main(int argc, char** argv) {  // <int4|int2mm|int8|int4g> x.bin N C rows_per_cta
   const std::string mode = argv[1];
   auto x = slurp(argv[2]);
   const int N = atoi(argv[3]), C = atoi(argv[4]), rpc = atoi(argv[5]);
   const __half* xh = reinterpret_cast<const __half*>(x.data());
   if (mode == "int8") return run_int8(xh, N, C, rpc);
+  if (mode == "int4g") return run_int4_generic(xh, N, C);
   return mode == "int4" ? run<cf::MODE_INT4>(xh, N, C, rpc) : run<cf::MODE_INT2MM>(xh, N, C, rpc);
 }
 '''
@@ -116,3 +133,18 @@ def test_int4_and_int2_minmax_kernel_source_match_the_reference_goldens(emulator
     assert np.array_equal(s8, bits16(h16(g[f"{name}/int8_scale"])).reshape(s8.shape))
     assert np.array_equal(zp8.view(np.int16), g[f"{name}/int8_zp"].reshape(zp8.shape))
     assert np.array_equal(deq8, bits16(h16(g[f"{name}/int8_deq"])).reshape(deq8.shape)) and np.array_equal(recon8, deq8)
+
+
+@pytest.mark.parametrize("n,c", [(64, 12), (130, 20), (96, 33)])
+def test_generic_int4_kernel_source_matches_the_oracle(emulator, n, c):
+    """C % 8 != 0 (LOW_RANK_Q quantises its (N, r) / (C, r) factors): the scalar kernels, bit-exact against the
+    oracle's quantize_int4 / dequantize_int4 restatement (itself pinned to the reference's goldens)."""
+    from oracle import codecs as oc
+    g = torch.Generator().manual_seed(n + c)
+    x = (torch.randn(n, c, generator=g) * torch.rand(1, c, generator=g) * 3).half()
+    packed, scale, mn, recon, deq = _run(emulator, "int4g", x, 1)
+    o_packed, o_scale, o_min = oc.int4_quantize(x)
+    assert np.array_equal(packed, o_packed), "codes differ"
+    assert np.array_equal(scale, bits16(o_scale).reshape(scale.shape)) and np.array_equal(mn, bits16(o_min).reshape(mn.shape))
+    want = bits16(oc.int4_dequantize(o_packed, o_scale, o_min))
+    assert np.array_equal(deq, want.reshape(deq.shape)) and np.array_equal(recon, deq)
