@@ -45,10 +45,14 @@ struct FanOut {
   uint32_t* done;                     // local: CTA ticket counter, reset by the last CTA
   unsigned long long u_off, v_off;    // byte offsets of U (N) and V (C) inside a payload
   int n_dst;
+  int publish_mode;                   // 0: every CTA adds 1 to every flag; 1: the last CTA stores the new count
 };
 
 __device__ __forceinline__ void red_add_relaxed_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // Tail of the kernel that completes a fused put.  Every CTA calls it after its last payload store: the
 // barrier orders the CTA's stores before thread 0's system-scope fence (cumulative), then thread 0 adds 1
@@ -66,11 +70,24 @@ __device__ __forceinline__ void fanout_publish_impl(const FanOut& f, unsigned to
     __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
-    for (int q = 0; q < f.n_dst; ++q) red_add_relaxed_sys_u32(f.flag[q], 1u);
-    const unsigned ticket = atomicAdd(f.done, 1u);
-    if (ticket == total_ctas - 1) {
-      *f.count += total_ctas;  // read by kernels launched after this one (stream order / PDL wait)
-      *f.done = 0u;
+    if (f.publish_mode == 0) {
+      for (int q = 0; q < f.n_dst; ++q) red_add_relaxed_sys_u32(f.flag[q], 1u);
+      const unsigned ticket = atomicAdd(f.done, 1u);
+      if (ticket == total_ctas - 1) {
+        *f.count += total_ctas;  // read by kernels launched after this one (stream order / PDL wait)
+        *f.done = 0u;
+      }
+    } else {
+      // CF_PUBLISH_MODE=1 (A/B): n_dst flag stores by ONE CTA instead of n_dst remote atomics by every CTA,
+      // at the price of a second fence on the critical path (the pattern of k_p2p_put).  Same count units.
+      const unsigned ticket = atomicAdd(f.done, 1u);
+      if (ticket == total_ctas - 1) {
+        __threadfence_system();
+        const uint32_t v = *f.count + total_ctas;
+        for (int q = 0; q < f.n_dst; ++q) st_relaxed_sys_u32(f.flag[q], v);
+        *f.count = v;
+        *f.done = 0u;
+      }
     }
   }
 }
@@ -994,6 +1011,7 @@ static int sign_compress_put(int passes, int batch, const void* const* x, const 
   sp.rows_per_cta = pl.rows_per_cta;
   fp.B = pl.B;
   f.n_dst = n_dst;
+  f.publish_mode = pipe_env_int("CF_PUBLISH_MODE", 0);
   f.u_off = static_cast<unsigned long long>(N) * (MODE == MODE_BINARY ? C / 8 : C / 4);
   f.v_off = f.u_off + static_cast<unsigned long long>(N) * 2;
   f.count = static_cast<uint32_t*>(local_count);

@@ -440,8 +440,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // are relaxed; the poll that observes the awaited count is repeated as an acquire load (LDG.STRONG.SYS +
 // L1 invalidate -- no MEMBAR.SYS, which costs microseconds when 296 CTAs issue it at once), which orders
 // the payload reads of the CTA (behind the __syncthreads that follows) after the origin's release.
+// A wait that times out also sets *failed (shared memory): the caller then leaves the affected bases untouched.
 template <typename P>
-__device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last, int lane) {
+__device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last, int lane, int* failed) {
   for (int t = t_first + lane; t <= t_last; t += 32) {
     const uint32_t* f = p.wait_flag[t];
     if (f == nullptr) continue;
@@ -451,6 +452,7 @@ __device__ __forceinline__ void wait_origins(const P& p, int t_first, int t_last
     while (static_cast<int32_t>(cur - want) < 0) {
       if (clock64() - t0 > 4000000000LL) {
         atomicExch(p.error, 1u);
+        *failed = 1;
         break;
       }
       __nanosleep(32);
@@ -479,6 +481,10 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
   const int T1 = min(ts.total_tiles, T0 + ts.tiles_per_cta);
   const uint32_t code_row = (MODE == MODE_BINARY) ? static_cast<uint32_t>(C) / 8u : static_cast<uint32_t>(C) / 4u;
   const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
+  // set by warp 0 if a wait for an origin's payload timed out: the CTA then streams its tiles without storing,
+  // so a stale / partial slot never reaches the error-feedback cache (the host sees *p.error)
+  int* wait_failed = reinterpret_cast<int*>(sm.wsum);
+  if (tid == 32) *wait_failed = 0;
   pipe_init(sm, a, ncompute);
   const uint64_t ld_pol = a.l2_hints ? make_policy_evict_first() : 0ull;  // last use of these lines
   // early fill: the base tiles of the first `stages` tiles do not depend on the previous kernel
@@ -498,9 +504,11 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
   }
   pdl_wait();
   pdl_launch_dependents();
+  bool skip_stores = false;
   if (p.expected != nullptr) {
-    if (tid < 32 && T0 < T1) wait_origins(p, T0 / ts.tiles_per_tensor, (T1 - 1) / ts.tiles_per_tensor, tid);
+    if (tid < 32 && T0 < T1) wait_origins(p, T0 / ts.tiles_per_tensor, (T1 - 1) / ts.tiles_per_tensor, tid, wait_failed);
     __syncthreads();
+    skip_stores = *wait_failed != 0;
     // the codes are fetched by the async proxy (TMA): order its reads behind the acquire above
     if (tid == ncompute) asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
           for (int j = 0; j < G; ++j) {
             const H8 out = (MODE == MODE_BINARY) ? binary_apply8(as_h8(bv[f][j]), cd[f][j], u2, vfrag[j])
                                                  : int2_apply8(as_h8(bv[f][j]), cd[f][j], u2, vfrag[j]);
-            stg_stream_pol(rp + static_cast<size_t>(rl + f * TY) * C + 8 * j * TX, as_u4(out), st_pol);
+            if (!skip_stores) stg_stream_pol(rp + static_cast<size_t>(rl + f * TY) * C + 8 * j * TX, as_u4(out), st_pol);
           }
         }
       }
@@ -591,7 +599,7 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
           const uint32_t ca = cs_a + r * code_row + static_cast<uint32_t>(j * TX) * kCodeGrp;
           const H8 out = (MODE == MODE_BINARY) ? binary_apply8(b, lds8a(ca), u2, vfrag[j])
                                                : int2_apply8(b, lds16a(ca), u2, vfrag[j]);
-          stg_stream_pol(rp + static_cast<size_t>(rl) * C + 8 * j * TX, as_u4(out), st_pol);
+          if (!skip_stores) stg_stream_pol(rp + static_cast<size_t>(rl) * C + 8 * j * TX, as_u4(out), st_pol);
         }
       }
     }

@@ -38,6 +38,78 @@ from .utils import COMPACT_COMPRESS_TYPE as T
 _CODEC = {T.BINARY: nv.CODEC_BINARY, T.INT2: nv.CODEC_INT2}
 
 
+class _DevicePtr:
+    """`nbytes` of device memory at a raw address (a CUDA IPC region is not a torch allocation), exposed
+    through __cuda_array_interface__ so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _device_bytes(ptr: int, nbytes: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DevicePtr(ptr, nbytes), device=device)
+
+
+class LocalWorld:
+    """W virtual ranks of ONE process on one GPU: W engines whose receive regions are plain local
+    allocations "mapped" into each other by address -- exactly what a peer mapping looks like to the
+    kernels (fan-out table, slot offsets, flag / count arithmetic, flag-waiting reconstruct).  A
+    decompress launch spins on flags, so the driver must enqueue every rank's put of a layer before any
+    rank's decompress of that layer (`exchange_all`, `ring_all`); real concurrency and NVLink are what
+    the multi-process runs add.  Used by the parity tests (a W = 4 / 8 exchange against the oracle on a
+    1-GPU box) and by `bench.py --virtual-ranks`."""
+
+    def __init__(self, world: int, layers: int, n_local: int, c: int, device=None, engine_cls=None, **kw):
+        self.world = world
+        self.engines = []
+        self._regions = {}
+        cls = engine_cls or PatchGatherEngine
+        for r in range(world):
+            self.engines.append(cls(layers, n_local, c, device=device, transport="p2p", local_world=self, rank=r, **kw))
+
+    def map_regions(self, ctype, total, flags_bytes, slot_bytes):
+        sts = self._regions.get(ctype)
+        if sts is None:
+            dev = self.engines[0].device
+            mem = [torch.zeros(total, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            ptrs = [m.data_ptr() for m in mem]
+            sts = []
+            for r, e in enumerate(self.engines):
+                st = {"base": ptrs[r], "peers": list(ptrs), "flags_bytes": flags_bytes, "slot_bytes": slot_bytes,
+                      "total_bytes": total, "ipc": False, "mem": mem,
+                      "count": torch.zeros(e.layers, dtype=torch.int32, device=dev),
+                      "ticket": torch.zeros(1, dtype=torch.int32, device=dev),
+                      "error": torch.zeros(1, dtype=torch.int32, device=dev)}
+                e._p2p[ctype] = st
+                sts.append(st)
+            self._regions[ctype] = sts
+        return sts
+
+    def exchange_all(self, layer: int, ks, vs, ctype):
+        """One layer of one step for all W virtual ranks (ks[r], vs[r]: rank r's shards); returns the engines'
+        (global_k, global_v) pairs."""
+        if ctype == T.WARMUP:
+            return [e.warmup(layer, ks[r], vs[r]) for r, e in enumerate(self.engines)]
+        for r, e in enumerate(self.engines):
+            e.send(layer, ks[r], vs[r], ctype)
+        for e in self.engines:
+            e.decompress(layer, ctype)
+        return [(e.global_k[layer], e.global_v[layer]) for e in self.engines]
+
+    def ring_all(self, layer: int, ks, vs, ctype):
+        """The ring engines' consumption order: own shard first (hop 0), then origin (rank - s) mod W per hop."""
+        if ctype == T.WARMUP:
+            return [e.warmup(layer, ks[r], vs[r]) for r, e in enumerate(self.engines)]
+        for r, e in enumerate(self.engines):
+            e.send(layer, ks[r], vs[r], ctype)
+        for e in self.engines:
+            e.decompress(layer, ctype, origins=(e.rank,))
+        for s in range(1, self.world):
+            for e in self.engines:
+                e.hop(layer, s, ctype)
+        return [(e.global_k[layer], e.global_v[layer]) for e in self.engines]
+
+
 class PatchGatherEngine:
     """Compressed patch-parallel K/V all-gather for `layers` attention layers (bs = 1).
 
@@ -46,11 +118,16 @@ class PatchGatherEngine:
     attention (identical on all ranks) and are the bases of the next step.
     """
 
-    def __init__(self, layers: int, n_local: int, c: int, group=None, device=None, transport: str = "nccl"):
+    def __init__(self, layers: int, n_local: int, c: int, group=None, device=None, transport: str = "nccl",
+                 inputs_stable: bool = False, local_world: "LocalWorld | None" = None, rank: int | None = None):
         self.layers, self.n, self.c = layers, n_local, c
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local = local_world
+        if local_world is not None:  # virtual ranks of one process (LocalWorld): no process group
+            self.world, self.rank = local_world.world, int(rank)
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         W, n = self.world, n_local
         self.global_k = [torch.zeros((W * n, c), dtype=torch.half, device=self.device) for _ in range(layers)]
@@ -69,10 +146,12 @@ class PatchGatherEngine:
         #  per-layer slots are only hazard-free when another layer's exchange separates two uses)
         if transport in ("p2p", "auto") and self.world > 1 and layers >= 2:
             self.transport = "p2p"  # regions are mapped lazily per codec (payload size differs)
-        # CF_FLAG_INPUTS_STABLE: with >= 2 layers the kernel launched right before a compress / decompress
-        # belongs to another layer (or only writes codes / scales), so it never writes the K/V inputs or the
-        # cached bases this call reads -- their first tiles may be fetched while that kernel drains
-        self._flags = nv.FLAG_INPUTS_STABLE if layers >= 2 else 0
+        # CF_FLAG_INPUTS_STABLE (include/compactb200.h) is a CALLER promise: the kernel launched right before a
+        # compress / decompress on this stream did not write the K/V inputs or the cached bases that call reads,
+        # so their first tiles may be fetched while that kernel drains.  True for a runtime that walks distinct
+        # per-layer buffers with static inputs (bench.py passes inputs_stable=True); NOT true in a model, where
+        # the projection / RoPE kernel that produces K and V is launched right before -- hence off by default.
+        self._flags = nv.FLAG_INPUTS_STABLE if (inputs_stable and layers >= 2) else 0
         # fused compress + put (cf_sign_compress_put): the codec kernels store the payload straight into every
         # rank's receive slot; CF_FUSED_PUT=0 keeps the separate put kernel (A/B)
         self.fused_put = os.environ.get("CF_FUSED_PUT", "1") != "0"
@@ -97,6 +176,9 @@ class PatchGatherEngine:
         ok = slot_bytes % 16 == 0 and (self._numel(ctype) * 2) % 16 == 0
         flags_bytes = (L * W * 4 + 255) // 256 * 256
         total = flags_bytes + L * W * slot_bytes
+        if self._local is not None:
+            assert ok, "payload sizes must be multiples of 16 bytes for the one-sided transport"
+            return self._local.map_regions(ctype, total, flags_bytes, slot_bytes)[self.rank]
         lib = nv.lib()
         base_ptr, handle, err = ctypes.c_void_p(), ctypes.create_string_buffer(64), None
         if ok:
@@ -122,6 +204,12 @@ class PatchGatherEngine:
         flag = torch.tensor([1 if all_ok else 0], device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
+            # nothing of a half-built transport may stay mapped / allocated
+            for r, pp in enumerate(peers):
+                if pp is not None and r != self.rank:
+                    lib.cf_ipc_close(pp)
+            if base_ptr.value:
+                lib.cf_ipc_free(base_ptr)
             if self._p2p_requested == "p2p":
                 raise nv.NativeError(f"p2p transport unavailable on rank {self.rank}: {err or 'a peer failed'}")
             self.transport = "nccl"
@@ -129,6 +217,7 @@ class PatchGatherEngine:
             return False
         st = {
             "base": base_ptr.value, "peers": peers, "flags_bytes": flags_bytes, "slot_bytes": slot_bytes,
+            "total_bytes": total, "ipc": True,
             "count": torch.zeros(L, dtype=torch.int32, device=self.device),     # puts issued per layer slot
             "ticket": torch.zeros(1, dtype=torch.int32, device=self.device),
             "error": torch.zeros(1, dtype=torch.int32, device=self.device),
@@ -136,6 +225,33 @@ class PatchGatherEngine:
         self._p2p[ctype] = st
         dist.barrier(group=self.group)
         return st
+
+    def close(self):
+        """Release the one-sided transport: unmap every peer region (cf_ipc_close) and free the own one
+        (cf_ipc_free).  Collective in spirit -- call it on all ranks once no rank touches the slots any more
+        (after a barrier).  Idempotent; the engine falls back to lazily re-creating regions if used again."""
+        torch.cuda.synchronize(self.device)
+        lib = nv.lib()
+        for st in self._p2p.values():
+            if not st or not st.get("ipc"):
+                continue
+            for r, pp in enumerate(st["peers"]):
+                if pp is not None and r != self.rank:
+                    lib.cf_ipc_close(pp)
+            lib.cf_ipc_free(st["base"])
+        self._p2p.clear()
+        self._ptr_cache.clear()
+
+    def slot_bytes(self, layer: int, origin: int, ctype, kv: int = 0) -> torch.Tensor:
+        """The wire payload [codes | U | V] of tensor `kv` (0: K, 1: V) that `origin` delivered for `layer`, as it
+        sits in THIS rank's receive memory (one-sided transport: the slot peers write over NVLink; otherwise
+        the gather / send buffer), as a uint8 tensor view -- what parity checks decode with the oracle."""
+        pn_bytes = self._numel(ctype) * 2
+        st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
+        if st:
+            return _device_bytes(self._slot(st, st["base"], layer, origin) + kv * pn_bytes, pn_bytes, self.device)
+        _, recv = self._buffers(ctype, layer)
+        return recv[origin, kv].view(torch.uint8)
 
     def _slot(self, st, region_base, layer, origin):
         return region_base + st["flags_bytes"] + (layer * self.world + origin) * st["slot_bytes"]
@@ -181,6 +297,10 @@ class PatchGatherEngine:
         if self.world == 1:
             self.global_k[layer].copy_(k2)
             self.global_v[layer].copy_(v2)
+        elif self._local is not None:  # virtual ranks: the "all-gather" is W local copies
+            for e in self._local.engines:
+                e._shard(e.global_k[layer], self.rank).copy_(k2)
+                e._shard(e.global_v[layer], self.rank).copy_(v2)
         else:
             dist.all_gather_into_tensor(self.global_k[layer], k2, group=self.group)
             dist.all_gather_into_tensor(self.global_v[layer], v2, group=self.group)
@@ -338,18 +458,29 @@ class PatchGatherEngine:
             nv.check(rc, "cf_sign_decompress_batched_wait")
             self.kernel_launches += 1
 
-    def exchange(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
-        """One layer of one step; returns (global_k, global_v) ready for attention."""
-        if ctype == T.WARMUP:
-            return self.warmup(layer, k, v)
+    def send(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
+        """Sender side of one layer: compress this rank's K and V and deliver the payloads to every rank."""
         assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
         if self.fused(ctype):
             self.compress_put(layer, k, v, ctype)
         else:
             self.compress(layer, k, v, ctype)
             self.gather(ctype, layer)
+
+    def exchange(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
+        """One layer of one step; returns (global_k, global_v) ready for attention."""
+        if ctype == T.WARMUP:
+            return self.warmup(layer, k, v)
+        self.send(layer, k, v, ctype)
         self.decompress(layer, ctype)
         return self.global_k[layer], self.global_v[layer]
+
+    def check_errors(self):
+        """Raise if a device-side flag wait timed out (a peer never delivered; the affected reconstructions were
+        skipped, so that origin's cache is one step stale on this rank).  Synchronises: call it at step end."""
+        if self.p2p_error():
+            raise nv.NativeError(f"rank {self.rank}: a device-side wait for a peer's payload timed out (~2 s); "
+                                 "the caches of the ranks have diverged -- reset the plugin state")
 
     # -- whole step ------------------------------------------------------------------------
     OVERLAP_LAG = 2  # layers the compress chain may run ahead of the reconstruct chain
@@ -393,11 +524,7 @@ class PatchGatherEngine:
         for layer in range(self.layers):
             if layer >= lag:
                 main.wait_event(done[layer - lag])
-            if self.fused(ctype):
-                self.compress_put(layer, ks[layer], vs[layer], ctype)
-            else:
-                self.compress(layer, ks[layer], vs[layer], ctype)
-                self.gather(ctype, layer)
+            self.send(layer, ks[layer], vs[layer], ctype)
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(side):
@@ -454,12 +581,7 @@ class RingExchangeEngine(PatchGatherEngine):
         if ctype == T.WARMUP:
             self.warmup(layer, k, v)
             return
-        assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
-        if self.fused(ctype):
-            self.compress_put(layer, k, v, ctype)
-        else:
-            self.compress(layer, k, v, ctype)
-            self.gather(ctype, layer)
+        self.send(layer, k, v, ctype)
         self.decompress(layer, ctype, origins=(self.rank,))
 
     def hop(self, layer: int, hop: int, ctype):

@@ -81,6 +81,10 @@ class FakeDist:
         for i in range(len(out)):
             out[i] = obj
 
+    def all_gather(self, outs, inp, group=None):
+        for o in outs:
+            o.copy_(inp)
+
     def all_gather_into_tensor(self, out, inp, group=None):
         out.view(self.world, -1).copy_(inp.reshape(1, -1).expand(self.world, -1))
 
@@ -98,6 +102,9 @@ def _run_bench(monkeypatch, capsys, argv, world=1):
     monkeypatch.setattr(nv, "stream_ptr", lambda: FakeCuda.current().cuda_stream)
     monkeypatch.setattr(nv, "workspace", lambda nbytes, device: torch.empty(max(int(nbytes), 16), dtype=torch.uint8))
     monkeypatch.setattr(nv, "workspace_bytes", lambda *a, **k: 4096)
+    monkeypatch.setattr(nv, "require_cuda_half", lambda t, name: None)
+    # a made-up IPC pointer cannot be wrapped: the parity leg reads zeros instead of a receive slot
+    monkeypatch.setattr(eng_mod, "_device_bytes", lambda ptr, nbytes, device: torch.zeros(nbytes, dtype=torch.uint8))
     for name, val in dict(current_stream=lambda *a, **k: FakeCuda.current(), Stream=FakeStream, Event=TimedEvent,
                           stream=FakeCuda.stream_ctx, is_available=lambda: True, set_device=lambda d: None,
                           synchronize=lambda *a, **k: None, CUDAGraph=FakeGraph, graph=fake_graph_ctx,
@@ -137,9 +144,9 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 @pytest.mark.parametrize("argv", [
-    ["--layers", "2", "--steps", "4", "--no-cpu-baseline"],
-    ["--layers", "6", "--steps", "3", "--no-cpu-baseline", "--overlap", "--codec", "int2"],
-    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-graph", "--no-e2e"],
+    ["--layers", "2", "--steps", "4", "--no-cpu-baseline", "--no-parity"],
+    ["--layers", "6", "--steps", "3", "--no-cpu-baseline", "--overlap", "--codec", "int2", "--no-parity"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-graph", "--no-e2e", "--no-parity"],
     ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--codec", "raw"],
     ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--workload", "pixart_patch_parallel"],
 ])
@@ -164,16 +171,20 @@ def test_bench_gpu_arm_single_gpu_dry_run(monkeypatch, capsys, argv):
     assert (line["e2e"] is None) == ("--no-e2e" in argv)
     if line["e2e"]:
         assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
-    assert "rel_l2" in line["fidelity"] or "error" in line["fidelity"]
-    assert "error" not in line["fidelity"], line["fidelity"]
+    assert {"rel_l2", "max_abs", "psnr_db", "finite"} <= set(line["fidelity"]) and line["fidelity"]["finite"] is True
+    assert line["ranks_identical"]["ok"] is True and isinstance(line["parity_ok"], bool)
+    if "--no-parity" in argv or raw:
+        assert line["oracle_parity"] is None
+    else:  # the stand-in library computes nothing: the oracle must notice (and the line must survive it)
+        assert line["oracle_parity"]["ok"] is False and line["parity_ok"] is False
 
 
 @pytest.mark.parametrize("argv", [
     ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline"],
-    ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--overlap"],
-    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--transport", "nccl"],
+    ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--overlap", "--no-parity"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--transport", "nccl", "--no-parity"],
     ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--workload", "cogvideox5b_ring",
-     "--codec", "int2"],
+     "--codec", "int2", "--no-parity"],
 ])
 def test_bench_gpu_arm_two_rank_dry_run(monkeypatch, capsys, argv):
     """Rank 0 of a pretended 2-rank job: the transport probe, CUDA-IPC region setup, fused put, flag-waiting

@@ -326,6 +326,7 @@ print("WORKER_OK", rank)
 '''
 
 
+@pytest.mark.multigpu(2)
 def test_two_gpu_all_gather_and_ring(tmp_path):
     """NCCL path on 2 GPUs (skipped on a 1-GPU box): drop-in all-gather, engine, compressed ring."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
@@ -341,3 +342,122 @@ def test_two_gpu_all_gather_and_ring(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"WORKER_OK {r}" in o, o[-4000:]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# W virtual ranks on ONE GPU (engine.LocalWorld) against the oracle: the multi-rank exchange -- fan-out table,
+# per-(layer, origin) slots, flag / count arithmetic, flag-waiting batched reconstruct -- checked on a 1-GPU box
+# ---------------------------------------------------------------------------------------------------------
+def _world_data(world, n, c, steps, layers, seed):
+    g = torch.Generator().manual_seed(seed)
+    x0 = [[[torch.randn(n, c, generator=g) for _ in range(world)] for _ in range(2)] for _ in range(layers)]
+    return [[[[(0.97 ** t * x0[l][j][r] + 0.2 * torch.randn(n, c, generator=g)).half() for r in range(world)]
+              for j in range(2)] for l in range(layers)] for t in range(steps)]  # [t][layer][kv][rank]
+
+
+@pytest.mark.parametrize("mode", ["patch", "ring"])
+@pytest.mark.parametrize("codec", ["binary", "int2"])
+@pytest.mark.parametrize("world,n,c", [(4, 144, 3072), (8, 72, 1152), (2, 288, 1536)])
+def test_virtual_ranks_exchange_vs_oracle(world, n, c, codec, mode):
+    """4 steps x 2 layers of the W-rank exchange through cf_sign_compress_put into every (virtual) rank's
+    receive region.  Per step, on EVERY receiver: the payload that arrived from every origin carries the
+    oracle's codes (bit-exact) and scales (<= 1 ulp), and the receiver's reconstruction is bit-identical to the
+    oracle's dequant of that payload against the cached base (oracle/check.py; main.py:398-419,
+    ring.py:184-200).  All receivers end bit-identical; an independent oracle run of `all_gather_step` /
+    `ring_step` over the same 4 steps stays within the 1-ulp-scale drift."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200.engine import LocalWorld, PatchGatherEngine, RingExchangeEngine
+    from oracle import check as ocheck
+    from oracle.state import OracleCompact, all_gather_step, ring_step
+    T = cf.COMPACT_COMPRESS_TYPE
+    ctype, layers, steps = T(codec), 2, 4
+    data = _world_data(world, n, c, steps, layers, seed=world * 1000 + n)
+    lw = LocalWorld(world, layers, n, c, device=dev, engine_cls=RingExchangeEngine if mode == "ring" else PatchGatherEngine)
+    run = lw.ring_all if mode == "ring" else lw.exchange_all
+    oracle = [OracleCompact(residual=1, ef=True, fastpath=True) for _ in range(world)]
+    for t in range(steps):
+        ct = ctype if t >= 1 else T.WARMUP
+        for l in range(layers):
+            ks = [data[t][l][0][r].to(dev) for r in range(world)]
+            vs = [data[t][l][1][r].to(dev) for r in range(world)]
+            before = [(e.global_k[l].cpu(), e.global_v[l].cpu()) for e in lw.engines]
+            run(l, ks, vs, ct)
+            torch.cuda.synchronize()
+            after = [(e.global_k[l].cpu(), e.global_v[l].cpu()) for e in lw.engines]
+            for q in range(1, world):  # the error-feedback invariant: every rank holds the same caches
+                assert torch.equal(after[q][0], after[0][0]) and torch.equal(after[q][1], after[0][1]), (t, l, q)
+            # the independent oracle run (its own scales, its own drift)
+            for j, sfx in enumerate("kv"):
+                xs = [data[t][l][j][r] for r in range(world)]
+                if mode == "ring":
+                    ring_step(oracle, l, xs, ct.value, suffix=sfx)
+                else:
+                    all_gather_step(oracle, f"{l}-{sfx}", xs, ct.value)
+            if t == 0:
+                for r in range(world):
+                    assert torch.equal(after[0][0][r * n:(r + 1) * n], data[0][l][0][r])
+                continue
+            for q, e in enumerate(lw.engines):  # every receiver against the oracle
+                for j in range(2):
+                    sh = lambda g, r: g[r * n:(r + 1) * n]  # noqa: E731
+                    verdict = ocheck.check_exchange(
+                        codec, [data[t][l][j][r] for r in range(world)], [sh(before[q][j], r) for r in range(world)],
+                        [e.slot_bytes(l, r, ctype, j).cpu().numpy() for r in range(world)],
+                        [sh(after[q][j], r) for r in range(world)])
+                    assert verdict["ok"], (t, l, q, j, verdict)
+        assert not any(e.p2p_error() for e in lw.engines)
+    # after 4 steps the independent oracle caches and the GPU caches agree up to the scale-ulp drift
+    for l in range(layers):
+        for j, sfx in enumerate("kv"):
+            for r in range(world):
+                key = f"{l}-{r}-{sfx}" if mode == "ring" else f"{l}-{sfx}-{r}"
+                got = (lw.engines[0].global_k[l] if j == 0 else lw.engines[0].global_v[l])[r * n:(r + 1) * n]
+                assert rel_l2(got, oracle[0].base[key]) < 2e-3, (l, sfx, r)
+
+
+def test_virtual_ranks_graph_and_publish_modes(monkeypatch):
+    """The W = 4 virtual-rank step as ONE replayed CUDA graph, and with the alternative flag publication
+    (CF_PUBLISH_MODE=1: one CTA stores the new count instead of every CTA adding 1): bit-identical caches."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200.engine import LocalWorld
+    T = cf.COMPACT_COMPRESS_TYPE
+    world, n, c, layers, steps = 4, 144, 3072, 3, 3
+    data = _world_data(world, n, c, steps, layers, seed=77)
+
+    def run(publish_mode, graph):
+        monkeypatch.setenv("CF_PUBLISH_MODE", str(publish_mode))
+        lw = LocalWorld(world, layers, n, c, device=dev)
+        ks = [[data[0][l][0][r].to(dev) for r in range(world)] for l in range(layers)]
+        vs = [[data[0][l][1][r].to(dev) for r in range(world)] for l in range(layers)]
+        for l in range(layers):
+            lw.exchange_all(l, ks[l], vs[l], T.WARMUP)
+        g = None
+        for t in range(1, steps):
+            for l in range(layers):
+                for r in range(world):
+                    ks[l][r].copy_(data[t][l][0][r])
+                    vs[l][r].copy_(data[t][l][1][r])
+            if graph and t == 2:
+                if g is None:
+                    s = torch.cuda.Stream()
+                    s.wait_stream(torch.cuda.current_stream())
+                    g = torch.cuda.CUDAGraph()
+                    for e in lw.engines:
+                        e._ptr_cache.clear()
+                    with torch.cuda.graph(g):
+                        for l in range(layers):
+                            lw.exchange_all(l, ks[l], vs[l], T.BINARY)
+                g.replay()
+            else:
+                for l in range(layers):
+                    lw.exchange_all(l, ks[l], vs[l], T.BINARY)
+        torch.cuda.synchronize()
+        assert not any(e.p2p_error() for e in lw.engines)
+        return [x.clone() for x in lw.engines[world - 1].global_k + lw.engines[0].global_v]
+
+    ref = run(0, False)
+    for mode, graph in ((1, False), (0, True)):
+        for a, b in zip(run(mode, graph), ref):
+            assert torch.equal(a, b), (mode, graph)
