@@ -93,7 +93,9 @@ def parse():
     p.add_argument("--no-parity", action="store_true", help="skip the oracle parity leg (one extra step of layer 0 "
                    "checked by the CPU oracle on rank 0, outside the timed region)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-sample-layers", type=int, default=2)
+    p.add_argument("--no-gpu-reference", action="store_true",
+                   help="skip timing the unmodified reference's GPU kernels (baseline/_ref) in the same run (N = 1)")
+    p.add_argument("--cpu-sample-layers", type=int, default=1)
     p.add_argument("--hang-dump", type=float, default=0.0,
                    help="debug: dump all Python stacks and exit if the run takes longer than this many seconds")
     return p.parse_args()
@@ -196,79 +198,143 @@ def ncu_traffic(kernel, codec, n_local, world):
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: oracle port of the reference's eager torch path
+# CPU arm: the reference's own eager-torch path (baseline/_ref), else the oracle port
 # --------------------------------------------------------------------------------------------
-class CpuRankSample:
-    """One rank's share of `sample_layers` layers on the host (oracle port of the reference's eager
-    torch path): compress own K and V shard (no cache update) + decompress all `world` origins (cache
-    update), main.py:390-420.  Inputs and the warm-up step are prepared once; `step()` is the timed unit."""
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _load_reference_main():
+    """The UNMODIFIED reference's `xfuser.compact.main` from baseline/_ref (staged by tools/stage_reference.sh in
+    the build container, git-ignored, travels with gpurun), imported through oracle/ref_loader.py's namespace
+    stub; None if it is not staged.  Eager (TORCHDYNAMO_DISABLE=1): the semantics its own tests pin."""
+    if not os.path.isdir(os.path.join(REF_ROOT, "xfuser", "compact")):
+        return None
+    os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+    os.environ["CF_REFERENCE_ROOT"] = REF_ROOT
+    try:
+        from oracle import ref_loader
+        ref_loader.REFERENCE_ROOT = REF_ROOT
+        ref_loader.load_reference()
+        import xfuser.compact.main as cm
+        from xfuser.compact.utils import COMPACT_COMPRESS_TYPE as RT
+        from xfuser.compact.utils import CompactConfig as RCfg
+        return cm, RT, RCfg
+    except Exception as e:  # noqa: BLE001 -- an unusable staging falls back to the port, and says so
+        print(f"[bench] baseline/_ref present but not importable ({type(e).__name__}: {e}); using the oracle port",
+              file=sys.stderr)
+        return None
+
+
+class CpuSample:
+    """The whole job's work for `sample_layers` layers on the host: for EVERY rank q of `world`, compress q's own
+    K and V shard (no cache update) and decompress all `world` origins (cache update) -- compact_all_gather
+    without the collective (main.py:390-420).  kind "reference": the reference's own compact_compress /
+    compact_decompress with simulate=True (BINARY / INT2 fastpath kernels are Triton-only; simulate routes to
+    its eager `sim_binary` / `sim_int2`, main.py:116-127), imported from baseline/_ref.  kind "port": the oracle.
+    Inputs and the warm-up step are prepared once; `step()` is the timed unit."""
 
     def __init__(self, codec, world, sample_layers):
-        from oracle.state import OracleCompact
-        self.codec, self.world = codec, world
-        n_local = SEQ // world
+        self.codec, self.world, self.layers = codec, world, sample_layers
+        self.n = SEQ // world
         torch.set_num_threads(os.cpu_count() or 1)
         g = torch.Generator().manual_seed(0)
-        self.ranks = OracleCompact(residual=1, ef=True, fastpath=True)
-        self.cur, self.nxt = [], []
-        for _ in range(sample_layers * 2):
-            x0 = torch.randn(n_local, CH, generator=g)
-            self.cur.append(x0.half())
-            self.nxt.append((0.97 * x0 + 0.243 * torch.randn(n_local, CH, generator=g)).half())
-        # warm-up step: bases for every origin (all origins carry the same synthetic shard)
-        for i, x in enumerate(self.cur):
-            for r in range(world):
-                self.ranks.decompress(f"{i}-{r}", x, "warmup", x.shape, update_cache=True)
+        ref = _load_reference_main()
+        self.kind = "reference" if ref else "port"
+        self.xs = []  # [version][tensor][rank]
+        x0 = [[torch.randn(self.n, CH, generator=g) for _ in range(world)] for _ in range(sample_layers * 2)]
+        for ver in range(2):
+            self.xs.append([[(x if ver == 0 else 0.97 * x + 0.243 * torch.randn(self.n, CH, generator=g)).half()
+                             for x in per] for per in x0])
+        if ref:
+            cm, RT, RCfg = ref
+            self.cm, self.ct, self.warm = cm, RT(codec), RT.WARMUP
+            cm.compact_init(RCfg(enabled=True, residual=1, ef=True, simulate=True, comp_rank=-1,
+                                 compress_func=lambda l, s: RT(codec)))
+            self._compress = lambda key, x: cm.compact_compress(key, x, self.ct, update_cache=False)
+            self._decompress = lambda key, p, shape: cm.compact_decompress(key, p, self.ct, shape, update_cache=True)
+            warm = lambda key, x: cm.compact_decompress(key, x, self.warm, x.shape, update_cache=True)  # noqa: E731
+        else:
+            from oracle.state import OracleCompact
+            oc = OracleCompact(residual=1, ef=True, fastpath=True)
+            self._compress = lambda key, x: oc.compress(key, x, codec, update_cache=False)
+            self._decompress = lambda key, p, shape: oc.decompress(key, p, codec, shape, update_cache=True)
+            warm = lambda key, x: oc.decompress(key, x, "warmup", x.shape, update_cache=True)  # noqa: E731
+        # warm-up step: receiver q's base for every origin r
+        for i, per in enumerate(self.xs[0]):
+            for q in range(world):
+                for r in range(world):
+                    warm(self._key(i, q, r), per[r].clone())
+        self.ver = 1
+
+    def _key(self, tensor, receiver, origin):
+        # the reference's key format "{layer}-k-{origin}" (main.py:399,412; utils.py parses int(key.split('-')[0])):
+        # the receiving rank is folded into the layer index, since one process holds every rank's cache here
+        return f"{tensor * self.world + receiver}-k-{origin}"
+
+    def sample_bytes(self):
+        """Raw fp16 K/V bytes reconstructed by one sample step, all ranks (the metric's numerator)."""
+        return self.world * self.layers * 2 * SEQ * CH * 2
 
     def step(self):
-        """Seconds for one compressed step of the sampled layers (inputs alternate between two versions)."""
+        """Seconds for one compressed step of the sampled layers, all `world` ranks' shares, back to back."""
+        xs = self.xs[self.ver]
         t0 = time.perf_counter()
-        for i, x in enumerate(self.nxt):
-            payload = self.ranks.compress(f"{i}-0", x, self.codec, update_cache=False)
-            for r in range(self.world):
-                self.ranks.decompress(f"{i}-{r}", payload, self.codec, x.shape, update_cache=True)
+        for i, per in enumerate(xs):
+            payloads = [self._compress(self._key(i, q, q), per[q]) for q in range(self.world)]
+            for q in range(self.world):
+                for r in range(self.world):
+                    self._decompress(self._key(i, q, r), payloads[r], per[r].shape)
         dt = time.perf_counter() - t0
-        self.cur, self.nxt = self.nxt, self.cur
+        self.ver ^= 1
         return dt
+
+    def describe(self, n_steps, total_s):
+        src = ("the reference's own compact_compress / compact_decompress (simulate=True, eager torch, unmodified, "
+               "baseline/_ref)") if self.kind == "reference" else "oracle port of the reference's eager torch path"
+        return (f"{src} on {torch.get_num_threads()} host threads: each step = {self.layers} of {LAYERS} layers "
+                f"(K and V) of the {WORKLOAD} step, the shares of all {self.world} rank(s) run back to back "
+                f"(per rank: compress own {self.n}x{CH} shard + decompress {self.world} origins); "
+                f"{n_steps} steps, {total_s:.1f} s of CPU work; the rate is per byte, not extrapolated")
 
 
 def cpu_baseline(codec, world, layers, sample_layers, budget_s=12.0):
-    """Bounded sample: repeat the sampled layers for ~budget_s of CPU work, keep the mean."""
-    sample = CpuRankSample(codec, world, sample_layers)
+    """Bounded sample: repeat the sampled layers for ~budget_s of CPU work, keep the mean rate."""
+    sample = CpuSample(codec, world, sample_layers)
     sample.step()  # page-in / thread-pool warm-up
     times = []
     while sum(times) < budget_s and len(times) < 500:
         times.append(sample.step())
     dt = sum(times) / len(times)
-    step_s = dt * layers / sample_layers * world  # all `world` ranks' work on this host's cores
-    return {"value": job_bytes(layers, world) / step_s / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"oracle port (eager torch CPU, {torch.get_num_threads()} threads) of one rank's work for "
-                      f"{sample_layers} of {layers} layers (K and V: compress own {SEQ // world}x{CH} shard + decompress "
-                      f"{world} origins), mean of {len(times)} repeats ({sum(times):.1f} s of CPU work), extrapolated "
-                      f"to all layers and all {world} ranks on this host"}
+    return {"value": sample.sample_bytes() / dt / 1e9, "unit": UNIT, "cores": os.cpu_count(), "kind": sample.kind,
+            "threads": torch.get_num_threads(), "sample_ms_per_step": dt * 1e3,
+            "sample": sample.describe(len(times), sum(times))}
 
 
 def run_reference(args, world, rank):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores (rank 0 only).
+    `ms_per_step` is the measured time of one SAMPLE step (so steps x ms_per_step is this run's real duration);
+    `value` is the sample's bytes over that time -- a rate, comparable with the GPU arm's."""
     if rank != 0:
         return
     assert args.codec != "raw", "--codec raw is a GPU comparison line; the CPU arm runs the compressed path"
-    cpu = CpuRankSample(args.codec, world, args.cpu_sample_layers)
+    cpu = CpuSample(args.codec, world, args.cpu_sample_layers)
     for _ in range(args.warmup):
         cpu.step()
     per = [cpu.step() for _ in range(args.steps)]
     dt = sum(per) / len(per)
-    step_s = dt * args.layers / args.cpu_sample_layers * world
-    val = job_bytes(args.layers, world) / step_s / 1e9
-    sample = (f"each step = one rank's work for {args.cpu_sample_layers} of {args.layers} layers on the host "
-              f"({torch.get_num_threads()} threads), extrapolated to all layers and all {world} ranks")
+    val = cpu.sample_bytes() / dt / 1e9
+    sample = cpu.describe(args.steps, sum(per))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "codec": args.codec, "layers": args.layers, "seq": SEQ,
+        "config": {"workload": WORKLOAD, "exchange": MODE, "codec": args.codec, "layers": args.layers, "seq": SEQ,
                    "channels": CH, "world": world, "shard_rows": SEQ // world, "launch_mode": "cpu (no GPU work)",
-                   "transport": "in-process (all ranks' work on this host)", "l2": "n/a"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                   "schedule": "serial", "transport": "in-process (all ranks' shares on this host)", "l2": "n/a",
+                   "sampled_layers": args.cpu_sample_layers,
+                   "ms_per_full_step_extrapolated": dt * 1e3 * args.layers / args.cpu_sample_layers},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": cpu.kind,
+                         "threads": torch.get_num_threads(), "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -565,6 +631,45 @@ def measure_e2e(args, eng, sample, ctype, world, n_local, layers, device, transp
     return e2e
 
 
+def gpu_reference(args, ks, vs, pattern, layers, n_local, device, steps=3):
+    """The kernel-to-beat, in the same run on the same GPU: the UNMODIFIED reference (baseline/_ref: Triton fastpath
+    kernels + eager torch scale passes, its own compact_compress / compact_decompress, per-call allocation and
+    Python dispatch as shipped) doing this workload's single-GPU step -- per layer, K and V: compress without cache
+    update, decompress with cache update (compact_all_gather at world size 1, main.py:390-420).  CUDA events around
+    `steps` full steps after one untimed step (Triton JIT + warm-up).  None if baseline/_ref is not staged."""
+    ref = _load_reference_main()
+    if ref is None:
+        return None
+    cm, RT, RCfg = ref
+    ct = RT(args.codec)
+    cm.compact_init(RCfg(enabled=True, residual=1, ef=True, simulate=False, fastpath=True, comp_rank=-1,
+                         compress_func=lambda l, s: ct))
+    shape = (1, n_local, 1, CH)
+
+    def step(v):
+        for l in range(layers):
+            for tag, x in ((f"{l}-k", ks[v][l]), (f"{l}-v", vs[v][l])):
+                p = cm.compact_compress(f"{tag}-0", x.view(shape), ct, update_cache=False)
+                cm.compact_decompress(f"{tag}-0", p, ct, shape, update_cache=True)
+
+    for l in range(layers):  # the reference's WARMUP step: cache the raw tensors
+        cm.compact_decompress(f"{l}-k-0", ks[0][l].view(shape), RT.WARMUP, shape, update_cache=True)
+        cm.compact_decompress(f"{l}-v-0", vs[0][l].view(shape), RT.WARMUP, shape, update_cache=True)
+    step(1)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(pattern[(i + 2) % len(pattern)])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    cm.compact_reset()
+    return {"ms_per_step": ms, "value": job_bytes(layers, 1) / (ms * 1e-3) / 1e9, "unit": UNIT, "steps": steps,
+            "what": "unmodified reference (baseline/_ref: Triton fastpath + eager torch, compact_compress / "
+                    "compact_decompress as shipped) on the same GPU, same inputs, world size 1"}
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -704,6 +809,13 @@ def main():
     e2e = None if args.no_e2e else measure_e2e(args, eng, acts[0][0][0], ctype, world, n_local, layers, device,
                                                transport, barrier)
     note(rank, "e2e done")
+    gpu_ref = None
+    if world == 1 and not raw and not args.no_gpu_reference:
+        try:
+            gpu_ref = gpu_reference(args, ks, vs, pattern, layers, n_local, device)
+        except Exception as e:  # noqa: BLE001 -- a side figure: report why it is missing
+            gpu_ref = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not raw:
         try:
@@ -729,7 +841,8 @@ def main():
                        **({"transport_note": probe_note} if probe_note else {}),
                        "l2": f"inputs larger than L2 (each step touches {(1 + world) * layers * 2 * n_local * CH * 2 / 1e9:.1f} GB "
                              "of distinct K/V inputs + cached bases per rank)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clock_info,
             "fidelity": fidelity,
             "ranks_identical": {"ok": identical, "buffers_hashed": n_hashed,
                                 "what": "64-bit checksum of every layer's global K and V buffer, equal on all ranks"},

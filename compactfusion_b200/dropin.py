@@ -1,0 +1,98 @@
+"""The engines behind the reference's hooks.
+
+xDiT calls `compact_fwd` per attention layer (hybrid/attn_layer.py:59-64), which resolves to
+`ring._compact_ring_fwd` or `patchpara.fwd.patch_gather_fwd`.  Written like the reference, those paths allocate a
+payload and W reconstructions per call, `torch.cat` them, and exchange through eager NCCL.  This module lets the
+SAME hooks run on `engine.PatchGatherEngine` / `engine.RingExchangeEngine` instead: persistent per-layer buffers
+that are at once the error-feedback cache, the reconstruction and the attention input; K and V in one launch;
+all origins in one flag-waiting launch; payloads stored straight into the peers' receive slots over NVLink.
+
+An engine is built lazily per (hook, process group, shard shape).  The layer count is not known up front: like
+hybrid/attn_layer.py:176-179 numbers the attention modules in the order of their first forward, an engine
+grows one layer per new `mod_idx` while the warm-up step(s) run (compress_func returns WARMUP there,
+examples/configs.py:9) and freezes its layout at the first compressed call, when the one-sided transport is
+mapped (a collective over `group`: every rank reaches it at the same layer).
+
+The engines are used when the configuration is the fast one the reference ships for production
+(`fastpath=True`, `comp_rank=-1`, BINARY / INT2 / WARMUP, no stats logging, no consistency check, no quantised
+cache); everything else keeps the per-call path.  `CF_DROPIN_ENGINE=0` forces the per-call path (A/B, tests).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+from .utils import COMPACT_COMPRESS_TYPE as T
+
+_ENGINE_TYPES = (T.WARMUP, T.BINARY, T.INT2)
+_engines: dict = {}
+
+
+def enabled() -> bool:
+    return os.environ.get("CF_DROPIN_ENGINE", "1") != "0"
+
+
+def usable(cfg, ctype, k: torch.Tensor) -> bool:
+    """True if this call can run on an engine (see the module docstring for the conditions)."""
+    if not (enabled() and cfg.fastpath and cfg.comp_rank == -1 and ctype in _ENGINE_TYPES):
+        return False
+    if cfg.log_compress_stats or cfg.check_cache_consistency or cfg.quantized_cache:
+        return False
+    c = k.shape[-2] * k.shape[-1]
+    return k.is_cuda and k.dtype == torch.half and k.dim() == 4 and c % 128 == 0 and 64 <= c <= 8192
+
+
+def _group_key(group):
+    return "world" if group is None else id(group)
+
+
+def get(kind: str, group, k: torch.Tensor, mod_idx):
+    """(engine, dense layer index) for this hook / group / shard shape; `mod_idx` (any hashable the caller uses
+    to name the layer) is mapped to the engine's own 0-based index in order of first appearance."""
+    from .engine import PatchGatherEngine, RingExchangeEngine
+    n, c = k.shape[0] * k.shape[1], k.shape[2] * k.shape[3]
+    key = (kind, _group_key(group), n, c, k.device.index)
+    ent = _engines.get(key)
+    if ent is None:
+        cls = RingExchangeEngine if kind == "ring" else PatchGatherEngine
+        transport = os.environ.get("CF_DROPIN_TRANSPORT", "auto")
+        ent = (cls(0, n, c, group=group, device=k.device, transport=transport), {})
+        _engines[key] = ent
+    eng, index = ent
+    layer = index.get(mod_idx)
+    if layer is None:
+        layer = len(index)
+        index[mod_idx] = layer
+        eng.ensure_layer(layer)
+    return eng, layer
+
+
+def as_sequence(glob: torch.Tensor, world: int, shard_shape) -> torch.Tensor:
+    """(W * bs * s, h * d) engine buffer -> (bs, W * s, h, d), the tensor `torch.cat(k_list, dim=1)` builds in the
+    reference (patchpara/fwd.py:206-207): a VIEW for bs == 1 (FLUX), one gather copy otherwise."""
+    bs, s, h, d = shard_shape
+    if bs == 1:
+        return glob.view(1, world * s, h, d)
+    return glob.view(world, bs, s, h, d).transpose(0, 1).reshape(bs, world * s, h, d)
+
+
+def reset():
+    """compact_reset (per image): the engines stay -- their buffers are re-based by the next warm-up step and
+    their transport stays mapped; only the mod_idx numbering is kept as is (same model, same layers)."""
+    return None
+
+
+def shutdown():
+    """compact_init (new configuration): release every engine (unmaps the peers' receive regions)."""
+    for eng, _ in _engines.values():
+        try:
+            eng.close()
+        except Exception:  # noqa: BLE001 -- best effort at teardown
+            pass
+    _engines.clear()
+
+
+def engines():
+    return [e for e, _ in _engines.values()]

@@ -142,10 +142,11 @@ class PatchGatherEngine:
         self.transport = "nccl"
         self._p2p = {}
         self._p2p_requested = transport
-        # (with a single layer a fast rank could overwrite a slot its peer is still reading: the
-        #  per-layer slots are only hazard-free when another layer's exchange separates two uses)
-        if transport in ("p2p", "auto") and self.world > 1 and layers >= 2:
-            self.transport = "p2p"  # regions are mapped lazily per codec (payload size differs)
+        # layers == 0: the layer count is discovered while the warm-up step(s) walk the model (`ensure_layer`, what
+        # hybrid/attn_layer.py:176-179 does for mod_idx) and frozen by the first compressed exchange (`freeze`)
+        self._frozen = layers > 0
+        if self._frozen:
+            self._pick_transport()
         # CF_FLAG_INPUTS_STABLE (include/compactb200.h) is a CALLER promise: the kernel launched right before a
         # compress / decompress on this stream did not write the K/V inputs or the cached bases that call reads,
         # so their first tiles may be fetched while that kernel drains.  True for a runtime that walks distinct
@@ -157,6 +158,32 @@ class PatchGatherEngine:
         self.fused_put = os.environ.get("CF_FUSED_PUT", "1") != "0"
         self._per_layer_send = False
         self._side = None  # second stream of the overlapped step
+
+    def _pick_transport(self):
+        # (with a single layer a fast rank could overwrite a slot its peer is still reading: the
+        #  per-layer slots are only hazard-free when another layer's exchange separates two uses)
+        if self._p2p_requested in ("p2p", "auto") and self.world > 1 and self.layers >= 2:
+            self.transport = "p2p"  # regions are mapped lazily per codec (payload size differs)
+
+    def ensure_layer(self, layer: int):
+        """Grow the per-layer buffers up to `layer` (lazy engines only; frozen once compression starts, because
+        the receive regions of the one-sided transport are laid out per layer and mapped by every peer)."""
+        if layer < len(self.global_k):
+            return
+        if self._frozen and self._p2p:
+            raise nv.NativeError(f"layer {layer} first seen after the one-sided transport was mapped for "
+                                 f"{self.layers} layers: every attention layer must run in the warm-up step")
+        W = self.world
+        while len(self.global_k) <= layer:
+            self.global_k.append(torch.zeros((W * self.n, self.c), dtype=torch.half, device=self.device))
+            self.global_v.append(torch.zeros((W * self.n, self.c), dtype=torch.half, device=self.device))
+        self.layers = len(self.global_k)
+
+    def freeze(self):
+        """First compressed exchange: the layer count is final, choose the transport."""
+        if not self._frozen:
+            self._frozen = True
+            self._pick_transport()
 
     def prepare(self, ctype) -> str:
         """Set up the transport for `ctype` now (collective call); returns the transport in use."""
@@ -294,6 +321,8 @@ class PatchGatherEngine:
         """Uncompressed step (COMPACT_COMPRESS_TYPE.WARMUP): raw shards are gathered straight
         into the global buffers, which become the first bases (main.py:195-209, :351-366)."""
         k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
+        if not self._frozen:
+            self.ensure_layer(layer)
         if self.world == 1:
             self.global_k[layer].copy_(k2)
             self.global_v[layer].copy_(v2)
@@ -307,7 +336,9 @@ class PatchGatherEngine:
         return self.global_k[layer], self.global_v[layer]
 
     def _compress_args(self, layer, k2, v2, ctype):
-        key = ("c", layer, k2.data_ptr(), v2.data_ptr(), ctype)
+        # cached per (layer, codec); the input pointers are patched in place every call (a model hands over
+        # freshly allocated K / V tensors each step: keying the cache on their addresses would grow it forever)
+        key = ("c", layer, ctype)
         args = self._ptr_cache.get(key)
         if args is None:
             send, _ = self._buffers(ctype, layer)
@@ -319,6 +350,7 @@ class PatchGatherEngine:
             args = (nv.ptr_array([k2, v2]), nv.ptr_array(bases), nv.ptr_array([None, None]), nv.ptr_array([pk, pv]),
                     nv.ptr_array([uk, uv]), nv.ptr_array([vk, vv]), ws)
             self._ptr_cache[key] = args
+        args[0][0], args[0][1] = k2.data_ptr(), v2.data_ptr()
         return args
 
     def _decompress_args_p2p(self, layer, ctype, st, origins=None):
@@ -395,7 +427,7 @@ class PatchGatherEngine:
         st = self._p2p_region(ctype)
         assert st, "compress_put needs the p2p transport"
         k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
-        key = ("cp", layer, k2.data_ptr(), v2.data_ptr(), ctype)
+        key = ("cp", layer, ctype)
         args = self._ptr_cache.get(key)
         if args is None:
             W, pn_bytes = self.world, self._numel(ctype) * 2
@@ -407,6 +439,7 @@ class PatchGatherEngine:
             args = (nv.ptr_array([k2, v2]), nv.ptr_array(bases), dst, flg, st["count"][layer:layer + 1].data_ptr(), ws)
             self._ptr_cache[key] = args
         xs, bases, dst, flg, count_ptr, ws = args
+        xs[0], xs[1] = k2.data_ptr(), v2.data_ptr()
         rc = nv.lib().cf_sign_compress_put(_CODEC[ctype] | self._flags, passes, 2, xs, bases, self.world, self.rank, dst, flg, count_ptr,
                                            st["ticket"].data_ptr(), self.n, self.c, ws.data_ptr(), ws.numel(),
                                            nv.stream_ptr())
@@ -461,6 +494,7 @@ class PatchGatherEngine:
     def send(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
         """Sender side of one layer: compress this rank's K and V and deliver the payloads to every rank."""
         assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
+        self.freeze()
         if self.fused(ctype):
             self.compress_put(layer, k, v, ctype)
         else:

@@ -42,6 +42,8 @@ _owned: set = set()  # cache keys whose base tensor was allocated by this module
 def compact_init(config: CompactConfig):
     """main.py:37-52.  Must precede pipeline construction."""
     global _config, _cache, _step, _allgather_cache, _current_cache_key
+    from . import dropin
+    dropin.shutdown()  # engines behind the hooks are built for one configuration
     _config = config
     _cache = CompactCache(quantize=config.quantized_cache)
     _owned.clear()

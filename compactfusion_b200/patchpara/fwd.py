@@ -35,10 +35,20 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
     rank = dist.get_rank(group)
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
 
+    key_to_use = value_to_use = None
     if config.use_compact:
         ctype = compact_config().compress_func(mod_idx, current_iter)
-        k_list = compact_all_gather(f"{mod_idx}-k", k, comp_type=ctype, group=group)
-        v_list = compact_all_gather(f"{mod_idx}-v", v, comp_type=ctype, group=group)
+        from .. import dropin
+        if dropin.usable(compact_config(), ctype, k):
+            # K and V of the layer through the persistent-buffer engine: one compress(+put) launch pair, one
+            # reconstruct launch for all W origins, straight into the buffer attention reads (no cat for bs == 1)
+            eng, layer = dropin.get("patch", group, k, mod_idx)
+            gk, gv = eng.exchange(layer, k, v, ctype)
+            key_to_use = dropin.as_sequence(gk, world_size, k.shape)
+            value_to_use = dropin.as_sequence(gv, world_size, v.shape)
+        else:
+            k_list = compact_all_gather(f"{mod_idx}-k", k, comp_type=ctype, group=group)
+            v_list = compact_all_gather(f"{mod_idx}-v", v, comp_type=ctype, group=group)
     elif not config.async_comm:
         k_list = [torch.empty_like(k) for _ in range(world_size)]
         v_list = [torch.empty_like(v) for _ in range(world_size)]
@@ -73,8 +83,9 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
                 cache.put(kk, dist.all_gather(nk, k, group=group, async_op=True), nk, k)
                 cache.put(vk, dist.all_gather(nv_, v, group=group, async_op=True), nv_, v)
 
-    key_to_use = torch.cat(k_list, dim=1)
-    value_to_use = torch.cat(v_list, dim=1)
+    if key_to_use is None:
+        key_to_use = torch.cat(k_list, dim=1)
+        value_to_use = torch.cat(v_list, dim=1)
     if is_joint and joint_strategy == "front":
         key_to_use = torch.cat([joint_tensor_key, key_to_use], dim=1)
         value_to_use = torch.cat([joint_tensor_value, value_to_use], dim=1)

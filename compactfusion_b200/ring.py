@@ -107,6 +107,16 @@ def _compact_ring_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, win
     shape = k.shape
     assert v.shape == shape
 
+    from . import dropin
+    if (dropin.usable(compact_config(), ctype, k) and not causal and dropout_p == 0
+            and tuple(window_size) == (-1, -1)):
+        # the ring on the persistent-buffer engine: the payload goes to every rank's slot at once, hop s consumes
+        # origin (rank - s) mod W with one flag-waiting launch for K and V, the LSE merge is one fused kernel
+        eng, layer = dropin.get("ring", group, k, mod_idx)
+        out, lse = eng.ring_forward(layer, q, k, v, ctype, softmax_scale, joint_tensor_key, joint_tensor_value,
+                                    joint_strategy)
+        return out, lse, None
+
     k_send = compact_compress(f"{mod_idx}-{me % W}-k", k, ctype, update_cache=True)
     v_send = compact_compress(f"{mod_idx}-{me % W}-v", v, ctype, update_cache=True)
     # one message per hop: [K payload | V payload]

@@ -144,11 +144,11 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 @pytest.mark.parametrize("argv", [
-    ["--layers", "2", "--steps", "4", "--no-cpu-baseline", "--no-parity"],
-    ["--layers", "6", "--steps", "3", "--no-cpu-baseline", "--overlap", "--codec", "int2", "--no-parity"],
-    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-graph", "--no-e2e", "--no-parity"],
-    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--codec", "raw"],
-    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--workload", "pixart_patch_parallel"],
+    ["--layers", "2", "--steps", "4", "--no-cpu-baseline", "--no-gpu-reference", "--no-parity"],
+    ["--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--overlap", "--codec", "int2", "--no-parity"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-graph", "--no-e2e", "--no-parity"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--codec", "raw"],
+    ["--layers", "2", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--workload", "pixart_patch_parallel"],
 ])
 def test_bench_gpu_arm_single_gpu_dry_run(monkeypatch, capsys, argv):
     line = _run_bench(monkeypatch, capsys, argv)
@@ -180,10 +180,10 @@ def test_bench_gpu_arm_single_gpu_dry_run(monkeypatch, capsys, argv):
 
 
 @pytest.mark.parametrize("argv", [
-    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline"],
-    ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--overlap", "--no-parity"],
-    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--transport", "nccl", "--no-parity"],
-    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-e2e", "--workload", "cogvideox5b_ring",
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference"],
+    ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--overlap", "--no-parity"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--transport", "nccl", "--no-parity"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--workload", "cogvideox5b_ring",
      "--codec", "int2", "--no-parity"],
 ])
 def test_bench_gpu_arm_two_rank_dry_run(monkeypatch, capsys, argv):
@@ -205,3 +205,29 @@ def test_bench_gpu_arm_two_rank_dry_run(monkeypatch, capsys, argv):
         assert "k_p2p_put" not in names
     if "cogvideox5b_ring" in argv:
         assert cfg["exchange"] == "ring"
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_reference_arm_runs_on_the_host(gpus):
+    """`bench.py --impl reference`: the reference's own eager-torch path when baseline/_ref is staged (kind
+    "reference"), the oracle port otherwise; ms_per_step is the measured sample step, never an extrapolation."""
+    import os
+    import subprocess
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t0 = time.time()
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", str(gpus),
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                       env={k: v for k, v in os.environ.items() if k not in ("WORLD_SIZE", "RANK", "LOCAL_RANK")})
+    wall = time.time() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == gpus and line["unit"] == "GB/s"
+    staged = os.path.isdir(os.path.join(root, "baseline", "_ref", "xfuser", "compact"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"] and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["ms_per_step"] * line["steps"] / 1e3 < wall, "the claimed steps must fit inside the run"
+    assert line["config"]["workload"] == "flux1024_patch_parallel"
