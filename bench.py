@@ -48,16 +48,16 @@ WORKLOAD, MODE = "flux1024_patch_parallel", "patch"
 # The default (configs[1], the one `metric` is quoted on) is the headline; the others are extra bench lines.
 WORKLOADS = {
     # FLUX.1-dev 1024^2: 57 layers, 4096 image + 512 text tokens, 24 x 128 channels, patch-parallel all-gather
-    "flux1024_patch_parallel": dict(layers=57, rows=4096 + 512, ch=3072, mode="patch",
+    "flux1024_patch_parallel": dict(layers=57, rows=4096 + 512, ch=3072, mode="patch", bs=1, heads=24,
                                     what="FLUX 1024^2 patch parallel"),
     # CogVideoX-5b 49 frames 720x480: 42 layers, bs 2 (CFG) x 17550 tokens (padded to 17552), 48 x 64 channels,
     # compressed ring attention (configs[2])
-    "cogvideox5b_ring": dict(layers=42, rows=2 * 17552, ch=3072, mode="ring",
+    "cogvideox5b_ring": dict(layers=42, rows=2 * 17552, ch=3072, mode="ring", bs=2, heads=48,
                              what="CogVideoX-5b 49x720x480 compressed ring attention"),
     # PixArt-alpha / SD3-medium 1024^2: bs 2 x 4096 tokens, 16 x 72 / 24 x 64 channels, patch parallel (configs[3])
-    "pixart_patch_parallel": dict(layers=28, rows=2 * 4096, ch=1152, mode="patch",
+    "pixart_patch_parallel": dict(layers=28, rows=2 * 4096, ch=1152, mode="patch", bs=2, heads=16,
                                   what="PixArt-alpha 1024^2 patch parallel"),
-    "sd3_patch_parallel": dict(layers=24, rows=2 * 4096, ch=1536, mode="patch",
+    "sd3_patch_parallel": dict(layers=24, rows=2 * 4096, ch=1536, mode="patch", bs=2, heads=24,
                                what="SD3-medium 1024^2 patch parallel"),
 }
 
@@ -81,8 +81,15 @@ def parse():
     p.add_argument("--codec", default="binary", choices=["binary", "int2", "raw"],
                    help="raw = the uncompressed exchange of the same K/V (NCCL all-gather of fp16 shards, what "
                         "xDiT does without the plugin): a comparison line, none of our kernels run")
+    p.add_argument("--raw-exchange", default="allgather", choices=["allgather", "ring", "async"],
+                   help="--codec raw: which uncompressed exchange to time (sync all-gather, NCCL P2P ring relay, "
+                        "DistriFusion stale-async all-gather)")
     p.add_argument("--workload", default="flux1024_patch_parallel", choices=sorted(WORKLOADS))
     p.add_argument("--layers", type=int, default=None, help="default: the workload's layer count")
+    p.add_argument("--api", default="engine", choices=["engine", "dropin"],
+                   help="engine: the whole-step runtime (engine.PatchGatherEngine / RingExchangeEngine, one CUDA graph "
+                        "per step); dropin: the reference's own hook, compact_fwd per attention layer (hybrid/"
+                        "attn_layer.py:59-64), eager launches, with the attention that follows the exchange stubbed out")
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     p.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                    help="payload exchange for N > 1: one-sided NVLink puts (p2p) or NCCL all-gather")
@@ -670,6 +677,107 @@ def gpu_reference(args, ks, vs, pattern, layers, n_local, device, steps=3):
                     "compact_decompress as shipped) on the same GPU, same inputs, world size 1"}
 
 
+class RawBaseline:
+    """`--codec raw`: what xDiT moves WITHOUT the plugin, same K / V, same harness.  None of
+    our kernels run; the lines say `"impl": "uncompressed_baseline"`.
+      allgather : synchronous all-gather of the fp16 shards, K and V per layer (patchpara/fwd.py:103-111)
+      ring      : the uncompressed ring -- every layer relays the raw [K | V] block W-1 hops with batch_isend_irecv
+                  (xfuser/core/long_ctx_attention/ring/ring_flash_attn.py:16-137, attention left out)
+      async     : DistriFusion's stale all-gather -- the collective of step t is waited for in step t+1, the
+                  attention of step t uses the peers' previous K / V (patchpara/fwd.py:113-173)"""
+
+    def __init__(self, kind, eng, world, rank, layers, n_local, device):
+        self.kind, self.eng, self.world, self.rank, self.layers = kind, eng, world, rank, layers
+        self.kernel_launches = 0
+        if kind == "ring" and world > 1:
+            self.buf = [torch.empty((2, n_local, CH), dtype=torch.half, device=device) for _ in range(2)]
+        if kind == "async":
+            self.pending = [None] * layers
+            self.nxt_k = [torch.empty_like(g) for g in eng.global_k]
+            self.nxt_v = [torch.empty_like(g) for g in eng.global_v]
+
+    def step(self, ks, vs, _ctype=None, _overlap=False):
+        eng, W = self.eng, self.world
+        for l in range(self.layers):
+            k2, v2 = ks[l].reshape(eng.n, eng.c), vs[l].reshape(eng.n, eng.c)
+            if W == 1 or self.kind == "allgather":
+                eng.warmup(l, k2, v2)
+            elif self.kind == "ring":
+                cur = self.buf[0]
+                cur[0].copy_(k2)
+                cur[1].copy_(v2)
+                send_to, recv_from = (self.rank + 1) % W, (self.rank - 1) % W
+                for s in range(W):
+                    origin = (self.rank - s) % W
+                    eng._shard(eng.global_k[l], origin).copy_(cur[0])  # hand the block to "attention"
+                    eng._shard(eng.global_v[l], origin).copy_(cur[1])
+                    if s + 1 < W:
+                        nxt = self.buf[(s + 1) & 1]
+                        for r in dist.batch_isend_irecv([dist.P2POp(dist.isend, cur, send_to),
+                                                         dist.P2POp(dist.irecv, nxt, recv_from)]):
+                            r.wait()
+                        cur = nxt
+            else:  # stale-async
+                if self.pending[l] is not None:
+                    for h in self.pending[l]:
+                        h.wait()
+                    eng.global_k[l], self.nxt_k[l] = self.nxt_k[l], eng.global_k[l]   # the peers' previous step
+                    eng.global_v[l], self.nxt_v[l] = self.nxt_v[l], eng.global_v[l]
+                eng._shard(eng.global_k[l], self.rank).copy_(k2)                       # fresh local shard
+                eng._shard(eng.global_v[l], self.rank).copy_(v2)
+                self.pending[l] = [dist.all_gather_into_tensor(self.nxt_k[l], k2, async_op=True),
+                                   dist.all_gather_into_tensor(self.nxt_v[l], v2, async_op=True)]
+
+    def finish(self):
+        if self.kind == "async":
+            for hs in self.pending:
+                for h in hs or []:
+                    h.wait()
+            self.pending = [None] * self.layers
+
+
+class DropinDriver:
+    """`--api dropin`: the step as an xDiT pipeline drives it -- `compact_fwd(q, k, v, ..., mod_idx, current_iter)` once
+    per attention layer (ring.py:36-70 -> _compact_ring_fwd / patch_gather_fwd), eager launches on the current
+    stream, the plugin's own state machine deciding WARMUP vs codec from `compress_func(layer, step)`.  The attention
+    block behind the exchange is replaced by a stub that launches nothing (`attention.set_attention_override`), so
+    the figure is the exchange hooks' cost, comparable with the engine lines."""
+
+    def __init__(self, ctype, layers, n_local, device, transport):
+        import compactfusion_b200 as cf
+        from compactfusion_b200 import attention, dropin
+        from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+        w = WORKLOADS[WORKLOAD]
+        self.cf, self.dropin, self.layers = cf, dropin, layers
+        self.bs, self.h = w["bs"], w["heads"]
+        self.shape = (self.bs, n_local // self.bs, self.h, CH // self.h)
+        os.environ["CF_DROPIN_TRANSPORT"] = transport
+        patch = MODE == "patch"
+        cfg = cf.CompactConfig(enabled=True, override_with_patch_gather_fwd=patch,
+                               patch_gather_fwd_config=cf.PatchConfig(True, False, 1) if patch else None,
+                               compress_func=lambda l, s: ctype if s >= 1 else T.WARMUP, comp_rank=-1, residual=1,
+                               ef=True, fastpath=True)
+        cf.compact_init(cfg)
+        self.q = torch.zeros(self.shape, dtype=torch.half, device=device)
+        out = torch.zeros(self.shape, dtype=torch.half, device=device)
+        lse = torch.zeros((self.bs, self.h, self.shape[1]), dtype=torch.float32, device=device)
+        attention.set_attention_override(lambda q, k, v, *a: (out, lse))
+        self.it = 0
+        self.kernel_launches_base = 0
+
+    @property
+    def eng(self):
+        return self.dropin.engines()[0]
+
+    def step(self, ks, vs, _ctype=None, _overlap=False):
+        """One denoising step: every layer's hook call.  The step index decides WARMUP (step 0) vs the codec."""
+        self.cf.compact_set_step(self.it)
+        for l in range(self.layers):
+            self.cf.compact_fwd(self.q, ks[l].view(self.shape), vs[l].view(self.shape), causal=False, mod_idx=l,
+                                current_iter=self.it)
+        self.it += 1
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -689,6 +797,13 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    elif args.api == "dropin":
+        # the reference's hooks ask torch.distributed for rank / world size (patchpara/fwd.py:60-61): a one-rank group
+        import socket
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=1, rank=0)
 
     from compactfusion_b200 import build as cf_build
     if not os.path.exists(cf_build.OUT) and local_rank == 0:
@@ -704,14 +819,21 @@ def main():
     # patch workloads reconstruct all origins in one launch
     engine_cls = RingExchangeEngine if MODE == "ring" else PatchGatherEngine
     probe_note = None
-    if world > 1 and args.transport == "auto" and not raw:
+    dropin_api = args.api == "dropin"
+    assert not (dropin_api and raw), "--api dropin drives the compressed hooks; use --api engine for --codec raw"
+    if world > 1 and args.transport == "auto" and not raw and not dropin_api:
         ok, why = p2p_probe(engine_cls, n_local, ctype, device)
         if not ok:
             args.transport, probe_note = "nccl", "one-sided transport rejected by the probe step: " + (why or "a peer failed")
         note(rank, f"p2p probe: {'ok' if ok else probe_note}")
     # inputs_stable: the bench's K/V inputs are static buffers, so the early pipeline fill is legitimate here
-    eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport, inputs_stable=True)
-    transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
+    driver = None
+    if dropin_api:
+        driver = DropinDriver(ctype, layers, n_local, device, args.transport)
+        args.no_graph, eng, transport = True, None, "pending"
+    else:
+        eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport, inputs_stable=True)
+        transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
     if raw and world > 1:
         transport = "nccl"  # all_gather_into_tensor of the raw fp16 shards (engine.warmup)
     note(rank, f"transport: {transport}")
@@ -735,17 +857,26 @@ def main():
 
     note(rank, "inputs ready")
     # step 0: WARMUP (uncompressed), not timed
-    eng.step(ks[0], vs[0], T.WARMUP)
+    if dropin_api:
+        driver.step(ks[0], vs[0])
+        eng = driver.eng  # the engine the hooks built while the warm-up step walked the layers
+    else:
+        eng.step(ks[0], vs[0], T.WARMUP)
+    stepper = driver if dropin_api else eng
+    if raw:
+        stepper = RawBaseline(args.raw_exchange, eng, world, rank, layers, n_local, device)
     torch.cuda.synchronize()
     note(rank, "warmup step done")
     # first compressed step, eagerly, on the NEXT version: loads the kernels and sizes the workspaces before any
     # capture.  (Never compress a tensor against an identical base: delta == 0 gives the reference's 0/0 BINARY
     # token scale, fastpath.py:164-165, and the NaN would stay in the error-feedback cache.)
     if not raw:
-        eng.step(ks[1], vs[1], ctype, args.overlap)
+        stepper.step(ks[1], vs[1], ctype, args.overlap)
         torch.cuda.synchronize()
+    if dropin_api:
+        transport = eng.transport if world > 1 else "none (single GPU)"
     graphs = None
-    mode = "eager"
+    mode = "eager (compact_fwd hook per layer)" if dropin_api else "eager"
     if not args.no_graph:
         try:
             graphs = [eng.capture_step(ks[v], vs[v], ctype, warmup_iters=0, overlap=args.overlap)
@@ -766,8 +897,10 @@ def main():
         if graphs is not None:
             graphs[v].replay()
         else:
-            eng.step(ks[v], vs[v], ctype, args.overlap)
+            stepper.step(ks[v], vs[v], ctype, args.overlap)
 
+    if raw:
+        mode = f"eager (uncompressed {args.raw_exchange})"
     for i in range(max(args.warmup, 3)):
         run_step(i)
     barrier()
@@ -780,6 +913,8 @@ def main():
     ev0.record()
     for i in range(args.steps):
         run_step(i)
+    if raw:
+        stepper.finish()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -834,7 +969,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "exchange": MODE, "codec": args.codec, "layers": layers, "seq": SEQ,
+            "config": {"workload": WORKLOAD, "api": ("dropin (compact_fwd hooks, eager launches, attention stubbed out)"
+                                                     if dropin_api else "engine (whole-step runtime)"),
+                       "exchange": MODE, "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
                        "schedule": "two chains (compress | reconstruct)" if (args.overlap and not raw and eng.can_overlap(ctype)) else "serial",
                        "transport": transport + (" (fused into the codec kernels)" if world > 1 and eng.fused(ctype) else ""),
@@ -851,7 +988,7 @@ def main():
                               and (parity is None or parity.get("ok"))),
             "p2p_wait_timeouts": timeouts,
         }))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

@@ -83,6 +83,24 @@ __device__ __forceinline__ uint64_t make_policy_evict_last() {
   return p;
 }
 
+// shared -> global bulk store (TMA 1-D): one instruction moves a staged span (codes of a row tile) to a
+// destination that may be peer memory over NVLink, instead of one sub-word store per thread and destination.
+// dst / src 16-byte aligned, bytes a multiple of 16.  Completion is tracked per thread in bulk groups.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed groups have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed groups are complete: their global writes are performed and visible to this thread
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared by the compute warps) -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// async-proxy global writes (completed bulk stores) ordered before later generic-proxy accesses of this thread
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // named barrier among the compute warps only (the producer warp never joins)
 __device__ __forceinline__ void compute_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");

@@ -46,6 +46,8 @@ struct FanOut {
   unsigned long long u_off, v_off;    // byte offsets of U (N) and V (C) inside a payload
   int n_dst;
   int publish_mode;                   // 0: every CTA adds 1 to every flag; 1: the last CTA stores the new count
+  int vec16;                          // U and V of every destination are 16-byte aligned and N % 8 == 0, C % 32 == 0:
+                                      // the finalize kernel stores them 8 scales at a time
 };
 
 __device__ __forceinline__ void red_add_relaxed_sys_u32(uint32_t* p, uint32_t v) {
@@ -290,19 +292,47 @@ __global__ void __launch_bounds__(1024) k_finalize_scales(const FinalizeParams p
 #pragma unroll
     for (int k = 0; k < 32; ++k) tot += red[k][cx];
     const __half v = __float2half_rn(tot / n_f);
-    if (PUT) {
+    if (PUT && f.vec16) {
+      // 8 neighbouring lanes' scales in one 16-byte store per destination (a remote 2-byte store per lane and
+      // destination costs an NVLink packet each)
+      // (C % 32 == 0 here, so all 32 lanes of this warp are inside the tensor and take part in the shuffles)
+      const uint32_t mine = __half_as_ushort(v);
+      const uint32_t next = __shfl_xor_sync(0xffffffffu, mine, 1);
+      const uint32_t pair = mine | (next << 16);            // valid on even lanes
+      uint4 w;
+      w.x = pair;
+      w.y = __shfl_xor_sync(0xffffffffu, pair, 2);          // lanes 0 / 4 (mod 8): the pair of lanes 2 / 6
+      w.z = __shfl_xor_sync(0xffffffffu, pair, 4);          // lane 0 (mod 8): the pair of lane 4
+      w.w = __shfl_xor_sync(0xffffffffu, w.y, 4);           // lane 0 (mod 8): the pair of lane 6
+      if ((cx & 7) == 0)
+        for (int q = 0; q < f.n_dst; ++q)
+          *reinterpret_cast<uint4*>(f.dst[t * f.n_dst + q] + f.v_off + 2 * static_cast<size_t>(c)) = w;
+    } else if (PUT) {
       for (int q = 0; q < f.n_dst; ++q) reinterpret_cast<__half*>(f.dst[t * f.n_dst + q] + f.v_off)[c] = v;
     } else {
       p.scale_v[t][c] = v;
     }
   }
   const float denom = denom_s;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-    const __half u = __float2half_rn(__half2float(p.rowmean[t][n]) / denom);
-    if (PUT) {
-      for (int q = 0; q < f.n_dst; ++q) reinterpret_cast<__half*>(f.dst[t * f.n_dst + q] + f.u_off)[n] = u;
-    } else {
-      p.scale_u[t][n] = u;
+  if (PUT && f.vec16) {
+    for (int n8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8; n8 < N; n8 += gridDim.x * blockDim.x * 8) {
+      const uint4 rm = *reinterpret_cast<const uint4*>(p.rowmean[t] + n8);  // workspace: 256-byte aligned
+      const __half* rh = reinterpret_cast<const __half*>(&rm);
+      __align__(16) __half u8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u8[e] = __float2half_rn(__half2float(rh[e]) / denom);
+      for (int q = 0; q < f.n_dst; ++q)
+        *reinterpret_cast<uint4*>(f.dst[t * f.n_dst + q] + f.u_off + 2 * static_cast<size_t>(n8)) =
+            *reinterpret_cast<const uint4*>(u8);
+    }
+  } else {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+      const __half u = __float2half_rn(__half2float(p.rowmean[t][n]) / denom);
+      if (PUT) {
+        for (int q = 0; q < f.n_dst; ++q) reinterpret_cast<__half*>(f.dst[t * f.n_dst + q] + f.u_off)[n] = u;
+      } else {
+        p.scale_u[t][n] = u;
+      }
     }
   }
   if (PUT && publish) fanout_publish(f, gridDim.x * gridDim.y);
@@ -609,8 +639,18 @@ static int l2_keep_base(int64_t N, int64_t C, int batch) {
 }
 static int l2_stream_hints() { return pipe_env_int("CF_L2_HINTS", 1) != 0 ? 1 : 0; }
 
+// CF_PUT_BULK=0 keeps the per-thread sub-word stores of the fused put (A/B); the bulk flavour needs whole tiles of
+// code bytes to be 16-byte multiples at 16-byte aligned destinations
+static bool put_bulk_ok(const FanOut* fan, int batch, int64_t code_row_bytes) {
+  if (fan == nullptr || pipe_env_int("CF_PUT_BULK", 1) == 0 || code_row_bytes % 16 != 0) return false;
+  for (int i = 0; i < batch * fan->n_dst; ++i)
+    if (!aligned16(fan->dst[i])) return false;
+  return true;
+}
+
 static PipeArgs pipe_args(const PipeGeom& g, int rows_per_cta, int l2_hints, bool early_load) {
   PipeArgs a{};
+  a.put_tile = g.put_tile;
   a.l2_hints = l2_hints;
   a.early_load = (early_load && pdl_enabled()) ? 1 : 0;
   a.TX = g.TX; a.TY = g.TY; a.R = g.R; a.stages = g.stages; a.chunk_rows = g.chunk_rows; a.u_cap = g.u_cap;
@@ -646,7 +686,7 @@ static StatsPlan make_stats_plan(int64_t N, int64_t C, int batch, bool allow_tma
   pl.geom = make_row_geom(C);
   pl.tma = false;
   if (allow_tma && !legacy_forced()) {
-    pl.pipe = make_pipe_geom(C, 2, 0, false);
+    pl.pipe = make_pipe_geom(C, 2, 0, false, static_cast<int>(C / 8));
     if (pl.pipe.ok) {
       int B = sm_count() * pl.pipe.ctas_per_sm / (batch > 0 ? batch : 1);
       if (B < 1) B = 1;
@@ -695,7 +735,8 @@ template <int MODE>
 static int launch_stats(const StatsPlan& pl, const StatsParams& sp, int batch, cudaStream_t st, bool stable = false,
                         const FanOut* fan = nullptr) {
   if (pl.tma) {
-    const PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta, l2_keep_base(sp.N, sp.C, batch), stable);
+    PipeArgs a = pipe_args(pl.pipe, pl.rows_per_cta, l2_keep_base(sp.N, sp.C, batch), stable);
+    a.put_bulk = (MODE == MODE_BINARY && put_bulk_ok(fan, batch, sp.C / 8)) ? 1 : 0;
     dim3 grid(pl.B, batch), block(pl.pipe.TX * pl.pipe.TY + 32);
     const int variant = (pl.pipe.G == 1 ? 0 : 2) + (pl.pipe.ctas_per_sm == 1 ? 0 : 1);
     // only BINARY emits codes in pass 1: the INT2 fused put stores them from the encode kernel
@@ -803,11 +844,12 @@ static int launch_int2_encode(const Int2EncodeParams& ep, int batch, cudaStream_
   for (int t = 0; t < batch && tma; ++t)
     tma = ep.base[t] != nullptr && aligned16(ep.base[t]) && aligned16(ep.x[t]) && aligned2(ep.packed[t]);
   if (tma) {
-    const PipeGeom pg = make_pipe_geom(ep.C, 2, 0, true);
+    const PipeGeom pg = make_pipe_geom(ep.C, 2, 0, true, ep.C / 4);
     if (pg.ok) {
       int n_cta = 1;
       const TileSched ts = make_tile_sched(pg, ep.N, batch, &n_cta);
-      const PipeArgs a = pipe_args(pg, 0, l2_keep_base(ep.N, ep.C, batch), stable);
+      PipeArgs a = pipe_args(pg, 0, l2_keep_base(ep.N, ep.C, batch), stable);
+      a.put_bulk = put_bulk_ok(fan, batch, ep.C / 4) ? 1 : 0;
       dim3 grid(n_cta), block(pg.TX * pg.TY + 32);
       const int variant = (pg.G == 1 ? 0 : 2) + (pg.ctas_per_sm == 1 ? 0 : 1);
       const bool put = fan != nullptr;
@@ -1020,6 +1062,9 @@ static int sign_compress_put(int passes, int batch, const void* const* x, const 
     CF_CHECK_ARG(dst_flag[q] != nullptr, "destination %d: null flag", q);
     f.flag[q] = static_cast<uint32_t*>(dst_flag[q]);
   }
+  bool vec16 = pipe_env_int("CF_PUT_BULK", 1) != 0 && N % 8 == 0 && C % 32 == 0 && f.u_off % 16 == 0;
+  for (int i = 0; i < batch * n_dst && vec16; ++i) vec16 = aligned16(dst_payload[i]);
+  f.vec16 = vec16 ? 1 : 0;
   for (int t = 0; t < batch; ++t) {
     char* ws = static_cast<char*>(workspace) + pl.per_tensor_bytes * t;
     sp.x[t] = static_cast<const __half*>(x[t]);

@@ -27,6 +27,7 @@ struct PipeGeom {
   uint32_t tile_bytes;   // R * C * 2
   uint32_t code_tile;    // R * code_row_bytes rounded up to 128 (apply only)
   uint32_t stage_bytes;
+  uint32_t put_tile;     // bytes of one staging buffer for the fused put's code bytes (R * put_row_bytes; 0: none)
   size_t smem_bytes;
   bool ok;
 };
@@ -38,7 +39,10 @@ static int pipe_env_int(const char* name, int dflt) {
 
 // nfull = number of full-size fp16 operands per stage (2: x + base, 1: base), code_row_bytes = bytes of
 // code per row staged alongside (0 if none), row_scales = the kernel stages per-row scales in smem
-static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes, bool row_scales) {
+// put_row_bytes = code bytes per row a fused put stages in smem before one bulk store per destination (the area is
+// reserved whether or not this launch is a put: put and plain launches must share ONE geometry, or their partial
+// sums -- and so the last ulp of the scales -- could differ)
+static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes, bool row_scales, int put_row_bytes = 0) {
   PipeGeom g{};
   g.ok = false;
   // tunables (measured on B200, profiles/r1_tuning.md)
@@ -74,8 +78,9 @@ static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes, bool ro
       g.code_tile = static_cast<uint32_t>((static_cast<size_t>(g.R) * code_row_bytes + 127) / 128 * 128);
       g.stage_bytes = g.tile_bytes * nfull + g.code_tile;
       g.chunk_rows = g.R * (128 / g.R > 0 ? 128 / g.R : 1);
+      g.put_tile = static_cast<uint32_t>((static_cast<size_t>(g.R) * put_row_bytes + 15) / 16 * 16);
       const size_t fixed = 256 /*barriers*/ + static_cast<size_t>(g.chunk_rows) * g.NWX * 4 + 256 /*warp sums*/ +
-                           static_cast<size_t>(g.u_cap) * 2;
+                           static_cast<size_t>(g.u_cap) * 2 + 2 * static_cast<size_t>(g.put_tile);
       if (budget < fixed + 2 * static_cast<size_t>(g.stage_bytes)) continue;
       int stages = static_cast<int>((budget - fixed) / g.stage_bytes);
       if (stages > max_stages) stages = max_stages;
@@ -92,6 +97,8 @@ static PipeGeom make_pipe_geom(int64_t C, int nfull, int code_row_bytes, bool ro
 struct PipeArgs {
   int TX, TY, R, stages, chunk_rows, u_cap;
   uint32_t tile_bytes, stage_bytes;
+  uint32_t put_tile;   // staging buffer bytes of the fused put (two buffers); 0: store the codes directly
+  int put_bulk;        // 1: the fused put moves a tile's code bytes with one bulk store per destination
   int rows_per_cta;
   // L2 residency plan (see l2_hints_for): pass 1 loads base with evict_last so the apply / encode pass
   // that follows re-reads it from L2; x, codes and the rewritten base lines are evict_first
@@ -110,6 +117,7 @@ struct PipeSmem {
   float* rowpart;   // [chunk_rows][NWX]
   float* wsum;      // [64]
   __half* u_s;      // [u_cap]
+  unsigned char* put_s;  // [2][put_tile]
 };
 __device__ __forceinline__ PipeSmem carve_smem(unsigned char* raw, const PipeArgs& a, int NWX) {
   PipeSmem s;
@@ -123,6 +131,8 @@ __device__ __forceinline__ PipeSmem carve_smem(unsigned char* raw, const PipeArg
   s.wsum = reinterpret_cast<float*>(p);
   p += 256;
   s.u_s = reinterpret_cast<__half*>(p);
+  p += static_cast<size_t>(a.u_cap) * 2;
+  s.put_s = p;
   return s;
 }
 
@@ -157,6 +167,31 @@ __device__ __forceinline__ void pipe_produce(const PipeSmem& s, const PipeArgs& 
     for (int o = 0; o < NOPS; ++o)
       bulk_g2s_pol(dst + off[o], src[o] + static_cast<size_t>(r0) * row_bytes[o],
                    static_cast<uint32_t>(rows) * row_bytes[o], &s.full[st], pol[o]);
+  }
+}
+
+// Fused put, bulk flavour.  The compute warps write a tile's code bytes into staging buffer `buf`; then
+//   thread 0: bulk_wait_read0()      the previous tile's stores have finished reading the OTHER buffer
+//   compute_sync                     every warp's bytes of this tile are staged
+//   thread 0: one cp.async.bulk shared -> global per destination (the tile is one contiguous span in every slot)
+// so the next tile can be staged in the other buffer while this one is in flight.
+__device__ __forceinline__ void put_tile_begin(int tid) {
+  if (tid == 0) bulk_wait_read0();
+}
+__device__ __forceinline__ void put_tile_push(const FanOut& f, int t, const unsigned char* staged, size_t dst_off,
+                                              uint32_t bytes, int tid, int ncompute) {
+  compute_sync(ncompute);
+  if (tid == 0) {
+    fence_async_smem();
+    for (int q = 0; q < f.n_dst; ++q) bulk_s2g(f.dst[t * f.n_dst + q] + dst_off, staged, bytes);
+    bulk_commit();
+  }
+}
+// before the kernel ends (and before flags are published): every bulk store of this thread has landed
+__device__ __forceinline__ void put_drain(int tid) {
+  if (tid == 0) {
+    bulk_wait_all0();
+    fence_async_all();
   }
 }
 
@@ -232,6 +267,9 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     const int rows = min(a.R, r_end - r0);
     const size_t pk_tile_off = static_cast<size_t>(r0) * groups + tx;
     uint8_t* pk_tile = PUT ? nullptr : packed + pk_tile_off;
+    const bool bulk = PUT && MODE == MODE_BINARY && a.put_bulk;
+    unsigned char* stg = sm.put_s + static_cast<size_t>(it & 1) * a.put_tile;
+    if (bulk) put_tile_begin(tid);
     for (int q = ty; 4 * q < rows; q += TY) {
       float rs[4];
       const uint32_t qa = xs_a + static_cast<uint32_t>(4 * q) * row_bytes;
@@ -239,7 +277,9 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
       const size_t pk_off = pk_tile_off + static_cast<size_t>(4 * q) * groups;
       // one code byte to p.packed[t], or to every destination slot of the fused put
       auto emit = [&](int idx, uint32_t bits) {
-        if (PUT) {
+        if (bulk) {
+          stg[4 * q * groups + tx + idx] = static_cast<uint8_t>(bits);
+        } else if (PUT) {
           for (int qq = 0; qq < f.n_dst; ++qq) f.dst[t * f.n_dst + qq][pk_off + idx] = static_cast<uint8_t>(bits);
         } else {
           pk[idx] = static_cast<uint8_t>(bits);
@@ -315,6 +355,8 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[st]);
+    if (bulk)
+      put_tile_push(f, t, stg, static_cast<size_t>(r0) * groups, static_cast<uint32_t>(rows) * groups, tid, ncompute);
 
     const int done = r0 + rows;  // rows [chunk_base, done) have partial sums staged
     if (done - chunk_base >= a.chunk_rows || done >= r_end) {
@@ -330,6 +372,8 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
       chunk_base = done;
     }
   }
+
+  if (PUT && MODE == MODE_BINARY && a.put_bulk) put_drain(tid);
 
   // ---- CTA partial of sum_n rowmean[n] ----
   {
@@ -662,6 +706,10 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
   constexpr int kFly = (G == 1) ? 4 : 2;  // rows whose loads are issued before the first use
   const uint64_t st_pol = a.l2_hints ? make_policy_evict_first() : 0ull;
 
+  // fused put, bulk flavour: a tile's code words are staged in smem and pushed with one bulk store per destination
+  const bool bulk = PUT && a.put_bulk;
+  unsigned char* stg = sm.put_s;
+  size_t tile_code_base = 0;
   // codes of 8 elements (+ optional error-feedback base) from delta and the final scales
   auto encode8 = [&](const H8& xv, const H8& b, __half2 u2, const uint32_t* vf, int t, size_t code_off, __half* nb_dst) {
     const __half2 zero2 = __float2half2_rn(0.f);
@@ -679,7 +727,9 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     }
     const uint32_t both = sacc | macc;
     const uint32_t codes = (both | (both >> 16)) & 0xFFFFu;
-    if (PUT) {
+    if (bulk) {
+      *reinterpret_cast<uint16_t*>(stg + (code_off - tile_code_base)) = static_cast<uint16_t>(codes);
+    } else if (PUT) {
       for (int q = 0; q < f.n_dst; ++q)
         *reinterpret_cast<uint16_t*>(f.dst[t * f.n_dst + q] + code_off) = static_cast<uint16_t>(codes);
     } else {
@@ -698,6 +748,11 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     }
     const size_t pk_off = (static_cast<size_t>(r0) * groups + tx) * 2;  // byte offset of this thread's codes in the tile
     __half* __restrict__ nbp = p.new_base[t] != nullptr ? p.new_base[t] + static_cast<size_t>(r0) * C + 8 * tx : nullptr;
+    if (bulk) {
+      tile_code_base = static_cast<size_t>(r0) * groups * 2;
+      stg = sm.put_s + static_cast<size_t>(it & 1) * a.put_tile;
+      put_tile_begin(tid);
+    }
     mbar_wait(&sm.full[st], k & 1);
     const uint32_t xs_a = stage_a + static_cast<uint32_t>(st) * a.stage_bytes + static_cast<uint32_t>(tx) * 16u;
     const uint32_t bs_off = a.tile_bytes;
@@ -745,7 +800,9 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[st]);
+    if (bulk) put_tile_push(f, t, stg, tile_code_base, static_cast<uint32_t>(rows) * groups * 2, tid, ncompute);
   }
+  if (bulk) put_drain(tid);  // thread 0: its bulk stores have landed before it fences and publishes below
   if (PUT) fanout_publish_compute(f, gridDim.x, ncompute);  // compute threads only: the producer warp has exited
 }
 

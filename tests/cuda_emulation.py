@@ -242,6 +242,15 @@ static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t
 }
 static inline void bulk_g2s_hint(void* d, const void* s, uint32_t n, uint64_t* bar, uint64_t) { bulk_g2s(d, s, n, bar); }
 static inline void bulk_g2s_pol(void* d, const void* s, uint32_t n, uint64_t* bar, uint64_t) { bulk_g2s(d, s, n, bar); }
+static inline void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15u) { fprintf(stderr, "misaligned bulk store\n"); abort(); }
+  memcpy(dst, src, bytes);
+}
+static inline void bulk_commit() {}
+static inline void bulk_wait_read0() {}
+static inline void bulk_wait_all0() {}
+static inline void fence_async_smem() {}
+static inline void fence_async_all() {}
 static inline uint64_t make_policy_evict_first() { return 1; }
 static inline uint64_t make_policy_evict_last() { return 2; }
 static inline void compute_sync(int) { pthread_barrier_wait(&compute_bar); }

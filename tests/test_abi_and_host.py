@@ -258,6 +258,39 @@ for codec in (T.BINARY, T.INT2):
         assert torch.allclose(lse, ref_lse, atol=1e-3)
     cr.attn_forward = real_attn
     assert cf.compact_cache().passed_count == steps
+
+# ---------------- patch_gather_fwd, all three modes (patchpara/fwd.py:20-237) ----------------
+from compactfusion_b200.patchpara import fwd as pf
+seen = []
+real_attn = pf.attn_forward
+def spy2(q, k, v, *a, **kw):
+    seen.append((k.clone(), v.clone()))
+    return real_attn(q, k, v, *a, **kw)
+pf.attn_forward = spy2
+vs_ = [[x.flip(1).contiguous() for x in step] for step in xs]
+for mode in ("compact", "sync", "async"):
+    cfg = cf.CompactConfig(enabled=True, override_with_patch_gather_fwd=True,
+                           patch_gather_fwd_config=cf.PatchConfig(mode == "compact", mode == "async", 1),
+                           compress_func=lambda l, s: T.BINARY if s >= 1 else T.WARMUP, comp_rank=-1, residual=1,
+                           ef=True, fastpath=True)
+    cf.compact_init(cfg)
+    ok_ranks = [OracleCompact(residual=1, ef=True, fastpath=True) for _ in range(world)]
+    ov_ranks = [OracleCompact(residual=1, ef=True, fastpath=True) for _ in range(world)]
+    for t in range(steps):
+        seen.clear()
+        out, lse, _ = cf.compact_fwd(xs[t][rank], xs[t][rank], vs_[t][rank], causal=False, mod_idx=3, current_iter=t)
+        assert len(seen) == 1 and out.shape == xs[t][rank].shape
+        if mode == "compact":     # every origin's reconstruction, own shard included (main.py:410-419)
+            ct = cfg.compress_func(3, t).value
+            wk, _ = all_gather_step(ok_ranks, "3-k", xs[t], ct)
+            wv, _ = all_gather_step(ov_ranks, "3-v", vs_[t], ct)
+            want_k, want_v = torch.cat(wk[rank], dim=1), torch.cat(wv[rank], dim=1)
+        else:                      # raw shards; stale-async: the peers' PREVIOUS step, the fresh local shard
+            stale = mode == "async" and t >= 1
+            want_k = torch.cat([xs[t - 1 if (stale and r != rank) else t][r] for r in range(world)], dim=1)
+            want_v = torch.cat([vs_[t - 1 if (stale and r != rank) else t][r] for r in range(world)], dim=1)
+        assert torch.equal(seen[0][0], want_k) and torch.equal(seen[0][1], want_v), (mode, t)
+pf.attn_forward = real_attn
 dist.destroy_process_group()
 print("WORKER_OK", rank)
 '''

@@ -85,8 +85,25 @@ class FakeDist:
         for o in outs:
             o.copy_(inp)
 
-    def all_gather_into_tensor(self, out, inp, group=None):
+    class _Done:
+        def wait(self):
+            return None
+
+    def all_gather_into_tensor(self, out, inp, group=None, async_op=False):
         out.view(self.world, -1).copy_(inp.reshape(1, -1).expand(self.world, -1))
+        return self._Done() if async_op else None
+
+    isend, irecv = "isend", "irecv"
+
+    def P2POp(self, op, tensor, peer, group=None):
+        return (op, tensor, peer)
+
+    def batch_isend_irecv(self, ops):
+        sent = [t for op, t, _ in ops if op == "isend"]
+        for op, t, _ in ops:
+            if op == "irecv":
+                t.copy_(sent[0])
+        return [self._Done() for _ in ops]
 
     def destroy_process_group(self):
         self.up = False
@@ -183,6 +200,8 @@ def test_bench_gpu_arm_single_gpu_dry_run(monkeypatch, capsys, argv):
     ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference"],
     ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--overlap", "--no-parity"],
     ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--transport", "nccl", "--no-parity"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-e2e", "--codec", "raw", "--raw-exchange", "ring"],
+    ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-e2e", "--codec", "raw", "--raw-exchange", "async"],
     ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--workload", "cogvideox5b_ring",
      "--codec", "int2", "--no-parity"],
 ])
@@ -195,6 +214,10 @@ def test_bench_gpu_arm_two_rank_dry_run(monkeypatch, capsys, argv):
     line = _run_bench(monkeypatch, capsys, argv, world=2)
     assert BASE_KEYS <= set(line) and line["n_gpus"] == 2
     cfg = line["config"]
+    if "raw" in argv:
+        assert line["impl"] == "uncompressed_baseline" and line["roofline"] is None and line["gpu_launches"] == 0
+        assert cfg["launch_mode"] == "eager (uncompressed %s)" % argv[-1]
+        return
     nccl = "nccl" in argv
     assert cfg["transport"].startswith("nccl" if nccl else "p2p"), cfg["transport"]
     assert cfg["launch_mode"] == ("eager" if nccl else "cuda_graph")
