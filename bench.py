@@ -472,7 +472,7 @@ def oracle_parity(eng, xk, xv, ctype, codec, world, rank, device, barrier):
                                           [sh(glob, r) for r in range(world)])
     return {"ok": out["k"]["ok"] and out["v"]["ok"], "layer": 0, "rows_checked": 2 * world * n,
             "what": "rank 0: payloads of all origins as received + reconstructions of layer 0 vs oracle/check.py "
-                    "(codes bit-exact, scales <= 1 ulp, reconstruction bit-exact)", **out}
+                    "(codes bit-exact, V <= 1 ulp and U <= 2 ulp, reconstruction bit-exact)", **out}
 
 
 def measure_kernels(args, eng, ks, vs, ctype, world, rank, n_local, layers, transport, barrier):
@@ -758,6 +758,10 @@ class DropinDriver:
                                compress_func=lambda l, s: ctype if s >= 1 else T.WARMUP, comp_rank=-1, residual=1,
                                ef=True, fastpath=True)
         cf.compact_init(cfg)
+        # like a production run of the reference: its scope profiler records two CUDA events per hook call unless
+        # switched off (xfuser/prof.py:14-16)
+        from compactfusion_b200.prof import Profiler
+        Profiler.instance().disable()
         self.q = torch.zeros(self.shape, dtype=torch.half, device=device)
         out = torch.zeros(self.shape, dtype=torch.half, device=device)
         lse = torch.zeros((self.bs, self.h, self.shape[1]), dtype=torch.float32, device=device)

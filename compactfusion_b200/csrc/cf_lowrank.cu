@@ -15,6 +15,7 @@
 
 #include "cf_common.cuh"
 #include "cf_lowrank_mma.cuh"
+#include "cf_lowrank_orth.cuh"
 
 namespace cf {
 
@@ -473,8 +474,32 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
     dim3 grid((c + kLrBM - 1) / kLrBM, p.aty_splits);
     k_lr_gemm<RP, true><<<grid, kLrThreads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
   };
-  // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies)
+  // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies).
+  // One launch on one 8-CTA cluster (k_lr_orth); CF_LR_ORTH=legacy keeps round 1's five-launch chain (A/B).
+  static const bool legacy_orth = [] { const char* e = getenv("CF_LR_ORTH"); return e && e[0] == 'l'; }();
+  const size_t smem_o = lr_orth_smem<RP>();
+  if (!legacy_orth)
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)));
   auto orth = [&](int S, int M, int ctas, int rows, float2* out2, __half* out16, float* out32c) -> int {
+    if (!legacy_orth) {
+      OrthParams o{};
+      o.part = part; o.S = S; o.part_stride = static_cast<size_t>(M) * RP; o.X = Xsum; o.M = M; o.r = r;
+      o.out2 = out2; o.out16 = out16; o.out32c = out32c;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(kClusterCtas);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem_o;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kClusterCtas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_lr_orth<RP>, o));
+      return CF_OK;
+    }
     // the S split-K partials are added by a wide kernel (all SMs); the 16 Gram CTAs then read one copy
     k_lr_sum_split<<<small_grid, 256, 0, st>>>(part, S, static_cast<size_t>(M) * RP, nullptr, Xsum,
                                                static_cast<size_t>(M) * RP);

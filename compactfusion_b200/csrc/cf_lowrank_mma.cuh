@@ -183,15 +183,24 @@ __global__ void __launch_bounds__(kLrThreads) k_lr_gemm(const __half* __restrict
         a_odd[q] = __float_as_uint(f.y);
       }
       const float2* brow = Bs + (16 * kk + 2 * t) * kLdB + g;
+      // the 4 MMAs into one accumulator are a dependent chain (the wrappers keep program order): issue them
+      // across the RP / 8 independent accumulators, term by term, so consecutive MMAs never wait on each other
+      float2 be0[RP / 8], be1[RP / 8], bo0[RP / 8], bo1[RP / 8];
 #pragma unroll
       for (int j = 0; j < RP / 8; ++j) {
-        const float2 be0 = brow[8 * j], be1 = brow[8 * kLdB + 8 * j];
-        const float2 bo0 = brow[kLdB + 8 * j], bo1 = brow[9 * kLdB + 8 * j];
-        mma_tf32(acc[j], a_even, __float_as_uint(be0.x), __float_as_uint(be1.x));
-        mma_tf32(acc[j], a_even, __float_as_uint(be0.y), __float_as_uint(be1.y));
-        mma_tf32(acc[j], a_odd, __float_as_uint(bo0.x), __float_as_uint(bo1.x));
-        mma_tf32(acc[j], a_odd, __float_as_uint(bo0.y), __float_as_uint(bo1.y));
+        be0[j] = brow[8 * j];
+        be1[j] = brow[8 * kLdB + 8 * j];
+        bo0[j] = brow[kLdB + 8 * j];
+        bo1[j] = brow[9 * kLdB + 8 * j];
       }
+#pragma unroll
+      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_even, __float_as_uint(be0[j].x), __float_as_uint(be1[j].x));
+#pragma unroll
+      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_even, __float_as_uint(be0[j].y), __float_as_uint(be1[j].y));
+#pragma unroll
+      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].x), __float_as_uint(bo1[j].x));
+#pragma unroll
+      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].y), __float_as_uint(bo1[j].y));
     }
   }
   float* o = out + static_cast<size_t>(blockIdx.y) * M * RP;

@@ -803,7 +803,8 @@ __global__ void __launch_bounds__(OCC == 2 ? kPipeThreadsOcc2 : kPipeMaxThreads,
     if (bulk) put_tile_push(f, t, stg, tile_code_base, static_cast<uint32_t>(rows) * groups * 2, tid, ncompute);
   }
   if (bulk) put_drain(tid);  // thread 0: its bulk stores have landed before it fences and publishes below
-  if (PUT) fanout_publish_compute(f, gridDim.x, ncompute);  // compute threads only: the producer warp has exited
+  // (CF_PUBLISH_MODE=2: a separate one-warp kernel behind this one publishes)
+  if (PUT && f.publish_mode != 2) fanout_publish_compute(f, gridDim.x, ncompute);  // compute threads only: the producer warp has exited
 }
 
 }  // namespace cf

@@ -28,17 +28,27 @@ from .utils import COMPACT_COMPRESS_TYPE as T
 
 _ENGINE_TYPES = (T.WARMUP, T.BINARY, T.INT2)
 _engines: dict = {}
+_cfg_ok: dict = {}     # id(config) -> bool: the per-configuration half of `usable`, decided once
+_groups: dict = {}     # group key -> (world, rank)
 
 
 def enabled() -> bool:
     return os.environ.get("CF_DROPIN_ENGINE", "1") != "0"
 
 
+def _config_ok(cfg) -> bool:
+    ok = _cfg_ok.get(id(cfg))
+    if ok is None:
+        ok = bool(enabled() and cfg.fastpath and cfg.comp_rank == -1 and not cfg.log_compress_stats
+                  and not cfg.check_cache_consistency and not cfg.quantized_cache)
+        _cfg_ok.clear()
+        _cfg_ok[id(cfg)] = ok
+    return ok
+
+
 def usable(cfg, ctype, k: torch.Tensor) -> bool:
     """True if this call can run on an engine (see the module docstring for the conditions)."""
-    if not (enabled() and cfg.fastpath and cfg.comp_rank == -1 and ctype in _ENGINE_TYPES):
-        return False
-    if cfg.log_compress_stats or cfg.check_cache_consistency or cfg.quantized_cache:
+    if not _config_ok(cfg) or ctype not in _ENGINE_TYPES:
         return False
     c = k.shape[-2] * k.shape[-1]
     return k.is_cuda and k.dtype == torch.half and k.dim() == 4 and c % 128 == 0 and 64 <= c <= 8192
@@ -46,6 +56,16 @@ def usable(cfg, ctype, k: torch.Tensor) -> bool:
 
 def _group_key(group):
     return "world" if group is None else id(group)
+
+
+def group_info(group):
+    """(world size, rank) of `group`, looked up once (torch.distributed's accessors cost microseconds per call)."""
+    key = _group_key(group)
+    info = _groups.get(key)
+    if info is None:
+        info = (dist.get_world_size(group), dist.get_rank(group))
+        _groups[key] = info
+    return info
 
 
 def get(kind: str, group, k: torch.Tensor, mod_idx):
@@ -92,6 +112,8 @@ def shutdown():
         except Exception:  # noqa: BLE001 -- best effort at teardown
             pass
     _engines.clear()
+    _cfg_ok.clear()
+    _groups.clear()
 
 
 def engines():

@@ -444,9 +444,11 @@ class PatchGatherEngine:
                                            st["ticket"].data_ptr(), self.n, self.c, ws.data_ptr(), ws.numel(),
                                            nv.stream_ptr())
         nv.check(rc, "cf_sign_compress_put")
+        last = nv.PASS_FINALIZE if ctype == T.BINARY else nv.PASS_ENCODE
+        publish = 1 if (passes & last and os.environ.get("CF_PUBLISH_MODE", "2") == "2") else 0  # k_publish_flags
         if ctype == T.BINARY:
             passes &= ~nv.PASS_ENCODE
-        self.kernel_launches += bin(passes).count("1")
+        self.kernel_launches += bin(passes).count("1") + publish
 
     def gather(self, ctype, layer: int = 0):
         """Move this rank's [K payload | V payload] to every rank: NCCL all-gather, or one put

@@ -6,12 +6,22 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from .. import dropin
 from ..attention import attn_forward
 from ..prof import Profiler
 from .df_cache import DummyHandle
 from .df_utils import PatchConfig
 
 _buffers = {}
+_main = None
+
+
+def _plugin():
+    global _main
+    if _main is None:
+        from .. import main as m   # (main imports this package: resolved at first call)
+        _main = m
+    return _main
 
 
 @Profiler.prof_func("patch_gather_fwd.gather_patch_fwd")
@@ -19,7 +29,8 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
                      alibi_slopes=None, return_attn_probs=None, deterministic=False, attn_layer=None, group=None,
                      joint_tensor_key=None, joint_tensor_value=None, joint_strategy="none", mod_idx=None,
                      current_iter=None):
-    from ..main import allgather_cache, compact_all_gather, compact_config
+    m = _plugin()
+    compact_config, compact_all_gather, allgather_cache = m.compact_config, m.compact_all_gather, m.allgather_cache
     from ..ring import _joint_flags
 
     assert alibi_slopes is None, "Alibi slopes not supported in this basic gather impl."
@@ -31,14 +42,12 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
     assert current_iter is not None, "current_iter is required for async logic"
     is_joint = _joint_flags(joint_tensor_key, joint_tensor_value, joint_strategy, ["front", "rear", "none"])
 
-    world_size = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world_size, rank = dropin.group_info(group)
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
 
     key_to_use = value_to_use = None
     if config.use_compact:
         ctype = compact_config().compress_func(mod_idx, current_iter)
-        from .. import dropin
         if dropin.usable(compact_config(), ctype, k):
             # K and V of the layer through the persistent-buffer engine: one compress(+put) launch pair, one
             # reconstruct launch for all W origins, straight into the buffer attention reads (no cat for bs == 1)

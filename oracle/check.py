@@ -10,8 +10,10 @@ Checked here, per origin:
 
   * sign bits (BINARY) of the payload == (x - base >= 0) computed by the oracle: bit-exact
     (fastpath.py:58-72);
-  * U / V scale vectors of the payload within 1 fp16 ulp of the oracle's (mean reductions: fp32
-    summation order is the one freedom, SURVEY.md section 7 hard part 2);
+  * V (a mean over N) within 1 fp16 ulp of the oracle's, U within 2: mean reductions leave the fp32 summation
+    order free (SURVEY.md section 7 hard part 2), so a row mean and the token mean it is divided by can each
+    sit one fp16 step away from the oracle's, and their quotient U = rowmean / mean(rowmean)
+    (fastpath.py:164-165) two;
   * INT2 code bytes == the oracle's codes GIVEN the payload's scales: bit-exact (fastpath.py:529-549);
   * reconstruction == oracle dequant of THAT payload against THAT base: bit-exact
     (fastpath.py:328-363 / :672-741).
@@ -65,7 +67,7 @@ def check_origin(ctype: str, x: torch.Tensor | None, base: torch.Tensor, payload
             out["code_mismatch"] = int((g_codes != codes).sum())
             out["code_mismatch_end_to_end_frac"] = float((o_codes != codes).mean())
     out["ok"] = (bad == 0 and out["scales_finite"] and out.get("code_mismatch", 0) == 0
-                 and out.get("u_ulp", 0) <= 1 and out.get("v_ulp", 0) <= 1)
+                 and out.get("u_ulp", 0) <= 2 and out.get("v_ulp", 0) <= 1)
     return out
 
 
@@ -78,5 +80,7 @@ def check_exchange(ctype: str, xs, bases, payloads, recons) -> dict:
         "recon_mismatch": sum(p["recon_mismatch"] for p in per),
         "code_mismatch": sum(p.get("code_mismatch", 0) for p in per),
         "max_scale_ulp": max([max(p.get("u_ulp", 0), p.get("v_ulp", 0)) for p in per] or [0]),
+        "max_u_ulp": max([p.get("u_ulp", 0) for p in per] or [0]),
+        "max_v_ulp": max([p.get("v_ulp", 0) for p in per] or [0]),
         "elements": sum(p["n"] * p["c"] for p in per),
     }

@@ -205,11 +205,11 @@ def test_recorded_engine_schedules_pass_the_model_check(fake_cuda, monkeypatch, 
         assert streams == ({"main", "side1"} if schedule == "overlap" else {"main"}), streams
         if schedule == "overlap":
             assert all(e["stream"] == "side1" for e in applies) and all(e["stream"] == "main" for e in puts)
-            assert eng.kernel_launches == layers * 3  # stats + finalize (fused put) + reconstruct
+            assert eng.kernel_launches == layers * 4  # stats + finalize (fused put) + flag publication + reconstruct
         elif schedule == "serial_putkernel":
             assert eng.kernel_launches == layers * 4  # stats, finalize, put kernel, reconstruct
         else:
-            assert eng.kernel_launches == layers * (2 + (world if schedule == "ring" else 1))
+            assert eng.kernel_launches == layers * (3 + (world if schedule == "ring" else 1))  # + k_publish_flags
     _simulate_recorded(templates, world, layers)
 
 

@@ -95,7 +95,7 @@ for codec in (T.BINARY, T.INT2):
                 kk = [(k if r == rank else ring._shard(gk, r).view(bs, s, h, d)) for r in range(world)]
                 vv = [(v if r == rank else ring._shard(gv, r).view(bs, s, h, d)) for r in range(world)]
                 ref, ref_lse = attn_forward(q, torch.cat(kk, dim=1), torch.cat(vv, dim=1), 0.0, None, causal=False)
-                assert torch.allclose(out.float(), ref.float(), atol=3e-3), float((out.float() - ref.float()).abs().max())
+                assert torch.allclose(out.float(), ref.float(), atol=8e-3), float((out.float() - ref.float()).abs().max())  # 2 fp16 ulps at |out| ~ 4
                 assert torch.allclose(lse, ref_lse, atol=1e-3)
         assert not ring.p2p_error(), "a device-side flag wait timed out"
         if transport == "p2p":
@@ -103,7 +103,7 @@ for codec in (T.BINARY, T.INT2):
             ks = [shard(steps, l, 0, rank).to(dev) for l in range(layers)]
             vs = [shard(steps, l, 1, rank).to(dev) for l in range(layers)]
             g = ring.capture_step(ks, vs, codec, warmup_iters=0)
-            assert ring.launches_per_graph == layers * ((2 if codec == T.BINARY else 3) + world)
+            assert ring.launches_per_graph == layers * ((3 if codec == T.BINARY else 4) + world)  # + k_publish_flags
             g.replay()
             torch.cuda.synchronize()
             for l in range(layers):
