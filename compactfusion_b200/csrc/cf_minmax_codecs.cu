@@ -520,6 +520,12 @@ size_t minmax_codec_workspace_bytes(int64_t N, int64_t C) {
   return make_minmax_plan(N, C).total_bytes;
 }
 
+}  // namespace cf
+
+#include "cf_minmax_tma.cuh"
+
+namespace cf {
+
 static int grid_rows(const RowGeom& g, int64_t rows) {
   const int threads = g.TX * g.TY;
   const int ctas_per_sm = threads >= 512 ? 2 : (1024 / threads);
@@ -588,6 +594,26 @@ static int minmax_compress(const void* x, const void* base, void* new_base, void
   const __half* xh = static_cast<const __half*>(x);
   const __half* bh = static_cast<const __half*>(base);
   const int n = static_cast<int>(N), c = static_cast<int>(C);
+  if (MODE != MODE_INT8 && mm_tma_enabled()) {
+    // bulk-async pipelined path (cf_minmax_tma.cuh): statistics -> finalize -> encode, chained with PDL
+    const MmStatsPlan sp = make_mm_stats_plan(N, C, bh != nullptr);
+    const MmPipe cp = make_mm_pipe(C, bh != nullptr ? 2 : 1, 0);
+    if (sp.pipe.ok && cp.ok && static_cast<size_t>(sp.B) * C * 2 <= pl.part_bytes) {
+      int rc = bh ? launch_mm_stats_tma<true>(sp, xh, bh, pmin, pmax, n, c, st)
+                  : launch_mm_stats_tma<false>(sp, xh, bh, pmin, pmax, n, c, st);
+      if (rc) return rc;
+      CF_CHECK_CUDA(mm_launch(k_minmax_finalize_v8<MODE>, dim3((c + 63) / 64), dim3(256), 0, st, pmin, pmax, sp.B, c,
+                              static_cast<__half*>(scale), second, min_ws));
+      constexpr int L = MmLevels<MODE>::value;
+      rc = bh ? launch_int4_codec_tma<true, true, L>(cp, xh, bh, static_cast<const __half*>(scale),
+                                                     static_cast<const __half*>(second), static_cast<uint8_t*>(codes),
+                                                     static_cast<__half*>(new_base), n, c, st)
+              : launch_int4_codec_tma<true, false, L>(cp, xh, bh, static_cast<const __half*>(scale),
+                                                      static_cast<const __half*>(second), static_cast<uint8_t*>(codes),
+                                                      static_cast<__half*>(new_base), n, c, st);
+      return rc;
+    }
+  }
   dim3 block(pl.geom.TX, pl.geom.TY);
 #define CF_MM_STATS(GG)                                                                         \
   case GG:                                                                                      \
@@ -656,6 +682,18 @@ static int minmax_decompress(const void* codes, const void* scale, const void* s
   dim3 block(g.TX, g.TY);
   const int n = static_cast<int>(N), c = static_cast<int>(C);
   const __half* bh = static_cast<const __half*>(base);
+  if (MODE == MODE_INT4 && mm_tma_enabled() && aligned16(codes) && C % 16 == 0 && aligned2(scale) && aligned2(second)) {
+    const MmPipe dp = make_mm_pipe(C, bh != nullptr ? 1 : 0, static_cast<int>(C));
+    if (dp.ok && (bh != nullptr || dp.stage_bytes > 0)) {
+      uint8_t* pk = const_cast<uint8_t*>(static_cast<const uint8_t*>(codes));
+      return bh ? launch_int4_codec_tma<false, true, 15>(dp, nullptr, bh, static_cast<const __half*>(scale),
+                                                         static_cast<const __half*>(second), pk,
+                                                         static_cast<__half*>(recon), n, c, st)
+                : launch_int4_codec_tma<false, false, 15>(dp, nullptr, bh, static_cast<const __half*>(scale),
+                                                          static_cast<const __half*>(second), pk,
+                                                          static_cast<__half*>(recon), n, c, st);
+    }
+  }
   if (MODE == MODE_INT4) {
     dim3 grid(grid_rows(g, N / 2));
 #define CF_I4D(GG)                                                                              \

@@ -113,7 +113,7 @@ def test_int2_fastpath_vs_oracle(shape, update_cache, kernel_path):
 
 
 @pytest.mark.parametrize("shape", [(2048, 1024), (512, 4096), (1088, 3072), (130, 64), (64, 8192)])
-def test_int4_int8_bit_exact(shape):
+def test_int4_int8_bit_exact(shape, kernel_path):
     dev = _cuda()
     from compactfusion_b200.compress_quantize import (dequantize_int4, dequantize_int8, quantize_int4, quantize_int8,
                                                       sim_int4)
@@ -138,7 +138,7 @@ def test_int4_int8_bit_exact(shape):
     assert_bits_equal(dequantize_int8(q8, s8, z8), oc.int8_dequantize(oq8, os8, oz8), "int8 deq")
 
 
-def test_int4_int8_exact_quotient_edge_cases():
+def test_int4_int8_exact_quotient_edge_cases(kernel_path):
     """The encode kernels replace the per-element IEEE division by a reciprocal multiply plus an
     exactness check (csrc/cf_minmax_codecs.cu: quot_for_rn16).  Columns built to sit ON the rounding
     ties, with tiny / huge / zero scales and subnormal quotients must still give the oracle's codes."""
@@ -179,7 +179,7 @@ def test_int4_int8_exact_quotient_edge_cases():
     assert_bits_equal(dequantize_int8(q8, s8, z8), oc.int8_dequantize(oq8, os8, oz8), "int8 deq")
 
 
-def test_int4_error_feedback_round_trip_baseline_config():
+def test_int4_error_feedback_round_trip_baseline_config(kernel_path):
     """BASELINE config 0 at full size (4096 x 3072, INT4 residual + error feedback): the fused
     sender update equals what the receiver reconstructs from the wire bytes, codes match the
     oracle on a 256-column slice, and the EF residual stays bounded over the steps."""
@@ -205,7 +205,7 @@ def test_int4_error_feedback_round_trip_baseline_config():
     assert max(errs) < 0.02 and errs[-1] < 1.5 * errs[0] + 1e-3, errs
 
 
-def test_int4_fused_residual_matches_composition():
+def test_int4_fused_residual_matches_composition(kernel_path):
     """cf_int4_compress(x, base, new_base) == base + dequant(quant(x - base)) bit-exactly."""
     dev = _cuda()
     from compactfusion_b200 import _native as nv
@@ -249,7 +249,7 @@ def test_topk_ties_pick_lowest_index():
 
 
 @pytest.mark.parametrize("name", CODEC_CASES)
-def test_against_reference_goldens(golden_codecs, name):
+def test_against_reference_goldens(golden_codecs, name, kernel_path):
     """CUDA kernels on the committed inputs vs what the reference itself produced."""
     dev = _cuda()
     from compactfusion_b200.compress_quantize import (quantize_int2, quantize_int4, quantize_int8, sim_binary,
