@@ -78,7 +78,7 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--codec", default="binary", choices=["binary", "int2", "raw"],
+    p.add_argument("--codec", default="binary", choices=["binary", "int2", "raw", "lowrank8", "lowrank32", "lowrankq32"],
                    help="raw = the uncompressed exchange of the same K/V (NCCL all-gather of fp16 shards, what "
                         "xDiT does without the plugin): a comparison line, none of our kernels run")
     p.add_argument("--raw-exchange", default="allgather", choices=["allgather", "ring", "async"],
@@ -247,6 +247,9 @@ class CpuSample:
         g = torch.Generator().manual_seed(0)
         ref = _load_reference_main()
         self.kind = "reference" if ref else "port"
+        lowrank = codec.startswith("lowrank")
+        rank_r = int(codec.lstrip("lowrankq")) if lowrank else -1
+        value = ("low-rank-int4" if codec.startswith("lowrankq") else "low-rank") if lowrank else codec
         self.xs = []  # [version][tensor][rank]
         x0 = [[torch.randn(self.n, CH, generator=g) for _ in range(world)] for _ in range(sample_layers * 2)]
         for ver in range(2):
@@ -254,17 +257,17 @@ class CpuSample:
                              for x in per] for per in x0])
         if ref:
             cm, RT, RCfg = ref
-            self.cm, self.ct, self.warm = cm, RT(codec), RT.WARMUP
-            cm.compact_init(RCfg(enabled=True, residual=1, ef=True, simulate=True, comp_rank=-1,
-                                 compress_func=lambda l, s: RT(codec)))
+            self.cm, self.ct, self.warm = cm, RT(value), RT.WARMUP
+            cm.compact_init(RCfg(enabled=True, residual=1, ef=True, simulate=True, comp_rank=rank_r,
+                                 compress_func=lambda l, s: RT(value)))
             self._compress = lambda key, x: cm.compact_compress(key, x, self.ct, update_cache=False)
             self._decompress = lambda key, p, shape: cm.compact_decompress(key, p, self.ct, shape, update_cache=True)
             warm = lambda key, x: cm.compact_decompress(key, x, self.warm, x.shape, update_cache=True)  # noqa: E731
         else:
             from oracle.state import OracleCompact
-            oc = OracleCompact(residual=1, ef=True, fastpath=True)
-            self._compress = lambda key, x: oc.compress(key, x, codec, update_cache=False)
-            self._decompress = lambda key, p, shape: oc.decompress(key, p, codec, shape, update_cache=True)
+            oc = OracleCompact(residual=1, ef=True, fastpath=not lowrank, comp_rank=rank_r)
+            self._compress = lambda key, x: oc.compress(key, x, value, update_cache=False)
+            self._decompress = lambda key, p, shape: oc.decompress(key, p, value, shape, update_cache=True)
             warm = lambda key, x: oc.decompress(key, x, "warmup", x.shape, update_cache=True)  # noqa: E731
         # warm-up step: receiver q's base for every origin r
         for i, per in enumerate(self.xs[0]):
@@ -358,7 +361,7 @@ def note(rank, msg):
         print(f"[bench r{rank} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
-def p2p_probe(engine_cls, n_local, ctype, device):
+def p2p_probe(engine_cls, n_local, ctype, device, comp_rank=None):
     """N > 1: run a 2-layer WARMUP + compressed step over the one-sided transport and check that no
     device-side flag wait timed out, BEFORE the 57-layer engine is built on it.  A transport that does
     not deliver would otherwise spin ~2 s in every reconstruct launch of the timed region.  The verdict
@@ -366,7 +369,7 @@ def p2p_probe(engine_cls, n_local, ctype, device):
     from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
     ok, why = 1, ""
     try:
-        probe = engine_cls(2, n_local, CH, group=None, device=device, transport="auto")
+        probe = engine_cls(2, n_local, CH, group=None, device=device, transport="auto", comp_rank=comp_rank)
         if probe.prepare(ctype) != "p2p":
             ok, why = 0, "p2p setup failed (CUDA IPC)"
         else:
@@ -378,6 +381,8 @@ def p2p_probe(engine_cls, n_local, ctype, device):
             torch.cuda.synchronize()
             if probe.p2p_error():
                 ok, why = 0, "a device-side flag wait timed out in the probe step"
+            dist.barrier()
+            probe.close()  # unmap the probe's regions (cf_ipc_close / cf_ipc_free)
     except Exception as e:  # noqa: BLE001 -- any failure means: do not use this transport
         ok, why = 0, f"{type(e).__name__}: {e}"
     t = torch.tensor([ok], device=device)
@@ -782,6 +787,52 @@ class DropinDriver:
         self.it += 1
 
 
+def dropin_requested(args):
+    return args.api == "dropin"
+
+
+def measure_lowrank(args, eng, ks, vs, ctype, world, layers, barrier):
+    """Low-rank codecs: the two phases of a layer timed over all layers (eager launches, CUDA events): project
+    (+ int4 of the factors, + put) and reconstruct.  Algorithmic bytes of the projector: delta must be streamed 4
+    times at least (2 iterations, U, V: SURVEY.md section 8d) from x and base, 4 x 4E, plus the payload."""
+    e = eng.n * CH
+    vsel = 2
+
+    def timed(fn, reps=2):
+        barrier()
+        for l in range(layers):
+            fn(l)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            for l in range(layers):
+                fn(l)
+        b.record()
+        barrier()
+        return a.elapsed_time(b) * 1e3 / (reps * layers)
+
+    payload = eng._numel(ctype) * 2
+    us_c = timed(lambda l: eng.send(l, ks[vsel][l], vs[vsel][l], ctype))
+    us_d = timed(lambda l: eng.decompress(l, ctype))
+    kernels = [
+        {"kernel": "cf_lowrank_project (+ int4 of U, V^T) x {K, V}", "avg_launch_us": us_c,
+         "algorithmic_bytes_per_launch": 2 * (16 * e + payload), "achieved": 2 * (16 * e + payload) / us_c / 1e3},
+        {"kernel": "cf_lowrank_reconstruct x {K, V} x origins", "avg_launch_us": us_d,
+         "algorithmic_bytes_per_launch": 2 * world * (4 * e + payload), "achieved": 2 * world * (4 * e + payload) / us_d / 1e3},
+    ]
+    peak, peak_src = measured_hbm_peak()
+    tot = us_c + us_d
+    for k in kernels:
+        k["frac"] = k["achieved"] / peak
+        k["share_of_kernel_time"] = k["avg_launch_us"] / tot
+    dom = max(kernels, key=lambda k: k["share_of_kernel_time"])
+    return {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+            "kernel": dom["kernel"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+            "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_kernel_time"], "peak_source": peak_src,
+            "kernels": kernels, "method": "each phase of a layer (several launches) over all layers, eager, CUDA events"}
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -817,7 +868,15 @@ def main():
     from compactfusion_b200.engine import PatchGatherEngine, RingExchangeEngine
     from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
     raw = args.codec == "raw"
-    ctype = {"binary": T.BINARY, "int2": T.INT2, "raw": T.WARMUP}[args.codec]
+    lowrank = args.codec.startswith("lowrank")
+    comp_rank = int(args.codec.lstrip("lowrankq")) if lowrank else None
+    ctype = (T.LOW_RANK_Q if args.codec.startswith("lowrankq") else T.LOW_RANK) if lowrank else \
+        {"binary": T.BINARY, "int2": T.INT2, "raw": T.WARMUP}[args.codec]
+    if lowrank:
+        # the projector draws its random start and allocates per call (like subspace_iter, compress_lowrank.py:41):
+        # eager launches; the oracle leg is bit-exactness of the sign codecs, not applicable to a random subspace
+        args.no_graph, args.no_parity = True, True
+        assert not dropin_requested(args), "--api dropin with a low-rank codec: use the engine line"
     n_local, layers = SEQ // world, args.layers
     # ring workloads consume the origins hop by hop (one flag-waiting decompress launch per origin);
     # patch workloads reconstruct all origins in one launch
@@ -826,7 +885,7 @@ def main():
     dropin_api = args.api == "dropin"
     assert not (dropin_api and raw), "--api dropin drives the compressed hooks; use --api engine for --codec raw"
     if world > 1 and args.transport == "auto" and not raw and not dropin_api:
-        ok, why = p2p_probe(engine_cls, n_local, ctype, device)
+        ok, why = p2p_probe(engine_cls, n_local, ctype, device, comp_rank)
         if not ok:
             args.transport, probe_note = "nccl", "one-sided transport rejected by the probe step: " + (why or "a peer failed")
         note(rank, f"p2p probe: {'ok' if ok else probe_note}")
@@ -836,7 +895,8 @@ def main():
         driver = DropinDriver(ctype, layers, n_local, device, args.transport)
         args.no_graph, eng, transport = True, None, "pending"
     else:
-        eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport, inputs_stable=True)
+        eng = engine_cls(layers, n_local, CH, group=None, device=device, transport=args.transport, inputs_stable=True,
+                         comp_rank=comp_rank)
         transport = eng.prepare(ctype) if world > 1 else "none (single GPU)"
     if raw and world > 1:
         transport = "nccl"  # all_gather_into_tensor of the raw fp16 shards (engine.warmup)
@@ -943,13 +1003,17 @@ def main():
         except Exception as e:  # noqa: BLE001 -- reported, and parity_ok goes false
             parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
     note(rank, "fidelity / identity / oracle parity done")
-    roofline = None if raw else measure_kernels(args, eng, ks, vs, ctype, world, rank, n_local, layers, transport,
-                                                barrier)
+    if raw:
+        roofline = None
+    elif lowrank:
+        roofline = measure_lowrank(args, eng, ks, vs, ctype, world, layers, barrier)
+    else:
+        roofline = measure_kernels(args, eng, ks, vs, ctype, world, rank, n_local, layers, transport, barrier)
     e2e = None if args.no_e2e else measure_e2e(args, eng, acts[0][0][0], ctype, world, n_local, layers, device,
                                                transport, barrier)
     note(rank, "e2e done")
     gpu_ref = None
-    if world == 1 and not raw and not args.no_gpu_reference:
+    if world == 1 and not raw and not lowrank and not args.no_gpu_reference:
         try:
             gpu_ref = gpu_reference(args, ks, vs, pattern, layers, n_local, device)
         except Exception as e:  # noqa: BLE001 -- a side figure: report why it is missing

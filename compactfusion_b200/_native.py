@@ -51,6 +51,7 @@ SYMBOLS = {
     "cf_ipc_close": (c_int, [c_void_p]),
     "cf_ipc_free": (c_int, [c_void_p]),
     "cf_p2p_put": (c_int, [c_void_p, c_size_t, c_int, _VPP, _VPP, c_void_p, c_void_p, c_void_p]),
+    "cf_p2p_wait": (c_int, [c_int, _VPP, c_void_p, c_void_p, c_void_p]),
     "cf_sign_compress_put": (c_int, [c_int, c_int, c_int, _VPP, _VPP, c_int, c_int, _VPP, _VPP, c_void_p, c_void_p, c_int64, c_int64,
                                      c_void_p, c_size_t, c_void_p]),
     "cf_sign_decompress_batched_wait": (c_int, [c_int, c_int] + [_VPP] * 6 + [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),

@@ -466,13 +466,16 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   k_lr_pad_split<<<small_grid, 256, 0, st>>>(q0, Q2, c, r, RP);
   CF_CHECK_LAUNCH();
 
+  // 16 warps per CTA when there are >= 2 column tiles to split between two warp groups (CF_LR_WARPS=8: round 1's 8)
+  static const bool wide = [] { const char* e = getenv("CF_LR_WARPS"); return !(e && e[0] == '8'); }();
+  const int gemm_threads = (RP >= 16 && wide) ? 2 * kLrThreads : kLrThreads;
   auto gemm_AQ = [&]() {  // part[s] (N, RP) = A Q
     dim3 grid((n + kLrBM - 1) / kLrBM, p.aq_splits);
-    k_lr_gemm<RP, false><<<grid, kLrThreads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
+    k_lr_gemm<RP, false><<<grid, gemm_threads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
   };
   auto gemm_AtY = [&]() {  // part[s] (C, RP) = A^T Y
     dim3 grid((c + kLrBM - 1) / kLrBM, p.aty_splits);
-    k_lr_gemm<RP, true><<<grid, kLrThreads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
+    k_lr_gemm<RP, true><<<grid, gemm_threads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
   };
   // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies).
   // One launch on one 8-CTA cluster (k_lr_orth); CF_LR_ORTH=legacy keeps round 1's five-launch chain (A/B).
@@ -661,6 +664,18 @@ int cf_lowrank_reconstruct(const void* U, const void* V, const void* base, void*
       const __half* b = static_cast<const __half*>(base);
       __half* o = static_cast<__half*>(recon);
       const int n = static_cast<int>(N), c = static_cast<int>(C);
+      static const bool v2 = [] { const char* e2 = getenv("CF_LR_RECON"); return !(e2 && e2[0] == '1'); }();
+      if (v2 && rank % 8 == 0 && aligned16(U)) {  // prefetching version (CF_LR_RECON=1: round 1's kernel, A/B)
+        dim3 g2(static_cast<unsigned>((C + 127) / 128), static_cast<unsigned>((N + 63) / 64));
+        switch ((rank + 15) / 16) {
+          case 1: k_lr_reconstruct_v2<1><<<g2, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+          case 2: k_lr_reconstruct_v2<2><<<g2, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+          case 3: k_lr_reconstruct_v2<3><<<g2, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+          default: k_lr_reconstruct_v2<4><<<g2, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
+        }
+        CF_CHECK_LAUNCH();
+        return CF_OK;
+      }
       switch ((rank + 15) / 16) {
         case 1: k_lr_reconstruct_mma<1><<<mgrid, 128, 0, st>>>(u, v, b, o, n, c, rank); break;
         case 2: k_lr_reconstruct_mma<2><<<mgrid, 128, 0, st>>>(u, v, b, o, n, c, rank); break;

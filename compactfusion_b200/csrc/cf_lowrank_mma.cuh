@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_lr_pad_split(const float* __restrict__ 
 // B2 = B pre-split into {hi, lo} TF32 pairs, (K, RP) row-major.   grid (ceil(M/128), splits), block 256
 // ---------------------------------------------------------------------------------------
 template <int RP, bool TRANS>
-__global__ void __launch_bounds__(kLrThreads) k_lr_gemm(const __half* __restrict__ x, const __half* __restrict__ base,
+__global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __restrict__ x, const __half* __restrict__ base,
                                                 const float2* __restrict__ B2, float* __restrict__ out, int N, int C,
                                                 int k_per_split) {
   extern __shared__ __align__(128) unsigned char lr_smem_raw[];
@@ -102,7 +102,14 @@ __global__ void __launch_bounds__(kLrThreads) k_lr_gemm(const __half* __restrict
   const int m0 = blockIdx.x * kLrBM;
   const int k_begin = blockIdx.y * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // 8 warps cover the 128 rows of the tile; a block of 16 warps (RP >= 16) splits the RP / 8 column tiles between
+  // two warp groups: twice the warps to hide the ldmatrix -> convert -> MMA latency chain, half the B fragment
+  // loads per warp (ncu, round 2: 12 % warps active, stalls on fixed-latency dependencies)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nthreads = blockDim.x;
+  const int warp = (tid >> 5) & 7, warp_n = tid >> 8;
+  const int j_begin = (nthreads > kLrThreads) ? warp_n * (RP / 16) : 0;
+  const int j_end = (nthreads > kLrThreads) ? j_begin + RP / 16 : RP / 8;
   const int g = lane >> 2, t = lane & 3;
   const bool has_base = base != nullptr;
 
@@ -113,9 +120,7 @@ __global__ void __launch_bounds__(kLrThreads) k_lr_gemm(const __half* __restrict
     __half* bs = reinterpret_cast<__half*>(sp + kTileA);
     float2* Bs = reinterpret_cast<float2*>(sp + 2 * kTileA);
     constexpr int kChunkCols = kColsA / 8;
-#pragma unroll
-    for (int i = 0; i < kRowsA * kChunkCols / kLrThreads; ++i) {  // 16-byte chunks of the fp16 tile
-      const int ch = tid + i * kLrThreads;
+    for (int ch = tid; ch < kRowsA * kChunkCols; ch += nthreads) {  // 16-byte chunks of the fp16 tile
       const int r = ch / kChunkCols, cc = ch % kChunkCols;
       const int grow = TRANS ? (k0 + r) : (m0 + r);
       const int gcol = TRANS ? (m0 + 8 * cc) : (k0 + 8 * cc);
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(kLrThreads) k_lr_gemm(const __half* __restrict
       if (has_base) cp_async16(bs + r * kLdA + 8 * cc, base + off, ok);
     }
     constexpr int kChunksB = kLrBK * RP / 2;  // 16-byte chunks = 2 float2
-    for (int ch = tid; ch < kChunksB; ch += kLrThreads) {
+    for (int ch = tid; ch < kChunksB; ch += nthreads) {
       const int r = ch / (RP / 2), cc = ch % (RP / 2);
       const bool ok = k0 + r < k_end;
       const size_t off = ok ? (static_cast<size_t>(k0 + r) * RP + 2 * cc) : 0;
@@ -188,25 +193,31 @@ __global__ void __launch_bounds__(kLrThreads) k_lr_gemm(const __half* __restrict
       float2 be0[RP / 8], be1[RP / 8], bo0[RP / 8], bo1[RP / 8];
 #pragma unroll
       for (int j = 0; j < RP / 8; ++j) {
+        if (j < j_begin || j >= j_end) continue;   // warp-uniform: the other warp group's column tiles
         be0[j] = brow[8 * j];
         be1[j] = brow[8 * kLdB + 8 * j];
         bo0[j] = brow[kLdB + 8 * j];
         bo1[j] = brow[9 * kLdB + 8 * j];
       }
 #pragma unroll
-      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_even, __float_as_uint(be0[j].x), __float_as_uint(be1[j].x));
+      for (int j = 0; j < RP / 8; ++j)
+        if (j >= j_begin && j < j_end) mma_tf32(acc[j], a_even, __float_as_uint(be0[j].x), __float_as_uint(be1[j].x));
 #pragma unroll
-      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_even, __float_as_uint(be0[j].y), __float_as_uint(be1[j].y));
+      for (int j = 0; j < RP / 8; ++j)
+        if (j >= j_begin && j < j_end) mma_tf32(acc[j], a_even, __float_as_uint(be0[j].y), __float_as_uint(be1[j].y));
 #pragma unroll
-      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].x), __float_as_uint(bo1[j].x));
+      for (int j = 0; j < RP / 8; ++j)
+        if (j >= j_begin && j < j_end) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].x), __float_as_uint(bo1[j].x));
 #pragma unroll
-      for (int j = 0; j < RP / 8; ++j) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].y), __float_as_uint(bo1[j].y));
+      for (int j = 0; j < RP / 8; ++j)
+        if (j >= j_begin && j < j_end) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].y), __float_as_uint(bo1[j].y));
     }
   }
   float* o = out + static_cast<size_t>(blockIdx.y) * M * RP;
   const int r0 = m0 + 16 * warp + g;
 #pragma unroll
   for (int j = 0; j < RP / 8; ++j) {
+    if (j < j_begin || j >= j_end) continue;
     const int col = 8 * j + 2 * t;
     if (r0 < M) *reinterpret_cast<float2*>(o + static_cast<size_t>(r0) * RP + col) = make_float2(acc[j][0], acc[j][1]);
     if (r0 + 8 < M)

@@ -71,9 +71,58 @@ __global__ void __launch_bounds__(256) k_p2p_put(const PutParams p) {
   }
 }
 
+// Stand-alone flag wait for consumers that do not wait inside their own kernel (the low-rank reconstruct):
+// one warp, lane i polls flag i until it reaches *expected (relaxed polls, then one acquire load), ~2 s bound.
+// Kernels launched behind it on the stream (programmatic dependent launch: their griddepcontrol.wait, or plain
+// stream order) then read payloads that have fully landed.
+struct WaitParams {
+  const uint32_t* flag[CF_MAX_PEERS];
+  const uint32_t* expected;
+  uint32_t* error;
+  int n;
+};
+__global__ void __launch_bounds__(32) k_p2p_wait(const WaitParams p) {
+  pdl_wait();   // *expected is written by this rank's own put, earlier on the stream
+  const int lane = threadIdx.x;
+  if (lane < p.n) {
+    uint32_t want, cur;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(want) : "l"(p.expected) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(p.flag[lane]) : "memory");
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(cur - want) < 0) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(p.error, 1u);
+        break;
+      }
+      __nanosleep(32);
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(p.flag[lane]) : "memory");
+    }
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(p.flag[lane]) : "memory");
+  }
+  __syncwarp();
+  __threadfence();
+  pdl_launch_dependents();
+}
+
 }  // namespace cf
 
 extern "C" {
+
+int cf_p2p_wait(int n, const void* const* flags, const void* expected, void* error_word, cf_stream_t stream) {
+  CF_CHECK_ARG(flags && expected && error_word, "null pointer");
+  CF_CHECK_ARG(n >= 1 && n <= CF_MAX_PEERS, "n %d out of range [1,%d]", n, CF_MAX_PEERS);
+  cf::WaitParams p{};
+  p.n = n;
+  p.expected = static_cast<const uint32_t*>(expected);
+  p.error = static_cast<uint32_t*>(error_word);
+  for (int i = 0; i < n; ++i) {
+    CF_CHECK_ARG(flags[i] != nullptr, "flag %d is null", i);
+    p.flag[i] = static_cast<const uint32_t*>(flags[i]);
+  }
+  cf::k_p2p_wait<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
 
 int cf_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64) {
   CF_CHECK_ARG(dev_ptr != nullptr && handle64 != nullptr && bytes > 0, "bad arguments");

@@ -27,6 +27,7 @@ import torch.distributed as dist
 from .utils import COMPACT_COMPRESS_TYPE as T
 
 _ENGINE_TYPES = (T.WARMUP, T.BINARY, T.INT2)
+_LOWRANK_TYPES = (T.WARMUP, T.LOW_RANK, T.LOW_RANK_Q)
 _engines: dict = {}
 _cfg_ok: dict = {}     # id(config) -> bool: the per-configuration half of `usable`, decided once
 _groups: dict = {}     # group key -> (world, rank)
@@ -36,11 +37,19 @@ def enabled() -> bool:
     return os.environ.get("CF_DROPIN_ENGINE", "1") != "0"
 
 
-def _config_ok(cfg) -> bool:
-    ok = _cfg_ok.get(id(cfg))
-    if ok is None:
-        ok = bool(enabled() and cfg.fastpath and cfg.comp_rank == -1 and not cfg.log_compress_stats
-                  and not cfg.check_cache_consistency and not cfg.quantized_cache)
+def _config_ok(cfg):
+    """None, or the tuple of compress types an engine serves under this configuration: the fastpath presets
+    (BINARY / INT2, comp_rank -1) and the low-rank presets (LOW_RANK / LOW_RANK_Q with residual 1 + error
+    feedback and a real rank: CogVideoX's `lowrankq32`, examples/configs.py:87-97)."""
+    ok = _cfg_ok.get(id(cfg), 0)
+    if ok == 0:
+        ok = None
+        plain = enabled() and not (cfg.log_compress_stats or cfg.check_cache_consistency or cfg.quantized_cache)
+        if plain and cfg.fastpath and cfg.comp_rank == -1:
+            ok = _ENGINE_TYPES
+        elif (plain and not cfg.fastpath and not cfg.simulate_compress and cfg.compress_residual == 1
+              and cfg.error_feedback and isinstance(cfg.comp_rank, int) and 1 <= cfg.comp_rank <= 64):
+            ok = _LOWRANK_TYPES
         _cfg_ok.clear()
         _cfg_ok[id(cfg)] = ok
     return ok
@@ -48,8 +57,11 @@ def _config_ok(cfg) -> bool:
 
 def usable(cfg, ctype, k: torch.Tensor) -> bool:
     """True if this call can run on an engine (see the module docstring for the conditions)."""
-    if not _config_ok(cfg) or ctype not in _ENGINE_TYPES:
+    types = _config_ok(cfg)
+    if types is None or ctype not in types:
         return False
+    if types is _LOWRANK_TYPES and (k.shape[0] * k.shape[1]) % 2:
+        return False   # LOW_RANK_Q packs row pairs
     c = k.shape[-2] * k.shape[-1]
     return k.is_cuda and k.dtype == torch.half and k.dim() == 4 and c % 128 == 0 and 64 <= c <= 8192
 
@@ -68,7 +80,7 @@ def group_info(group):
     return info
 
 
-def get(kind: str, group, k: torch.Tensor, mod_idx):
+def get(kind: str, group, k: torch.Tensor, mod_idx, comp_rank=None):
     """(engine, dense layer index) for this hook / group / shard shape; `mod_idx` (any hashable the caller uses
     to name the layer) is mapped to the engine's own 0-based index in order of first appearance."""
     from .engine import PatchGatherEngine, RingExchangeEngine
@@ -78,7 +90,8 @@ def get(kind: str, group, k: torch.Tensor, mod_idx):
     if ent is None:
         cls = RingExchangeEngine if kind == "ring" else PatchGatherEngine
         transport = os.environ.get("CF_DROPIN_TRANSPORT", "auto")
-        ent = (cls(0, n, c, group=group, device=k.device, transport=transport), {})
+        ent = (cls(0, n, c, group=group, device=k.device, transport=transport,
+                   comp_rank=comp_rank if (isinstance(comp_rank, int) and comp_rank > 0) else None), {})
         _engines[key] = ent
     eng, index = ent
     layer = index.get(mod_idx)

@@ -36,6 +36,7 @@ from . import _native as nv
 from .utils import COMPACT_COMPRESS_TYPE as T
 
 _CODEC = {T.BINARY: nv.CODEC_BINARY, T.INT2: nv.CODEC_INT2}
+_LOWRANK = (T.LOW_RANK, T.LOW_RANK_Q)   # slowpath payloads the engines also carry (slowpath.py:54-75, :152-164)
 
 
 class _DevicePtr:
@@ -119,8 +120,10 @@ class PatchGatherEngine:
     """
 
     def __init__(self, layers: int, n_local: int, c: int, group=None, device=None, transport: str = "nccl",
-                 inputs_stable: bool = False, local_world: "LocalWorld | None" = None, rank: int | None = None):
+                 inputs_stable: bool = False, local_world: "LocalWorld | None" = None, rank: int | None = None,
+                 comp_rank: int | None = None):
         self.layers, self.n, self.c = layers, n_local, c
+        self.comp_rank = comp_rank  # rank r of the LOW_RANK / LOW_RANK_Q payloads (CompactConfig.comp_rank)
         self.group = group
         self._local = local_world
         if local_world is not None:  # virtual ranks of one process (LocalWorld): no process group
@@ -187,7 +190,7 @@ class PatchGatherEngine:
 
     def prepare(self, ctype) -> str:
         """Set up the transport for `ctype` now (collective call); returns the transport in use."""
-        if self.transport == "p2p" and ctype in _CODEC:
+        if self.transport == "p2p" and (ctype in _CODEC or ctype in _LOWRANK):
             self._p2p_region(ctype)
         return self.transport
 
@@ -292,6 +295,14 @@ class PatchGatherEngine:
 
     # -- buffers ---------------------------------------------------------------------------
     def _numel(self, ctype):
+        """fp16 elements of one tensor's wire payload."""
+        if ctype in _LOWRANK:
+            r = self.comp_rank
+            assert r is not None and 1 <= r <= 64, "LOW_RANK payloads need comp_rank in [1, 64]"
+            if ctype == T.LOW_RANK:
+                return r * (self.n + self.c)                      # [U (N,r) | V (r,C)]
+            assert self.n % 2 == 0 and self.c % 2 == 0, "LOW_RANK_Q packs row pairs of U and of V^T"
+            return r * (self.n + self.c) // 4 + 4 * r             # [qU, sU, mU, qV^T, sV, mV]
         per_byte = 8 if ctype == T.BINARY else 4
         return self.n * (self.c // per_byte) // 2 + self.n + self.c
 
@@ -477,6 +488,8 @@ class PatchGatherEngine:
     def decompress(self, layer, ctype, origins=None):
         """Origins x {K, V} (default: all W): recon = base + dequant, in place in the global buffers.
         With the one-sided transport the kernel first waits for the flags of exactly these origins."""
+        if ctype in _LOWRANK:
+            return self._lowrank_decompress(layer, ctype, origins)
         st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
         if st:
             expected = st["count"][layer:layer + 1].data_ptr()
@@ -493,10 +506,68 @@ class PatchGatherEngine:
             nv.check(rc, "cf_sign_decompress_batched_wait")
             self.kernel_launches += 1
 
+    # -- LOW_RANK / LOW_RANK_Q payloads (the CogVideoX preset, examples/configs.py:87-97) ---------------------
+    def _lowrank_compress(self, layer, k, v, ctype):
+        """K and V -> [U | V] (LOW_RANK) or [qU, sU, mU, qV^T, sV, mV] (LOW_RANK_Q: int4 per column of U and of
+        V^T, slowpath.py:62-75) in the send buffer; the projector subtracts the cached base on the fly."""
+        from .compress_lowrank import lowrank_project
+        from .compress_quantize import quantize_int4
+        n, c, r = self.n, self.c, self.comp_rank
+        send, _ = self._buffers(ctype, layer)
+        for j, (x, glob) in enumerate(((k, self.global_k[layer]), (v, self.global_v[layer]))):
+            x2, base, payload = x.reshape(n, c), self._shard(glob, self.rank), send[j]
+            if ctype == T.LOW_RANK:
+                lowrank_project(x2, base, r, 2, u_out=payload[:n * r].view(n, r), v_out=payload[n * r:].view(r, c))
+            else:
+                u, vv, _ = lowrank_project(x2, base, r, 2)
+                parts = list(quantize_int4(u)) + list(quantize_int4(vv.t().contiguous()))
+                off = 0
+                for p_ in parts:
+                    flat = p_.contiguous().view(torch.half).reshape(-1) if p_.dtype != torch.half else p_.reshape(-1)
+                    payload[off:off + flat.numel()].copy_(flat)
+                    off += flat.numel()
+            self.kernel_launches += 1
+
+    def _lowrank_payload(self, layer, origin, ctype, kv):
+        """fp16 view of the payload tensor `kv` that `origin` delivered for `layer`."""
+        return self.slot_bytes(layer, origin, ctype, kv).view(torch.half)
+
+    def _lowrank_decompress(self, layer, ctype, origins=None):
+        """recon = base + U V for the given origins, in place in the global buffers; with the one-sided transport a
+        one-warp kernel (cf_p2p_wait) first holds the stream until those origins' flags are up."""
+        from .compress_lowrank import lowrank_reconstruct
+        from .compress_quantize import dequantize_int4
+        origins = tuple(range(self.world)) if origins is None else tuple(origins)
+        n, c, r = self.n, self.c, self.comp_rank
+        st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
+        if st:
+            flags = (ctypes.c_void_p * len(origins))(*[self._flag(st, st["base"], layer, o) for o in origins])
+            rc = nv.lib().cf_p2p_wait(len(origins), flags, st["count"][layer:layer + 1].data_ptr(),
+                                      st["error"].data_ptr(), nv.stream_ptr())
+            nv.check(rc, "cf_p2p_wait")
+            self.kernel_launches += 1
+        for o in origins:
+            for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
+                payload, shard = self._lowrank_payload(layer, o, ctype, j), self._shard(glob, o)
+                if ctype == T.LOW_RANK:
+                    u, vv = payload[:n * r].view(n, r), payload[n * r:].view(r, c)
+                else:
+                    sizes = [n * r // 4, r, r, c * r // 4, r, r]
+                    qu, su, mu, qv, sv, mv = torch.split(payload, sizes)
+                    u8 = lambda t_, rows: t_.contiguous().view(torch.uint8).view(rows, r)  # noqa: E731
+                    u = dequantize_int4(u8(qu, n // 2), su.view(1, r), mu.view(1, r))
+                    vv = dequantize_int4(u8(qv, c // 2), sv.view(1, r), mv.view(1, r)).t().contiguous()
+                lowrank_reconstruct(u, vv, base=shard, out=shard)
+                self.kernel_launches += 1
+
     def send(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
         """Sender side of one layer: compress this rank's K and V and deliver the payloads to every rank."""
-        assert ctype in _CODEC, f"engine supports the fastpath codecs, got {ctype}"
+        assert ctype in _CODEC or ctype in _LOWRANK, f"engine supports BINARY / INT2 / LOW_RANK / LOW_RANK_Q, got {ctype}"
         self.freeze()
+        if ctype in _LOWRANK:
+            self._lowrank_compress(layer, k, v, ctype)
+            self.gather(ctype, layer)
+            return
         if self.fused(ctype):
             self.compress_put(layer, k, v, ctype)
         else:

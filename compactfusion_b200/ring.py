@@ -112,7 +112,7 @@ def _compact_ring_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, win
             and tuple(window_size) == (-1, -1)):
         # the ring on the persistent-buffer engine: the payload goes to every rank's slot at once, hop s consumes
         # origin (rank - s) mod W with one flag-waiting launch for K and V, the LSE merge is one fused kernel
-        eng, layer = dropin.get("ring", group, k, mod_idx)
+        eng, layer = dropin.get("ring", group, k, mod_idx, compact_config().comp_rank)
         out, lse = eng.ring_forward(layer, q, k, v, ctype, softmax_scale, joint_tensor_key, joint_tensor_value,
                                     joint_strategy)
         return out, lse, None

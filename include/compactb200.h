@@ -214,6 +214,13 @@ CF_API int cf_ipc_close(void* peer_ptr);
 CF_API int cf_ipc_free(void* dev_ptr);
 CF_API int cf_p2p_put(const void* src, size_t bytes, int n_peers, void* const* peer_dst,
                void* const* peer_flag, void* local_count, void* local_ticket, cf_stream_t stream);
+/* cf_p2p_wait: block the STREAM (one warp on the device, no host involvement) until *flags[i] >= *expected for
+ * i < n -- the counters cf_p2p_put / cf_sign_compress_put publish -- for consumers that do not wait inside their
+ * own kernel (the low-rank reconstruct; the BINARY / INT2 reconstruct waits itself,
+ * cf_sign_decompress_batched_wait).  A wait beyond ~2 s sets *error_word = 1 and lets the stream go on.
+ * Replaces the completion wait of the ring's batch_isend_irecv (ring.py:268-269) / of dist.all_gather. */
+CF_API int cf_p2p_wait(int n, const void* const* flags, const void* expected, void* error_word,
+                cf_stream_t stream);
 /* Fused compress + put: cf_sign_compress_passes (no cache update) whose kernels store the payload of
  * tensor t -- [codes | U (N) | V (C)], the App-A wire layout -- straight into `n_dst` receive slots
  * instead of a local send buffer: dst_payload is a HOST array of batch * n_dst device pointers, entry

@@ -461,3 +461,61 @@ def test_virtual_ranks_graph_and_publish_modes(monkeypatch):
     for mode, graph in ((1, False), (0, True)):
         for a, b in zip(run(mode, graph), ref):
             assert torch.equal(a, b), (mode, graph)
+
+
+@pytest.mark.parametrize("codec,rank", [("low-rank", 8), ("low-rank-int4", 32), ("low-rank", 32)])
+@pytest.mark.parametrize("world", [1, 2])
+def test_engine_carries_lowrank_payloads(codec, rank, world):
+    """LOW_RANK / LOW_RANK_Q (CogVideoX's preset, examples/configs.py:87-97) through the engines: payload sizes
+    are the reference's wire formats (slowpath.py:62-75), all (virtual) ranks hold bit-identical caches after every
+    step, and the error-feedback reconstruction tracks the input as well as the per-call plugin path does
+    (the random start of the projector differs per call, so the comparison is on quality, not bits)."""
+    dev = _cuda()
+    import compactfusion_b200 as cf
+    from compactfusion_b200.engine import LocalWorld, PatchGatherEngine
+    T = cf.COMPACT_COMPRESS_TYPE
+    ctype, n, c, layers, steps = T(codec), 288, 1536, 2, 4
+    g = torch.Generator().manual_seed(rank)
+    # low-rank-plus-noise residuals, so that a rank-r code has something to find
+    def series(seed):
+        gg = torch.Generator().manual_seed(seed)
+        x0 = torch.randn(n, c, generator=gg)
+        out = [x0.half()]
+        for _ in range(steps - 1):
+            x0 = x0 + torch.randn(n, 6, generator=gg) @ torch.randn(6, c, generator=gg) * 0.05 + 0.01 * torch.randn(n, c, generator=gg)
+            out.append(x0.half())
+        return out
+    data = [[[series(100 * l + 10 * j + r) for r in range(world)] for j in range(2)] for l in range(layers)]
+    if world == 1:
+        engines = [PatchGatherEngine(layers, n, c, device=dev, comp_rank=rank)]
+        run = lambda l, ks, vs, ct: [engines[0].exchange(l, ks[0], vs[0], ct)]  # noqa: E731
+    else:
+        lw = LocalWorld(world, layers, n, c, device=dev, comp_rank=rank)
+        engines, run = lw.engines, lw.exchange_all
+    want_numel = rank * (n + c) if ctype == T.LOW_RANK else rank * (n + c) // 4 + 4 * rank
+    assert engines[0]._numel(ctype) == want_numel
+    # the per-call plugin path on the same inputs (rank 0's K of layer 0)
+    cf.compact_init(cf.CompactConfig(enabled=True, compress_func=lambda l, s: ctype if s >= 1 else T.WARMUP,
+                                     comp_rank=rank, residual=1, ef=True))
+    for t in range(steps):
+        ct = ctype if t >= 1 else T.WARMUP
+        for l in range(layers):
+            ks = [data[l][0][r][t].to(dev) for r in range(world)]
+            vs = [data[l][1][r][t].to(dev) for r in range(world)]
+            before = engines[0].global_k[l].clone()
+            run(l, ks, vs, ct)
+            torch.cuda.synchronize()
+            for e in engines[1:]:
+                assert torch.equal(e.global_k[l], engines[0].global_k[l]) and torch.equal(e.global_v[l], engines[0].global_v[l])
+            if t >= 1:
+                for r in range(world):
+                    got, was = engines[0].global_k[l][r * n:(r + 1) * n], before[r * n:(r + 1) * n]
+                    assert rel_l2(got, ks[r]) < 0.5 * rel_l2(was, ks[r]) + 1e-3, (t, l, r, rel_l2(got, ks[r]), rel_l2(was, ks[r]))
+        x = data[0][0][0][t].to(dev).view(1, n, 12, c // 12)
+        p = cf.compact_compress("0-0-k", x, ct, update_cache=True)
+        ref = cf.compact_decompress("9-0-k", p, ct, x.shape, update_cache=True).view(n, c)
+        if t >= 1:
+            assert p.numel() == want_numel, "wire size differs from the plugin path's payload"
+            mine = engines[0].global_k[0][:n]
+            assert rel_l2(mine, x.view(n, c)) < 1.25 * rel_l2(ref, x.view(n, c)) + 2e-3
+    assert not any(e.p2p_error() for e in engines)
