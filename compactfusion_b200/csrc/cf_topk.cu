@@ -7,6 +7,8 @@
 // accesses are coalesced.  The residual subtract (v = x - base) and the error-feedback update
 // (new_base = base + sparsified v) are fused in.  Ties: lowest index wins (Triton argmax,
 // SURVEY.md App-B.7).
+#include <stdlib.h>
+
 #include "cf_common.cuh"
 
 namespace cf {
@@ -120,6 +122,19 @@ static int topk_grid(int64_t nthreads) {
   if (blocks > cap) blocks = cap;
   return static_cast<int>(blocks);
 }
+// second version (cf_topk_v2.cuh): one 16-byte group per thread, four in flight; CF_LEGACY_KERNELS=1 keeps the first
+static bool topk_v2() {
+  const char* e = getenv("CF_LEGACY_KERNELS");
+  return !(e && e[0] == '1');
+}
+static int topk_grid_v2(int64_t ngroups) {
+  int64_t blocks = (ngroups + 4 * 256 - 1) / (4 * 256);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+#include "cf_topk_v2.cuh"
 
 }  // namespace cf
 
@@ -139,6 +154,18 @@ int cf_topk_compress(const void* x, const void* base, void* new_base, void* val,
   __half* nb = static_cast<__half*>(new_base);
   __half* vh = static_cast<__half*>(val);
   uint8_t* ih = static_cast<uint8_t*>(idx);
+  if (cf::topk_v2() && (reinterpret_cast<uintptr_t>(idx) & 1u) == 0) {
+    const int64_t ng = numel / 8;
+    const int g2 = cf::topk_grid_v2(ng);
+    switch (m) {
+      case 2: cf::k_topk_compress_v2<2><<<g2, 256, 0, st>>>(xh, bh, nb, vh, ih, ng); break;
+      case 4: cf::k_topk_compress_v2<4><<<g2, 256, 0, st>>>(xh, bh, nb, vh, ih, ng); break;
+      case 8: cf::k_topk_compress_v2<8><<<g2, 256, 0, st>>>(xh, bh, nb, vh, ih, ng); break;
+      case 16: cf::k_topk_compress_v2<16><<<g2, 256, 0, st>>>(xh, bh, nb, vh, ih, ng); break;
+    }
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+  }
   switch (m) {
     case 2: cf::k_topk_compress<2><<<grid, 256, 0, st>>>(xh, bh, nb, vh, ih, nt); break;
     case 4: cf::k_topk_compress<4><<<grid, 256, 0, st>>>(xh, bh, nb, vh, ih, nt); break;
@@ -162,6 +189,18 @@ int cf_topk_decompress(const void* val, const void* idx, const void* base, void*
   const uint8_t* ih = static_cast<const uint8_t*>(idx);
   const __half* bh = static_cast<const __half*>(base);
   __half* rh = static_cast<__half*>(recon);
+  if (cf::topk_v2() && cf::aligned16(val) && (reinterpret_cast<uintptr_t>(idx) & 1u) == 0) {
+    const int64_t ng = numel / 8;
+    const int g2 = cf::topk_grid_v2(ng);
+    switch (m) {
+      case 2: cf::k_topk_decompress_v2<2><<<g2, 256, 0, st>>>(vh, ih, bh, rh, ng); break;
+      case 4: cf::k_topk_decompress_v2<4><<<g2, 256, 0, st>>>(vh, ih, bh, rh, ng); break;
+      case 8: cf::k_topk_decompress_v2<8><<<g2, 256, 0, st>>>(vh, ih, bh, rh, ng); break;
+      case 16: cf::k_topk_decompress_v2<16><<<g2, 256, 0, st>>>(vh, ih, bh, rh, ng); break;
+    }
+    CF_CHECK_LAUNCH();
+    return CF_OK;
+  }
   switch (m) {
     case 2: cf::k_topk_decompress<2><<<grid, 256, 0, st>>>(vh, ih, bh, rh, nt); break;
     case 4: cf::k_topk_decompress<4><<<grid, 256, 0, st>>>(vh, ih, bh, rh, nt); break;
