@@ -605,8 +605,11 @@ def measure_e2e(args, eng, sample, ctype, world, n_local, layers, device, transp
 
     def e2e_step():
         in_done = [None, None]
+        dones = []
         for layer in range(e2e_layers):
             s = layer & 1
+            if layer >= 2:
+                copy_in.wait_event(dones[layer - 2])  # staging buffer s was last read by the exchange of layer - 2
             with torch.cuda.stream(copy_in):
                 dk[s].copy_(hk[s], non_blocking=True)
                 dv[s].copy_(hv[s], non_blocking=True)
@@ -620,8 +623,11 @@ def measure_e2e(args, eng, sample, ctype, world, n_local, layers, device, transp
                 copy_out.wait_event(done)
                 out_k.copy_(gk, non_blocking=True)
                 out_v.copy_(gv, non_blocking=True)
-            copy_in.wait_event(done)  # the staging buffer may be refilled only after its exchange
+            dones.append(done)
         main_s.wait_stream(copy_out)
+        copy_in.wait_event(dones[-1])
+        if len(dones) > 1:
+            copy_in.wait_event(dones[-2])
 
     e2e_step()
     barrier()

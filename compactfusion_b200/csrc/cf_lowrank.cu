@@ -466,8 +466,10 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   k_lr_pad_split<<<small_grid, 256, 0, st>>>(q0, Q2, c, r, RP);
   CF_CHECK_LAUNCH();
 
-  // 16 warps per CTA when there are >= 2 column tiles to split between two warp groups (CF_LR_WARPS=8: round 1's 8)
-  static const bool wide = [] { const char* e = getenv("CF_LR_WARPS"); return !(e && e[0] == '8'); }();
+  // 16 warps per CTA split the column tiles between two warp groups
+  // (measured: 31-35 us per pass against 22 us with 8 warps -- both groups repeat the ldmatrix / convert work on
+  //  the streamed operand, which is the larger half of the loop; kept as an opt-in for A/B: CF_LR_WARPS=16)
+  static const bool wide = [] { const char* e = getenv("CF_LR_WARPS"); return e && e[0] == '1' && e[1] == '6'; }();
   const int gemm_threads = (RP >= 16 && wide) ? 2 * kLrThreads : kLrThreads;
   auto gemm_AQ = [&]() {  // part[s] (N, RP) = A Q
     dim3 grid((n + kLrBM - 1) / kLrBM, p.aq_splits);

@@ -1,5 +1,5 @@
-// Cluster CholeskyQR2 of the LOW_RANK projector (included by cf_lowrank.cu after cf_lowrank_mma.cuh, whose
-// cholesky_upper_256 / split_tf32 it uses).
+// Cluster orthonormalisation (shifted CholeskyQR3) and the prefetching reconstruct of the LOW_RANK codec (included
+// by cf_lowrank.cu after cf_lowrank_mma.cuh, whose split_tf32 / ldmatrix / mma wrappers they use).
 #pragma once
 
 #include "cf_lowrank_mma.cuh"
@@ -7,26 +7,24 @@
 namespace cf {
 
 // ---------------------------------------------------------------------------------------
-// CholeskyQR2 of X = sum of S split-K partials (M x RP, fp32) as ONE kernel on ONE thread-block cluster.
+// Orthonormalisation of X = sum of S split-K partials (M x RP, fp32) as ONE kernel on ONE thread-block cluster:
+// shifted CholeskyQR3, entirely in fp32.
 //
-// Round 1 measured 93 us per orthonormalisation (sum kernel + 2 x (Gram / Cholesky on a 16-CTA grid with a
-// global ticket + a forward-substitution kernel)): five dependent launches of latency-bound work, three times
-// per projector call -- 2/3 of the call.  Here the kClusterCtas CTAs of a cluster each own a contiguous row
-// range of X and make three streaming passes over it (the matrix is < 1 MB: L2-resident):
-//   A: X = sum_s part[s]            -> X (global), partial Gram G_cta = X_cta^T X_cta   (upper 2x2 blocks)
-//   B: X = X R1^-1                  -> X (global), partial Gram of the new X
-//   C: X = X R2^-1                  -> outputs ({hi,lo} TF32 pairs / fp16 / compact fp32)
-// Between the passes the partial Grams are reduced over the cluster through distributed shared memory in a
-// FIXED rank order (every CTA computes the same bits, no atomics), and every CTA factors the r x r Gram
-// redundantly (cholesky_upper_256), so nothing ever goes back to global memory or to the host.
+// Round 1 measured 93 us per orthonormalisation (sum kernel + 2 x (fp64 Gram / Cholesky on a 16-CTA grid with a
+// global ticket + a forward-substitution kernel)): five dependent launches, three times per projector call, 2/3
+// of the call.  Two cluster versions with an fp64 Gram / fp64 factorisation followed (109 and 79 us,
+// profiles/r2_kernel_times_lowrank_orth_v{1,2}.md): this part issues about 2.4 fp64 operations per clock per
+// SM, so ANY fp64 in the loop dominates.  CholeskyQR2 needs the fp64 Gram because it fails once
+// cond(X)^2 u32 ~ 1; shifted CholeskyQR3 (Fukaya, Kannan, Nakatsukasa, Yamamoto, Yanagisawa 2020) does not:
+//   pass 1:  R1 = chol(X^T X + s I),  X1 = X R1^-1     the shift makes the factorisation succeed for any X and
+//                                                       leaves cond(X1) <= sqrt(1 + sigma_1^2 / s)
+//   pass 2, 3: plain CholeskyQR on X1 (cond <= 100 with s = 1e-4 trace(X^T X)): orthogonal to fp32 rounding
+// Every pass spans the same column space as X, so U V -- the only quantity the codec ships -- is unchanged.
 //
-// Precision of the Gram matrix.  fp64 FMAs are the wrong tool on this part: the first version of this kernel
-// accumulated every product in fp64 and spent ~100 us per call in DFMA (profiles/r2_kernel_times_lowrank_orth_v1.md:
-// ~2.4 DFMA per clock per SM).  Now products and sums are fp32 inside blocks of 32 rows and the block sums are
-// added in fp64 (one DADD per 32 FFMAs): the error of an entry is ~0.5 u32 |x_i| |x_j| (product rounding
-// ~u32 / sqrt(M), summation ~u32 * 32 / sqrt(M)), where plain fp32 accumulation over M = 4608 rows would give
-// ~sqrt(M) u32.  The factorisation itself stays fp64.  CholeskyQR2 then holds for cond(X) up to ~1e3; beyond that
-// the pivot floor in cholesky_upper_256 keeps the result finite (rank-deficient directions carry no energy).
+// The kClusterCtas CTAs each own a contiguous row range of X (the matrix is < 1 MB: L2-resident) and stream it
+// once per pass; partial Grams (fp32, Kahan-compensated over blocks of 32 rows) are reduced over the cluster
+// through distributed shared memory in a FIXED rank order (identical bits in every CTA, no atomics) and every CTA
+// factors the r x r matrix redundantly, so nothing goes back to global memory or to the host between passes.
 // ---------------------------------------------------------------------------------------
 constexpr int kClusterCtas = 8;    // portable cluster size
 // rows staged per step: one row per thread in the substitution passes (RP = 64: half, to fit shared memory)
@@ -37,7 +35,7 @@ struct OrthParams {
   const float* part;     // S partial copies of X, `part_stride` floats apart
   int S;
   size_t part_stride;
-  float* X;              // (M, RP) scratch: the sum, then the intermediate X R1^-1
+  float* X;              // (M, RP) scratch: the sum, then the intermediate X R^-1
   int M, r;
   float2* out2;          // optional (M, RP) {hi, lo} TF32 pairs (the next product's skinny operand)
   __half* out16;         // optional (M, r) fp16
@@ -46,10 +44,10 @@ struct OrthParams {
 
 template <int RP>
 constexpr size_t lr_orth_smem() {
-  return sizeof(float) * orth_chunk<RP>() * (RP + 2)                  // row chunk (fp32)
-         + sizeof(double) * RP * RP                                   // this CTA's partial Gram (read by the cluster)
-         + sizeof(double) * (kLrMaxRank * (kLrMaxRank + 1) + kLrMaxRank)  // G + pivots for the factorisation
-         + sizeof(float) * (RP * RP + RP);                            // R (upper) and 1 / diag
+  return sizeof(float) * orth_chunk<RP>() * (RP + 2)      // row chunk
+         + sizeof(float) * RP * RP                        // this CTA's partial Gram (read by the cluster)
+         + sizeof(float) * (RP * (RP + 1) + RP)           // G (+ pivots) for the factorisation
+         + sizeof(float) * (RP * RP + RP) + 64;           // R (upper), 1 / diag, scalars
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -61,14 +59,42 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// read a double from the same shared-memory offset of CTA `rank` of the cluster (DSMEM)
-__device__ __forceinline__ double ld_dsmem_f64(const double* local, uint32_t rank) {
+// read a float from the same shared-memory offset of CTA `rank` of the cluster (DSMEM)
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local));
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(a), "r"(rank));
-  double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
   return v;
+}
+
+// Upper-triangular R with G = R^T R by the 256 threads of the CTA, fp32, one barrier per step: the trailing update
+// uses the unscaled pivot row, G[i][j] -= G[k][i] G[k][j] / G[k][k]; thread (ti, tj) of a 16 x 16 grid owns the
+// entries (ti + 16a, tj + 16b).  On return G[k][j] (j >= k) holds the unscaled pivot rows:
+// R[k][j] = G[k][j] * piv[k], piv[k] = G[k][k]^-1/2.  A pivot below `floor_piv` (rank-deficient input) is floored.
+template <int RP>
+__device__ void cholesky_upper_f32(float (*G)[RP + 1], float* piv, int r, int t, float floor_piv) {
+  const int ti = t >> 4, tj = t & 15;
+  for (int k = 0; k < r; ++k) {
+    float d = G[k][k];
+    if (!(d > floor_piv)) d = floor_piv;
+    const float inv_d = 1.0f / d;
+    if (t == 0) piv[k] = rsqrtf(d);
+#pragma unroll
+    for (int a = 0; a < (RP + 15) / 16; ++a) {
+      const int i = ti + 16 * a;
+      if (i > k && i < r) {
+        const float gki = G[k][i] * inv_d;
+#pragma unroll
+        for (int b = 0; b < (RP + 15) / 16; ++b) {
+          const int j = tj + 16 * b;
+          if (j >= i && j < r) G[i][j] = fmaf(-gki, G[k][j], G[i][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
 }
 
 template <int RP>
@@ -76,11 +102,12 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   extern __shared__ __align__(16) unsigned char orth_raw[];
   constexpr int kLdX = RP + 2, kOrthChunk = orth_chunk<RP>();
   float* Xd = reinterpret_cast<float*>(orth_raw);                         // [kOrthChunk][kLdX]
-  double* Gp = reinterpret_cast<double*>(Xd + kOrthChunk * kLdX);         // [RP][RP] partial Gram of this CTA
-  double (*G)[kLrMaxRank + 1] = reinterpret_cast<double (*)[kLrMaxRank + 1]>(Gp + RP * RP);
-  double* piv = reinterpret_cast<double*>(G) + kLrMaxRank * (kLrMaxRank + 1);
-  float* Rs = reinterpret_cast<float*>(piv + kLrMaxRank);                 // [RP][RP]
+  float* Gp = Xd + kOrthChunk * kLdX;                                     // [RP][RP] partial Gram of this CTA
+  float (*G)[RP + 1] = reinterpret_cast<float (*)[RP + 1]>(Gp + RP * RP);
+  float* piv = reinterpret_cast<float*>(G) + RP * (RP + 1);
+  float* Rs = piv + RP;                                                   // [RP][RP]
   float* Ds = Rs + RP * RP;                                               // [RP]
+  float* scal = Ds + RP;                                                  // [0]: trace(G)
   const int t = threadIdx.x, r = p.r, M = p.M;
   const uint32_t rank = cluster_ctarank();
   int rows_per = (M + kClusterCtas - 1) / kClusterCtas;
@@ -100,16 +127,22 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     bi[q] = id >= 0 ? i : -1;
     bj[q] = id >= 0 ? i + id : -1;
   }
-  double acc[KB][4];
+  float acc[KB][4], comp[KB][4];   // Kahan sum of the 32-row block sums
 
   auto zero_acc = [&]() {
 #pragma unroll
     for (int q = 0; q < KB; ++q)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[q][e] = 0.0;
+      for (int e = 0; e < 4; ++e) acc[q][e] = comp[q][e] = 0.f;
+  };
+  auto kahan = [&](float& sum, float& c, float v) {
+    const float y = v - c;
+    const float tsum = sum + y;
+    c = (tsum - sum) - y;
+    sum = tsum;
   };
   auto gram_chunk = [&](int rows) {   // acc += Xd[0..rows)^T Xd[0..rows) on this thread's blocks
-    for (int rb = 0; rb < rows; rb += 32) {   // fp32 inside a block of 32 rows, fp64 across blocks
+    for (int rb = 0; rb < rows; rb += 32) {
       const int re = min(rows, rb + 32);
 #pragma unroll
       for (int q = 0; q < KB; ++q) {
@@ -124,16 +157,16 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
             a2 = fmaf(xi.y, xj.x, a2);
             a3 = fmaf(xi.y, xj.y, a3);
           }
-          acc[q][0] += static_cast<double>(a0);
-          acc[q][1] += static_cast<double>(a1);
-          acc[q][2] += static_cast<double>(a2);
-          acc[q][3] += static_cast<double>(a3);
+          kahan(acc[q][0], comp[q][0], a0);
+          kahan(acc[q][1], comp[q][1], a1);
+          kahan(acc[q][2], comp[q][2], a2);
+          kahan(acc[q][3], comp[q][3], a3);
         }
       }
     }
   };
-  // partial Gram -> Gp; cluster-wide sum in rank order -> G (upper); Cholesky -> Rs, Ds
-  auto reduce_and_factor = [&]() {
+  // partial Gram -> Gp; cluster-wide sum in rank order -> G (upper); (+ shift) Cholesky -> Rs, Ds
+  auto reduce_and_factor = [&](float shift_rel) {
 #pragma unroll
     for (int q = 0; q < KB; ++q)
       if (bi[q] >= 0) {
@@ -148,35 +181,46 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     for (int q = 0; q < KB; ++q)
       if (bi[q] >= 0) {
         const int i = 2 * bi[q], j = 2 * bj[q];
-        double v[kClusterCtas][4];
+        float v[kClusterCtas][4];
 #pragma unroll
-        for (uint32_t rk = 0; rk < kClusterCtas; ++rk) {   // all 32 remote loads in flight before the first add
-          v[rk][0] = ld_dsmem_f64(Gp + i * RP + j, rk);
-          v[rk][1] = ld_dsmem_f64(Gp + i * RP + j + 1, rk);
-          v[rk][2] = ld_dsmem_f64(Gp + (i + 1) * RP + j, rk);
-          v[rk][3] = ld_dsmem_f64(Gp + (i + 1) * RP + j + 1, rk);
+        for (uint32_t rk = 0; rk < kClusterCtas; ++rk) {   // all remote loads in flight before the first add
+          v[rk][0] = ld_dsmem_f32(Gp + i * RP + j, rk);
+          v[rk][1] = ld_dsmem_f32(Gp + i * RP + j + 1, rk);
+          v[rk][2] = ld_dsmem_f32(Gp + (i + 1) * RP + j, rk);
+          v[rk][3] = ld_dsmem_f32(Gp + (i + 1) * RP + j + 1, rk);
         }
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (uint32_t rk = 0; rk < kClusterCtas; ++rk) {   // fixed order: identical bits in every CTA
-          s[0] += v[rk][0];
-          s[1] += v[rk][1];
-          s[2] += v[rk][2];
-          s[3] += v[rk][3];
+          sm[0] += v[rk][0];
+          sm[1] += v[rk][1];
+          sm[2] += v[rk][2];
+          sm[3] += v[rk][3];
         }
-        G[i][j] = s[0];
-        G[i][j + 1] = s[1];
-        if (i != j) G[i + 1][j] = s[2];   // (below the diagonal inside a diagonal block: never read)
-        G[i + 1][j + 1] = s[3];
+        G[i][j] = sm[0];
+        G[i][j + 1] = sm[1];
+        if (i != j) G[i + 1][j] = sm[2];   // (below the diagonal inside a diagonal block: never read)
+        G[i + 1][j + 1] = sm[3];
       }
-    cluster_sync_all();   // all remote reads of Gp are done: it may be overwritten by the next round
+    cluster_sync_all();   // all remote reads of Gp are done: it may be overwritten by the next pass
     __syncthreads();
-    cholesky_upper_256(G, piv, r, t);
+    if (t == 0) {
+      float tr = 0.f;
+      for (int i = 0; i < r; ++i) tr += G[i][i];
+      scal[0] = tr;
+    }
+    __syncthreads();
+    const float tr = scal[0];
+    if (shift_rel > 0.f) {
+      if (t < r) G[t][t] += shift_rel * tr;
+      __syncthreads();
+    }
+    cholesky_upper_f32<RP>(G, piv, r, t, fmaxf(tr, 1e-30f) * 1e-7f);
     for (int e = t; e < RP * RP; e += 256) {
       const int i = e / RP, j = e % RP;
-      Rs[e] = (i < r && j < r && j >= i) ? static_cast<float>(G[i][j] * piv[i]) : 0.f;
+      Rs[e] = (i < r && j < r && j >= i) ? G[i][j] * piv[i] : 0.f;
     }
-    for (int j = t; j < RP; j += 256) Ds[j] = (j < r) ? static_cast<float>(piv[j]) : 0.f;
+    for (int j = t; j < RP; j += 256) Ds[j] = (j < r) ? piv[j] : 0.f;
     __syncthreads();
   };
   // X[m] <- X[m] R^-1 for one row held in registers (right-looking forward substitution)
@@ -191,8 +235,16 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
       asm volatile("" ::: "memory");
     }
   };
+  auto load_row = [&](float (&xr)[RP], int m) {
+    const float4* xrow = reinterpret_cast<const float4*>(p.X + static_cast<size_t>(m) * RP);
+#pragma unroll
+    for (int q = 0; q < RP / 4; ++q) {
+      const float4 v = xrow[q];
+      xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+    }
+  };
 
-  // ---- pass A: sum of the partials, first Gram ----
+  // ---- pass 1 (first half): sum of the partials, Gram ----
   zero_acc();
   for (int mc = m_begin; mc < m_end; mc += kOrthChunk) {
     const int rows = min(kOrthChunk, m_end - mc);
@@ -218,41 +270,34 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     __syncthreads();
     gram_chunk(rows);
   }
-  reduce_and_factor();
+  reduce_and_factor(1e-4f);   // shifted factorisation: always succeeds, leaves cond(X R1^-1) <= ~100
 
-  // ---- pass B: X <- X R1^-1, second Gram ----
-  zero_acc();
-  for (int mc = m_begin; mc < m_end; mc += kOrthChunk) {
-    const int rows = min(kOrthChunk, m_end - mc);
-    __syncthreads();
-    if (t < rows) {
-      float xr[RP];
-      float4* xrow = reinterpret_cast<float4*>(p.X + static_cast<size_t>(mc + t) * RP);
+  // ---- passes 1 (second half) and 2: X <- X R^-1, Gram of the new X, plain Cholesky ----
+  for (int pass = 0; pass < 2; ++pass) {
+    zero_acc();
+    for (int mc = m_begin; mc < m_end; mc += kOrthChunk) {
+      const int rows = min(kOrthChunk, m_end - mc);
+      __syncthreads();
+      if (t < rows) {
+        float xr[RP];
+        load_row(xr, mc + t);
+        solve_row(xr);
+        float4* xrow = reinterpret_cast<float4*>(p.X + static_cast<size_t>(mc + t) * RP);
 #pragma unroll
-      for (int q = 0; q < RP / 4; ++q) {
-        const float4 v = xrow[q];
-        xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+        for (int q = 0; q < RP / 4; ++q) xrow[q] = make_float4(xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]);
+#pragma unroll
+        for (int j = 0; j < RP; ++j) Xd[t * kLdX + j] = xr[j];
       }
-      solve_row(xr);
-#pragma unroll
-      for (int q = 0; q < RP / 4; ++q) xrow[q] = make_float4(xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]);
-#pragma unroll
-      for (int j = 0; j < RP; ++j) Xd[t * kLdX + j] = xr[j];
+      __syncthreads();
+      gram_chunk(rows);
     }
-    __syncthreads();
-    gram_chunk(rows);
+    reduce_and_factor(0.f);
   }
-  reduce_and_factor();
 
-  // ---- pass C: X <- X R2^-1, outputs ----
+  // ---- pass 3 (second half): X <- X R3^-1, outputs ----
   for (int m = m_begin + t; m < m_end; m += 256) {
     float xr[RP];
-    const float4* xrow = reinterpret_cast<const float4*>(p.X + static_cast<size_t>(m) * RP);
-#pragma unroll
-    for (int q = 0; q < RP / 4; ++q) {
-      const float4 v = xrow[q];
-      xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
-    }
+    load_row(xr, m);
     solve_row(xr);
     if (p.out2) {
 #pragma unroll
@@ -266,7 +311,6 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
       }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------
 // recon = base + fp16(U V), second version.  k_lr_reconstruct_mma loads U (2-byte loads), V, multiplies, and

@@ -602,7 +602,7 @@ static int minmax_compress(const void* x, const void* base, void* new_base, void
       int rc = bh ? launch_mm_stats_tma<true>(sp, xh, bh, pmin, pmax, n, c, st)
                   : launch_mm_stats_tma<false>(sp, xh, bh, pmin, pmax, n, c, st);
       if (rc) return rc;
-      CF_CHECK_CUDA(mm_launch(k_minmax_finalize_v8<MODE>, dim3((c + 63) / 64), dim3(256), 0, st, pmin, pmax, sp.B, c,
+      CF_CHECK_CUDA(mm_launch(k_minmax_finalize_v8<MODE>, dim3((c + 15) / 16), dim3(256), 0, st, pmin, pmax, sp.B, c,
                               static_cast<__half*>(scale), second, min_ws));
       constexpr int L = MmLevels<MODE>::value;
       rc = bh ? launch_int4_codec_tma<true, true, L>(cp, xh, bh, static_cast<const __half*>(scale),

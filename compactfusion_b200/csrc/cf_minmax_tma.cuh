@@ -243,25 +243,28 @@ __global__ void __launch_bounds__(OCC == 2 ? kMmThreads2 : kMmThreads1, OCC)
 }
 
 // ---------------------------------------------------------------------------------------
-// finalize, 8 columns per thread: block 256 = 8 column groups x 32 partial lanes, grid ceil(C / 64).  Every thread
-// folds ceil(B / 32) partial rows with independent 16-byte loads (the 2-byte version is a chain of B / 8
-// dependent L2 round trips per thread: 11.4 us for 3.6 MB).
+// finalize, 8 columns per thread: block 256 = 2 column groups x 128 partial lanes, grid ceil(C / 16).  Every
+// thread folds ceil(B / 128) partial rows (<= 3 for B = 296) with independent 16-byte loads, all in flight at
+// once; lanes are then combined with xor-shuffles inside a warp and through shared memory across the 8 warps.
+// (The 2-byte version is a chain of B / 8 dependent L2 round trips per thread: 11.4 us for 3.6 MB; a first
+// 8-column version with only C / 64 = 48 CTAs still took 8.1 us.)
 // ---------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256) k_minmax_finalize_v8(const __half* __restrict__ pmin, const __half* __restrict__ pmax,
                                                            int B, int C, __half* __restrict__ scale_out,
                                                            void* __restrict__ second_out, __half* __restrict__ min_ws) {
-  __shared__ uint4 smn[32][8], smx[32][8];
-  const int gx = threadIdx.x & 7, py = threadIdx.x >> 3;
-  const int g = blockIdx.x * 8 + gx;   // column group of 8
+  __shared__ uint4 smn[8][2], smx[8][2];
+  const int gx = threadIdx.x & 1, py = threadIdx.x >> 1;
+  const int warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * 2 + gx;   // column group of 8
   const bool in = 8 * g < C;
   pdl_wait();
   pdl_launch_dependents();
   const __half2 pinf = __half2half2(__ushort_as_half(0x7C00)), ninf = __half2half2(__ushort_as_half(0xFC00));
   __half2 mn[4] = {pinf, pinf, pinf, pinf}, mx[4] = {ninf, ninf, ninf, ninf};
   if (in) {
-#pragma unroll 4
-    for (int b = py; b < B; b += 32) {
+#pragma unroll 3
+    for (int b = py; b < B; b += 128) {
       const uint4 a = *reinterpret_cast<const uint4*>(pmin + static_cast<size_t>(b) * C + 8 * g);
       const uint4 c = *reinterpret_cast<const uint4*>(pmax + static_cast<size_t>(b) * C + 8 * g);
       mn[0] = __hmin2(mn[0], u2h2(a.x)); mn[1] = __hmin2(mn[1], u2h2(a.y));
@@ -270,16 +273,27 @@ __global__ void __launch_bounds__(256) k_minmax_finalize_v8(const __half* __rest
       mx[2] = __hmax2(mx[2], u2h2(c.z)); mx[3] = __hmax2(mx[3], u2h2(c.w));
     }
   }
-  smn[py][gx] = make_uint4(h22u(mn[0]), h22u(mn[1]), h22u(mn[2]), h22u(mn[3]));
-  smx[py][gx] = make_uint4(h22u(mx[0]), h22u(mx[1]), h22u(mx[2]), h22u(mx[3]));
+  // lanes of a warp: 16 partial lanes x 2 column groups (bit 0 of the lane): fold over bits 1..4
+#pragma unroll
+  for (int o = 2; o <= 16; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mn[i] = __hmin2(mn[i], u2h2(__shfl_xor_sync(0xffffffffu, h22u(mn[i]), o)));
+      mx[i] = __hmax2(mx[i], u2h2(__shfl_xor_sync(0xffffffffu, h22u(mx[i]), o)));
+    }
+  if ((threadIdx.x & 31) < 2) {
+    smn[warp][gx] = make_uint4(h22u(mn[0]), h22u(mn[1]), h22u(mn[2]), h22u(mn[3]));
+    smx[warp][gx] = make_uint4(h22u(mx[0]), h22u(mx[1]), h22u(mx[2]), h22u(mx[3]));
+  }
   __syncthreads();
-  // 64 threads finish the 64 columns of this CTA: thread t -> column group t / 8, element t % 8
-  if (threadIdx.x < 64) {
+  // 16 threads finish the 16 columns of this CTA: thread t -> column group t / 8, element t % 8
+  if (threadIdx.x < 16) {
     const int cg = threadIdx.x >> 3, e = threadIdx.x & 7;
-    const int c = (blockIdx.x * 8 + cg) * 8 + e;
+    const int c = (blockIdx.x * 2 + cg) * 8 + e;
     if (c < C) {
       __half m = __ushort_as_half(0x7C00), M = __ushort_as_half(0xFC00);
-      for (int k = 0; k < 32; ++k) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
         m = __hmin(m, reinterpret_cast<const __half*>(&smn[k][cg])[e]);
         M = __hmax(M, reinterpret_cast<const __half*>(&smx[k][cg])[e]);
       }
