@@ -483,26 +483,54 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   // One launch on one 8-CTA cluster (k_lr_orth); CF_LR_ORTH=legacy keeps round 1's five-launch chain (A/B).
   static const bool legacy_orth = [] { const char* e = getenv("CF_LR_ORTH"); return e && e[0] == 'l'; }();
   const size_t smem_o = lr_orth_smem<RP>();
-  if (!legacy_orth)
-    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)));
+  // cluster size: 16 CTAs (non-portable, needs the opt-in attribute) when the device can co-schedule them, else 8
+  static int orth_nc = 0;
+  if (!legacy_orth && orth_nc == 0) {
+    orth_nc = 8;
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)));
+    const char* e = getenv("CF_LR_CLUSTER");
+    if (!(e && e[0] == '8') &&
+        cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)) == cudaSuccess) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(16); q.blockDim = dim3(256); q.dynamicSmemBytes = smem_o;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_lr_orth<RP, 16>, &q) == cudaSuccess && nclusters > 0) orth_nc = 16;
+    }
+    (void)cudaGetLastError();
+  }
+  if (!legacy_orth) {  // (the attributes are per kernel instantiation: set for every RP this process uses)
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)));
+    if (orth_nc == 16) {
+      CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)));
+    }
+  }
   auto orth = [&](int S, int M, int ctas, int rows, float2* out2, __half* out16, float* out32c) -> int {
     if (!legacy_orth) {
       OrthParams o{};
       o.part = part; o.S = S; o.part_stride = static_cast<size_t>(M) * RP; o.X = Xsum; o.M = M; o.r = r;
       o.out2 = out2; o.out16 = out16; o.out32c = out32c;
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(kClusterCtas);
+      cfg.gridDim = dim3(orth_nc);
       cfg.blockDim = dim3(256);
       cfg.dynamicSmemBytes = smem_o;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = kClusterCtas;
+      attr[0].val.clusterDim.x = orth_nc;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      CF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_lr_orth<RP>, o));
+      if (orth_nc == 16)
+        CF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_lr_orth<RP, 16>, o));
+      else
+        CF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_lr_orth<RP, 8>, o));
       return CF_OK;
     }
     // the S split-K partials are added by a wide kernel (all SMs); the 16 Gram CTAs then read one copy

@@ -26,7 +26,7 @@ namespace cf {
 // through distributed shared memory in a FIXED rank order (identical bits in every CTA, no atomics) and every CTA
 // factors the r x r matrix redundantly, so nothing goes back to global memory or to the host between passes.
 // ---------------------------------------------------------------------------------------
-constexpr int kClusterCtas = 8;    // portable cluster size
+constexpr int kClusterCtas = 8;    // portable cluster size; 16 (non-portable, opt-in attribute) halves the rows per CTA
 // rows staged per step: one row per thread in the substitution passes (RP = 64: half, to fit shared memory)
 template <int RP>
 constexpr int orth_chunk() { return RP <= 32 ? 256 : 128; }
@@ -97,7 +97,7 @@ __device__ void cholesky_upper_f32(float (*G)[RP + 1], float* piv, int r, int t,
   }
 }
 
-template <int RP>
+template <int RP, int NC>
 __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   extern __shared__ __align__(16) unsigned char orth_raw[];
   constexpr int kLdX = RP + 2, kOrthChunk = orth_chunk<RP>();
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   float* scal = Ds + RP;                                                  // [0]: trace(G)
   const int t = threadIdx.x, r = p.r, M = p.M;
   const uint32_t rank = cluster_ctarank();
-  int rows_per = (M + kClusterCtas - 1) / kClusterCtas;
+  int rows_per = (M + NC - 1) / NC;
   rows_per = (rows_per + 3) / 4 * 4;
   const int m_begin = min(M, static_cast<int>(rank) * rows_per);
   const int m_end = min(M, m_begin + rows_per);
@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     for (int q = 0; q < KB; ++q)
       if (bi[q] >= 0) {
         const int i = 2 * bi[q], j = 2 * bj[q];
-        float v[kClusterCtas][4];
+        float v[NC][4];
 #pragma unroll
-        for (uint32_t rk = 0; rk < kClusterCtas; ++rk) {   // all remote loads in flight before the first add
+        for (uint32_t rk = 0; rk < NC; ++rk) {   // all remote loads in flight before the first add
           v[rk][0] = ld_dsmem_f32(Gp + i * RP + j, rk);
           v[rk][1] = ld_dsmem_f32(Gp + i * RP + j + 1, rk);
           v[rk][2] = ld_dsmem_f32(Gp + (i + 1) * RP + j, rk);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
         }
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (uint32_t rk = 0; rk < kClusterCtas; ++rk) {   // fixed order: identical bits in every CTA
+        for (uint32_t rk = 0; rk < NC; ++rk) {   // fixed order: identical bits in every CTA
           sm[0] += v[rk][0];
           sm[1] += v[rk][1];
           sm[2] += v[rk][2];
@@ -229,8 +229,16 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     for (int i = 0; i < RP; ++i) {
       const float xi = xr[i] * Ds[i];   // columns >= r: Ds = 0 -> exact zeros in the padding
       xr[i] = xi;
+      // row i of R in 16-byte pieces (one LDS.128 per 4 FMAs instead of one LDS per FMA: the kernel is
+      // instruction-issue bound, ncu profiles/r2_ncu_lowrank_orth_v3.md)
 #pragma unroll
-      for (int j = i + 1; j < RP; ++j) xr[j] = fmaf(-xi, Rs[i * RP + j], xr[j]);
+      for (int q = i / 4; q < RP / 4; ++q) {
+        const float4 rv = *reinterpret_cast<const float4*>(Rs + i * RP + 4 * q);
+        if (4 * q + 0 > i) xr[4 * q + 0] = fmaf(-xi, rv.x, xr[4 * q + 0]);
+        if (4 * q + 1 > i) xr[4 * q + 1] = fmaf(-xi, rv.y, xr[4 * q + 1]);
+        if (4 * q + 2 > i) xr[4 * q + 2] = fmaf(-xi, rv.z, xr[4 * q + 2]);
+        if (4 * q + 3 > i) xr[4 * q + 3] = fmaf(-xi, rv.w, xr[4 * q + 3]);
+      }
       // keep row i's loads of R inside step i (hoisting all RP^2 / 2 of them spills the row out of registers)
       asm volatile("" ::: "memory");
     }

@@ -105,12 +105,17 @@ struct PublishParams {
   uint32_t* flag[CF_MAX_PEERS];
   uint32_t* count;
   int n_dst;
+  int sc_fence;   // CF_PUBLISH_FENCE=sc: __threadfence_system() (MEMBAR.SC.SYS) instead of fence.acq_rel.sys (MEMBAR.ALL.SYS)
 };
 __global__ void __launch_bounds__(32) k_publish_flags(const PublishParams p) {
   pdl_wait();
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    // release = fence.acq_rel + relaxed store (PTX memory model); the sequentially consistent fence is not needed
+    if (p.sc_fence)
+      __threadfence_system();
+    else
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
     const uint32_t v = *p.count + 1u;
     for (int q = 0; q < p.n_dst; ++q) st_relaxed_sys_u32(p.flag[q], v);
     *p.count = v;  // read by the flag-waiting kernels launched after this one (stream order / PDL wait)
@@ -1140,6 +1145,10 @@ static int sign_compress_put(int passes, int batch, const void* const* x, const 
     PublishParams pp{};
     pp.n_dst = n_dst;
     pp.count = f.count;
+    {
+      const char* e = getenv("CF_PUBLISH_FENCE");
+      pp.sc_fence = (e && e[0] == 's') ? 1 : 0;
+    }
     for (int q = 0; q < n_dst; ++q) pp.flag[q] = f.flag[q];
     CF_CHECK_CUDA(launch_ex(k_publish_flags, dim3(1), dim3(32), 0, st, true, pp));
   }

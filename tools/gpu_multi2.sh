@@ -40,7 +40,11 @@ PY
 }
 has serial      && { echo "== serial (default: fused bulk put)"; run serial 300 --steps 20 --warmup 3 ; }
 has overlap     && { echo "== two-chain step"; run overlap 200 --steps 20 --warmup 3 --no-e2e --overlap ; }
+has publish0    && { echo "== CF_PUBLISH_MODE=0 (round 1: every CTA fences and adds to every flag)"; CF_PUBLISH_MODE=0 run publish0 200 --steps 20 --warmup 3 --no-e2e ; }
 has publish1    && { echo "== CF_PUBLISH_MODE=1"; CF_PUBLISH_MODE=1 run publish1 200 --steps 20 --warmup 3 --no-e2e ; }
+has fence_sc    && { echo "== CF_PUBLISH_FENCE=sc"; CF_PUBLISH_FENCE=sc run fence_sc 200 --steps 20 --warmup 3 --no-e2e ; }
+has ring_lrq    && { echo "== CogVideoX ring, LOW_RANK_Q r=32 (the example's preset)"; run ring_lrq 400 --steps 3 --warmup 3 --no-e2e --workload cogvideox5b_ring --codec lowrankq32 ; }
+has lrq         && { echo "== FLUX, LOW_RANK_Q r=32"; run lrq 300 --steps 3 --warmup 3 --no-e2e --codec lowrankq32 ; }
 has nobulk      && { echo "== CF_PUT_BULK=0 (round-1 sub-word remote stores)"; CF_PUT_BULK=0 run nobulk 200 --steps 20 --warmup 3 --no-e2e ; }
 has dropin      && { echo "== drop-in hooks (compact_fwd per layer)"; run dropin 200 --steps 20 --warmup 3 --no-e2e --api dropin ; }
 has dropin_nccl && { echo "== drop-in hooks, NCCL transport"; run dropin_nccl 200 --steps 10 --warmup 3 --no-e2e --api dropin --transport nccl ; }
