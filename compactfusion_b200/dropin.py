@@ -80,6 +80,24 @@ def group_info(group):
     return info
 
 
+_fast: dict = {}       # (kind, group key, mod_idx, shape) -> (engine, layer, key view, value view)
+
+
+def lookup(kind: str, group, k: torch.Tensor, mod_idx, comp_rank=None):
+    """`get` plus the (bs, W s, h, d) attention views of the layer's global buffers, cached per layer (the buffers
+    are persistent: for bs == 1 the views never change; bs > 1 gathers per call, None here)."""
+    key = (kind, _group_key(group), mod_idx, k.shape)
+    ent = _fast.get(key)
+    if ent is None:
+        eng, layer = get(kind, group, k, mod_idx, comp_rank)
+        kv = None
+        if k.shape[0] == 1:
+            kv = (as_sequence(eng.global_k[layer], eng.world, k.shape), as_sequence(eng.global_v[layer], eng.world, k.shape))
+        ent = (eng, layer, kv)
+        _fast[key] = ent
+    return ent
+
+
 def get(kind: str, group, k: torch.Tensor, mod_idx, comp_rank=None):
     """(engine, dense layer index) for this hook / group / shard shape; `mod_idx` (any hashable the caller uses
     to name the layer) is mapped to the engine's own 0-based index in order of first appearance."""
@@ -127,6 +145,7 @@ def shutdown():
     _engines.clear()
     _cfg_ok.clear()
     _groups.clear()
+    _fast.clear()
 
 
 def engines():

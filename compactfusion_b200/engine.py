@@ -159,6 +159,7 @@ class PatchGatherEngine:
         # fused compress + put (cf_sign_compress_put): the codec kernels store the payload straight into every
         # rank's receive slot; CF_FUSED_PUT=0 keeps the separate put kernel (A/B)
         self.fused_put = os.environ.get("CF_FUSED_PUT", "1") != "0"
+        self._publish_kernel = os.environ.get("CF_PUBLISH_MODE", "2") == "2"  # flags published by k_publish_flags
         self._per_layer_send = False
         self._side = None  # second stream of the overlapped step
 
@@ -421,6 +422,8 @@ class PatchGatherEngine:
         `passes` selects individual kernels of the call (bench.py times them one by one)."""
         k2, v2 = k.reshape(self.n, self.c), v.reshape(self.n, self.c)
         xs, bases, nones, pk, us, vs, ws = self._compress_args(layer, k2, v2, ctype)
+        if passes == 0:  # argument arrays only (exchange's bound plan)
+            return
         rc = nv.lib().cf_sign_compress_passes(_CODEC[ctype] | self._flags, passes, 2, xs, bases, nones, pk, us, vs, self.n, self.c,
                                               ws.data_ptr(), ws.numel(), nv.stream_ptr())
         nv.check(rc, "cf_sign_compress_passes")
@@ -451,12 +454,14 @@ class PatchGatherEngine:
             self._ptr_cache[key] = args
         xs, bases, dst, flg, count_ptr, ws = args
         xs[0], xs[1] = k2.data_ptr(), v2.data_ptr()
+        if passes == 0:  # argument arrays only (exchange's bound plan)
+            return
         rc = nv.lib().cf_sign_compress_put(_CODEC[ctype] | self._flags, passes, 2, xs, bases, self.world, self.rank, dst, flg, count_ptr,
                                            st["ticket"].data_ptr(), self.n, self.c, ws.data_ptr(), ws.numel(),
                                            nv.stream_ptr())
         nv.check(rc, "cf_sign_compress_put")
         last = nv.PASS_FINALIZE if ctype == T.BINARY else nv.PASS_ENCODE
-        publish = 1 if (passes & last and os.environ.get("CF_PUBLISH_MODE", "2") == "2") else 0  # k_publish_flags
+        publish = 1 if (passes & last and self._publish_kernel) else 0  # k_publish_flags
         if ctype == T.BINARY:
             passes &= ~nv.PASS_ENCODE
         self.kernel_launches += bin(passes).count("1") + publish
@@ -578,9 +583,68 @@ class PatchGatherEngine:
         """One layer of one step; returns (global_k, global_v) ready for attention."""
         if ctype == T.WARMUP:
             return self.warmup(layer, k, v)
-        self.send(layer, k, v, ctype)
-        self.decompress(layer, ctype)
+        plan = self._ptr_cache.get(("plan", layer, ctype))
+        if plan is None:
+            plan = self._build_plan(layer, k, v, ctype)
+        plan(k, v)
         return self.global_k[layer], self.global_v[layer]
+
+    def _build_plan(self, layer, k, v, ctype):
+        """The per-(layer, codec) call sequence of `exchange` with every argument bound once: the hooks run it once
+        per attention layer per step with eager launches, so the host side of a layer is two C calls and a handful
+        of Python operations.  (Rebuilt whenever `_ptr_cache` is cleared: new stream, graph capture.)"""
+        self.freeze()
+        generic = ctype in _LOWRANK or type(self).decompress is not PatchGatherEngine.decompress
+        if not generic and self.fused(ctype):
+            self.compress_put(layer, k, v, ctype, passes=0)          # builds and caches the argument arrays
+            xs, bases, dst, flg, count_ptr, ws = self._ptr_cache[("cp", layer, ctype)]
+            st = self._p2p[ctype]
+            chunks = self._decompress_args_p2p(layer, ctype, st)
+            lib, codec = nv.lib(), _CODEC[ctype] | self._flags
+            put, dec = lib.cf_sign_compress_put, lib.cf_sign_decompress_batched_wait
+            W, rank, n, c = self.world, self.rank, self.n, self.c
+            ticket, err, ws_ptr, ws_n = st["ticket"].data_ptr(), st["error"].data_ptr(), ws.data_ptr(), ws.numel()
+            n_launch = (3 if ctype == T.BINARY else 4) + len(chunks) - (0 if self._publish_kernel else 1)
+            stream_ptr = nv.stream_ptr
+
+            def plan(k_, v_):
+                xs[0], xs[1] = k_.data_ptr(), v_.data_ptr()
+                sp = stream_ptr()
+                rc = put(codec, nv.PASS_ALL, 2, xs, bases, W, rank, dst, flg, count_ptr, ticket, n, c, ws_ptr, ws_n, sp)
+                if rc:
+                    nv.check(rc, "cf_sign_compress_put")
+                for cnt, pk, us, vs, bs, recon, flags in chunks:
+                    rc = dec(codec, cnt, pk, us, vs, bs, recon, flags, count_ptr, err, n, c, sp)
+                    if rc:
+                        nv.check(rc, "cf_sign_decompress_batched_wait")
+                self.kernel_launches += n_launch
+        elif not generic and self.world == 1:
+            self.compress(layer, k, v, ctype, passes=0)
+            xs, bases, nones, pk, us, vs, ws = self._ptr_cache[("c", layer, ctype)]
+            chunks = self._decompress_args(layer, ctype)
+            lib, codec = nv.lib(), _CODEC[ctype] | self._flags
+            comp, dec = lib.cf_sign_compress_passes, lib.cf_sign_decompress_batched_wait
+            n, c, ws_ptr, ws_n = self.n, self.c, ws.data_ptr(), ws.numel()
+            n_launch = (2 if ctype == T.BINARY else 3) + len(chunks)
+            stream_ptr = nv.stream_ptr
+
+            def plan(k_, v_):
+                xs[0], xs[1] = k_.data_ptr(), v_.data_ptr()
+                sp = stream_ptr()
+                rc = comp(codec, nv.PASS_ALL, 2, xs, bases, nones, pk, us, vs, n, c, ws_ptr, ws_n, sp)
+                if rc:
+                    nv.check(rc, "cf_sign_compress_passes")
+                for cnt, dpk, dus, dvs, bs, recon in chunks:
+                    rc = dec(codec, cnt, dpk, dus, dvs, bs, recon, None, None, None, n, c, sp)
+                    if rc:
+                        nv.check(rc, "cf_sign_decompress_batched_wait")
+                self.kernel_launches += n_launch
+        else:
+            def plan(k_, v_):
+                self.send(layer, k_, v_, ctype)
+                self.decompress(layer, ctype)
+        self._ptr_cache[("plan", layer, ctype)] = plan
+        return plan
 
     def check_errors(self):
         """Raise if a device-side flag wait timed out (a peer never delivered; the affected reconstructions were

@@ -51,10 +51,13 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
         if dropin.usable(compact_config(), ctype, k):
             # K and V of the layer through the persistent-buffer engine: one compress(+put) launch pair, one
             # reconstruct launch for all W origins, straight into the buffer attention reads (no cat for bs == 1)
-            eng, layer = dropin.get("patch", group, k, mod_idx, compact_config().comp_rank)
+            eng, layer, views = dropin.lookup("patch", group, k, mod_idx, compact_config().comp_rank)
             gk, gv = eng.exchange(layer, k, v, ctype)
-            key_to_use = dropin.as_sequence(gk, world_size, k.shape)
-            value_to_use = dropin.as_sequence(gv, world_size, v.shape)
+            if views is not None:
+                key_to_use, value_to_use = views
+            else:
+                key_to_use = dropin.as_sequence(gk, world_size, k.shape)
+                value_to_use = dropin.as_sequence(gv, world_size, v.shape)
         else:
             k_list = compact_all_gather(f"{mod_idx}-k", k, comp_type=ctype, group=group)
             v_list = compact_all_gather(f"{mod_idx}-v", v, comp_type=ctype, group=group)
