@@ -46,7 +46,7 @@ template <int RP>
 constexpr size_t lr_orth_smem() {
   return sizeof(float) * orth_chunk<RP>() * (RP + 2)      // row chunk
          + sizeof(float) * RP * RP                        // this CTA's partial Gram (read by the cluster)
-         + sizeof(float) * (RP * (RP + 1) + RP)           // G (+ pivots) for the factorisation
+         + sizeof(float) * (2 * RP * (RP + 1) + RP)       // G, its copy (+ pivots) for the factorisation
          + sizeof(float) * (RP * RP + RP) + 64;           // R (upper), 1 / diag, scalars
 }
 
@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   float* Xd = reinterpret_cast<float*>(orth_raw);                         // [kOrthChunk][kLdX]
   float* Gp = Xd + kOrthChunk * kLdX;                                     // [RP][RP] partial Gram of this CTA
   float (*G)[RP + 1] = reinterpret_cast<float (*)[RP + 1]>(Gp + RP * RP);
-  float* piv = reinterpret_cast<float*>(G) + RP * (RP + 1);
+  float (*Gc)[RP + 1] = reinterpret_cast<float (*)[RP + 1]>(reinterpret_cast<float*>(G) + RP * (RP + 1));
+  float* piv = reinterpret_cast<float*>(Gc) + RP * (RP + 1);
   float* Rs = piv + RP;                                                   // [RP][RP]
   float* Ds = Rs + RP * RP;                                               // [RP]
-  float* scal = Ds + RP;                                                  // [0]: trace(G)
+  float* scal = Ds + RP;                                                  // [0]: trace(G), [1]: well-conditioned?
   const int t = threadIdx.x, r = p.r, M = p.M;
   const uint32_t rank = cluster_ctarank();
   int rows_per = (M + NC - 1) / NC;
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     }
   };
   // partial Gram -> Gp; cluster-wide sum in rank order -> G (upper); (+ shift) Cholesky -> Rs, Ds
-  auto reduce_and_factor = [&](float shift_rel) {
+  bool well = false;   // set by the adaptive first factorisation
+  auto reduce_and_factor = [&](float shift_rel, bool adaptive) {
 #pragma unroll
     for (int q = 0; q < KB; ++q)
       if (bi[q] >= 0) {
@@ -205,17 +207,45 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     cluster_sync_all();   // all remote reads of Gp are done: it may be overwritten by the next pass
     __syncthreads();
     if (t == 0) {
-      float tr = 0.f;
-      for (int i = 0; i < r; ++i) tr += G[i][i];
+      float tr = 0.f, mx = 0.f;
+      for (int i = 0; i < r; ++i) {
+        tr += G[i][i];
+        mx = fmaxf(mx, G[i][i]);
+      }
       scal[0] = tr;
+      scal[2] = mx;
     }
     __syncthreads();
     const float tr = scal[0];
-    if (shift_rel > 0.f) {
+    const float floor_piv = fmaxf(tr, 1e-30f) * 1e-7f;
+    bool shifted = false;
+    if (adaptive) {
+      // first try the plain factorisation on a copy: if every pivot stays above 1 % of the largest diagonal entry,
+      // X is well conditioned (cond^2 <~ 100 r) and CholeskyQR2 is enough -- the caller then runs one pass less.
+      // Every CTA holds the same bits of G, so every CTA takes the same decision.
+      for (int e = t; e < RP * (RP + 1); e += 256) (&Gc[0][0])[e] = (&G[0][0])[e];
+      __syncthreads();
+      cholesky_upper_f32<RP>(G, piv, r, t, floor_piv);
+      if (t == 0) {
+        float mn = 3.4e38f;
+        for (int k = 0; k < r; ++k) mn = fminf(mn, 1.0f / (piv[k] * piv[k]));   // the pivots d_k
+        scal[1] = (mn >= 1e-2f * scal[2]) ? 1.f : 0.f;
+      }
+      __syncthreads();
+      well = scal[1] != 0.f;
+      if (!well) {   // ill conditioned: restore G, shift, factor again
+        for (int e = t; e < RP * (RP + 1); e += 256) (&G[0][0])[e] = (&Gc[0][0])[e];
+        __syncthreads();
+        shifted = true;
+      }
+    } else if (shift_rel > 0.f) {
+      shifted = true;
+    }
+    if (shifted) {
       if (t < r) G[t][t] += shift_rel * tr;
       __syncthreads();
     }
-    cholesky_upper_f32<RP>(G, piv, r, t, fmaxf(tr, 1e-30f) * 1e-7f);
+    if (!adaptive || shifted) cholesky_upper_f32<RP>(G, piv, r, t, floor_piv);
     for (int e = t; e < RP * RP; e += 256) {
       const int i = e / RP, j = e % RP;
       Rs[e] = (i < r && j < r && j >= i) ? G[i][j] * piv[i] : 0.f;
@@ -278,10 +308,13 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     __syncthreads();
     gram_chunk(rows);
   }
-  reduce_and_factor(1e-4f);   // shifted factorisation: always succeeds, leaves cond(X R1^-1) <= ~100
+  // well-conditioned X (the common case): plain factorisation, CholeskyQR2; otherwise the shifted factorisation,
+  // which always succeeds and leaves cond(X R1^-1) <= ~100, and one more pass (CholeskyQR3)
+  reduce_and_factor(1e-4f, true);
+  const int more_passes = well ? 1 : 2;
 
   // ---- passes 1 (second half) and 2: X <- X R^-1, Gram of the new X, plain Cholesky ----
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < more_passes; ++pass) {
     zero_acc();
     for (int mc = m_begin; mc < m_end; mc += kOrthChunk) {
       const int rows = min(kOrthChunk, m_end - mc);
@@ -299,10 +332,10 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
       __syncthreads();
       gram_chunk(rows);
     }
-    reduce_and_factor(0.f);
+    reduce_and_factor(0.f, false);
   }
 
-  // ---- pass 3 (second half): X <- X R3^-1, outputs ----
+  // ---- last pass (second half): X <- X R^-1, outputs ----
   for (int m = m_begin + t; m < m_end; m += 256) {
     float xr[RP];
     load_row(xr, m);

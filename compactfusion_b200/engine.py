@@ -160,6 +160,9 @@ class PatchGatherEngine:
         # rank's receive slot; CF_FUSED_PUT=0 keeps the separate put kernel (A/B)
         self.fused_put = os.environ.get("CF_FUSED_PUT", "1") != "0"
         self._publish_kernel = os.environ.get("CF_PUBLISH_MODE", "2") == "2"  # flags published by k_publish_flags
+        # per-layer pointer-keyed graphs for `exchange` (the hooks' path); the whole-step graph of `capture_step`
+        # does not need them
+        self._layer_graphs = os.environ.get("CF_LAYER_GRAPHS", "1") != "0"
         self._per_layer_send = False
         self._side = None  # second stream of the overlapped step
 
@@ -203,8 +206,8 @@ class PatchGatherEngine:
         if st is not None:
             return st
         W, L = self.world, self.layers
-        slot_bytes = 2 * self._numel(ctype) * 2
-        ok = slot_bytes % 16 == 0 and (self._numel(ctype) * 2) % 16 == 0
+        slot_bytes = 2 * self._pad_bytes(ctype)   # [K payload | V payload], each padded to a 16-byte multiple
+        ok = True
         flags_bytes = (L * W * 4 + 255) // 256 * 256
         total = flags_bytes + L * W * slot_bytes
         if self._local is not None:
@@ -280,9 +283,10 @@ class PatchGatherEngine:
         pn_bytes = self._numel(ctype) * 2
         st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
         if st:
-            return _device_bytes(self._slot(st, st["base"], layer, origin) + kv * pn_bytes, pn_bytes, self.device)
+            return _device_bytes(self._slot(st, st["base"], layer, origin) + kv * self._pad_bytes(ctype), pn_bytes,
+                                 self.device)
         _, recv = self._buffers(ctype, layer)
-        return recv[origin, kv].view(torch.uint8)
+        return recv[origin, kv].view(torch.uint8)[:pn_bytes]
 
     def _slot(self, st, region_base, layer, origin):
         return region_base + st["flags_bytes"] + (layer * self.world + origin) * st["slot_bytes"]
@@ -295,6 +299,11 @@ class PatchGatherEngine:
         return any(bool(st["error"].item()) for st in self._p2p.values() if st)
 
     # -- buffers ---------------------------------------------------------------------------
+    def _pad_bytes(self, ctype):
+        """Bytes one tensor's payload occupies in a send buffer / receive slot: the wire size rounded up to 16, so
+        that K's and V's payloads both start 16-byte aligned (bulk copies) whatever the shard length."""
+        return (self._numel(ctype) * 2 + 15) // 16 * 16
+
     def _numel(self, ctype):
         """fp16 elements of one tensor's wire payload."""
         if ctype in _LOWRANK:
@@ -313,8 +322,8 @@ class PatchGatherEngine:
         being compressed, so every layer gets its own buffer."""
         key = (ctype, layer) if self._per_layer_send else ctype
         if key not in self._send:
-            pn = self._numel(ctype)
-            self._payload_numel[ctype] = pn
+            self._payload_numel[ctype] = self._numel(ctype)
+            pn = self._pad_bytes(ctype) // 2   # padded: the buffers mirror the receive slots' layout
             self._send[key] = torch.empty((2, pn), dtype=torch.half, device=self.device)
             self._recv[key] = (self._send[key].view(1, 2, pn) if self.world == 1 else
                                torch.empty((self.world, 2, pn), dtype=torch.half, device=self.device))
@@ -323,7 +332,7 @@ class PatchGatherEngine:
     def _views(self, flat, ctype):
         per_byte = 8 if ctype == T.BINARY else 4
         qh = self.n * (self.c // per_byte) // 2
-        return flat[:qh], flat[qh:qh + self.n], flat[qh + self.n:]
+        return flat[:qh], flat[qh:qh + self.n], flat[qh + self.n:qh + self.n + self.c]
 
     def _shard(self, buf, r):
         return buf[r * self.n:(r + 1) * self.n]
@@ -372,7 +381,7 @@ class PatchGatherEngine:
         if args is None:
             per_byte = 8 if ctype == T.BINARY else 4
             code_bytes = self.n * (self.c // per_byte)
-            pn_bytes = self._numel(ctype) * 2
+            pn_bytes = self._pad_bytes(ctype)
             packed, us, vs, bases, flags = [], [], [], [], []
             for r in origins:
                 slot = self._slot(st, st["base"], layer, r)
@@ -444,7 +453,7 @@ class PatchGatherEngine:
         key = ("cp", layer, ctype)
         args = self._ptr_cache.get(key)
         if args is None:
-            W, pn_bytes = self.world, self._numel(ctype) * 2
+            W, pn_bytes = self.world, self._pad_bytes(ctype)
             bases = [self._shard(self.global_k[layer], self.rank), self._shard(self.global_v[layer], self.rank)]
             dst = (ctypes.c_void_p * (2 * W))(*[self._slot(st, st["peers"][q], layer, self.rank) + j * pn_bytes
                                                for j in range(2) for q in range(W)])
@@ -522,7 +531,8 @@ class PatchGatherEngine:
         for j, (x, glob) in enumerate(((k, self.global_k[layer]), (v, self.global_v[layer]))):
             x2, base, payload = x.reshape(n, c), self._shard(glob, self.rank), send[j]
             if ctype == T.LOW_RANK:
-                lowrank_project(x2, base, r, 2, u_out=payload[:n * r].view(n, r), v_out=payload[n * r:].view(r, c))
+                lowrank_project(x2, base, r, 2, u_out=payload[:n * r].view(n, r),
+                                v_out=payload[n * r:n * r + r * c].view(r, c))
             else:
                 u, vv, _ = lowrank_project(x2, base, r, 2)
                 parts = list(quantize_int4(u)) + list(quantize_int4(vv.t().contiguous()))
@@ -643,7 +653,53 @@ class PatchGatherEngine:
             def plan(k_, v_):
                 self.send(layer, k_, v_, ctype)
                 self.decompress(layer, ctype)
+        if not generic and self._layer_graphs:
+            plan = self._graphed(plan)
         self._ptr_cache[("plan", layer, ctype)] = plan
+        return plan
+
+    def _graphed(self, eager):
+        """Pointer-keyed CUDA graph of one layer's launches.  A model hands over K / V tensors from the caching
+        allocator, whose addresses usually repeat from step to step: when a layer sees the same two addresses a
+        third time, its eager launch sequence is captured once and replayed from then on (one launch instead of
+        four or five: the hooks' host time per layer drops below the GPU time); any other address runs -- and
+        re-arms -- the eager path.  `CF_LAYER_GRAPHS=0` switches it off."""
+        state = {"ptrs": None, "hits": 0, "graph": None, "n": 0}
+
+        def plan(k_, v_):
+            ptrs = (k_.data_ptr(), v_.data_ptr())
+            if ptrs == state["ptrs"]:
+                g = state["graph"]
+                if g is not None:
+                    g.replay()
+                    self.kernel_launches += state["n"]
+                    return
+                state["hits"] += 1
+                if state["hits"] >= 2:
+                    try:
+                        if torch.cuda.is_current_stream_capturing():
+                            raise RuntimeError("already inside a capture (the whole-step graph)")
+                        before = self.kernel_launches
+                        g = torch.cuda.CUDAGraph()
+                        cur = torch.cuda.current_stream()
+                        side = torch.cuda.Stream(device=self.device)
+                        side.wait_stream(cur)
+                        with torch.cuda.stream(side):
+                            g.capture_begin(capture_error_mode="thread_local")
+                            try:
+                                eager(k_, v_)
+                            finally:
+                                g.capture_end()
+                        cur.wait_stream(side)
+                        state["n"] = self.kernel_launches - before   # kernels per replay (this call's run below)
+                        state["graph"] = g
+                        g.replay()
+                        return
+                    except Exception:  # noqa: BLE001 -- a capture that cannot be taken leaves the eager path in place
+                        state["hits"] = -(1 << 30)
+            else:
+                state["ptrs"], state["hits"], state["graph"] = ptrs, 0, None
+            eager(k_, v_)
         return plan
 
     def check_errors(self):
