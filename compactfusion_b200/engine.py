@@ -659,23 +659,27 @@ class PatchGatherEngine:
         return plan
 
     def _graphed(self, eager):
-        """Pointer-keyed CUDA graph of one layer's launches.  A model hands over K / V tensors from the caching
-        allocator, whose addresses usually repeat from step to step: when a layer sees the same two addresses a
-        third time, its eager launch sequence is captured once and replayed from then on (one launch instead of
-        four or five: the hooks' host time per layer drops below the GPU time); any other address runs -- and
-        re-arms -- the eager path.  `CF_LAYER_GRAPHS=0` switches it off."""
-        state = {"ptrs": None, "hits": 0, "graph": None, "n": 0}
+        """Pointer-keyed CUDA graphs of one layer's launches.  A model hands over K / V tensors from the caching
+        allocator, whose addresses repeat from step to step (or rotate among a few): when a layer sees the same pair
+        of addresses a second time, its eager launch sequence is captured once for that pair and replayed from then
+        on (one launch instead of four or five: the hooks' host time per layer drops below the GPU time); an unknown
+        pair runs the eager path.  At most 8 graphs per layer; `CF_LAYER_GRAPHS=0` switches the mechanism off."""
+        seen, graphs, launches = {}, {}, {}
+        state = {"ok": True}
 
         def plan(k_, v_):
             ptrs = (k_.data_ptr(), v_.data_ptr())
-            if ptrs == state["ptrs"]:
-                g = state["graph"]
-                if g is not None:
-                    g.replay()
-                    self.kernel_launches += state["n"]
-                    return
-                state["hits"] += 1
-                if state["hits"] >= 2:
+            g = graphs.get(ptrs)
+            if g is not None:
+                g.replay()
+                self.kernel_launches += launches[ptrs]
+                return
+            if state["ok"]:
+                n_seen = seen.get(ptrs, 0) + 1
+                if len(seen) > 64:
+                    seen.clear()
+                seen[ptrs] = n_seen
+                if n_seen >= 2 and len(graphs) < 8:
                     try:
                         if torch.cuda.is_current_stream_capturing():
                             raise RuntimeError("already inside a capture (the whole-step graph)")
@@ -691,14 +695,12 @@ class PatchGatherEngine:
                             finally:
                                 g.capture_end()
                         cur.wait_stream(side)
-                        state["n"] = self.kernel_launches - before   # kernels per replay (this call's run below)
-                        state["graph"] = g
+                        launches[ptrs] = self.kernel_launches - before   # kernels per replay (this call: below)
+                        graphs[ptrs] = g
                         g.replay()
                         return
                     except Exception:  # noqa: BLE001 -- a capture that cannot be taken leaves the eager path in place
-                        state["hits"] = -(1 << 30)
-            else:
-                state["ptrs"], state["hits"], state["graph"] = ptrs, 0, None
+                        state["ok"] = False
             eager(k_, v_)
         return plan
 
