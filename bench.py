@@ -971,7 +971,13 @@ def main():
 
     if raw:
         mode = f"eager (uncompressed {args.raw_exchange})"
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    if dropin_api:
+        # the hooks capture one small CUDA graph per (layer, K/V address pair) at the second sighting of a pair
+        # (engine._graphed): walk the whole version pattern twice before the timed region, so that it measures the
+        # steady state of a denoising loop and not the one-time captures
+        n_warm = max(n_warm, 2 * len(pattern) + 1)
+    for i in range(n_warm):
         run_step(i)
     barrier()
     clocks = ClockSampler(local_rank)
@@ -1041,7 +1047,7 @@ def main():
         print(json.dumps({
             **({"impl": "uncompressed_baseline"} if raw else {}),
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "api": ("dropin (compact_fwd hooks, eager launches, attention stubbed out)"
                                                      if dropin_api else "engine (whole-step runtime)"),

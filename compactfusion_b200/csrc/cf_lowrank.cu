@@ -408,12 +408,18 @@ struct LrMmaPlan {
   int gram_ctas_c, gram_rows_c, gram_ctas_n, gram_rows_n;
   size_t q2_off, y2_off, xsum_off, part_off, gpart_off, rinv_off, ticket_off, total;
 };
+// CF_LR_GEMM=small: 32-wide K chunks, 2 stages (58 KB of shared memory: two CTAs per SM, twice the split-K factor)
+static bool lr_gemm_small() {
+  static const bool v = [] { const char* e = getenv("CF_LR_GEMM"); return e && e[0] == 's'; }();
+  return v;
+}
 static void lr_split_cfg(int64_t M, int64_t K, int* splits, int* kper) {
   const int64_t m_tiles = (M + kLrBM - 1) / kLrBM;
-  int64_t s = (static_cast<int64_t>(sm_count()) + m_tiles / 2) / m_tiles;  // ~one CTA per SM, one wave
+  const int64_t ctas = static_cast<int64_t>(sm_count()) * (lr_gemm_small() ? 2 : 1);
+  int64_t s = (ctas + m_tiles / 2) / m_tiles;  // ~one CTA per SM (two with the small tiles), one wave
   if (s < 1) s = 1;
   if (s > 16) s = 16;
-  int64_t kp = ((K + s - 1) / s + kLrBK - 1) / kLrBK * kLrBK;
+  int64_t kp = ((K + s - 1) / s + kLrBK - 1) / kLrBK * kLrBK;   // (a multiple of 64: fine for both chunk widths)
   *kper = static_cast<int>(kp);
   *splits = static_cast<int>((K + kp - 1) / kp);
 }
@@ -471,13 +477,25 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   //  the streamed operand, which is the larger half of the loop; kept as an opt-in for A/B: CF_LR_WARPS=16)
   static const bool wide = [] { const char* e = getenv("CF_LR_WARPS"); return e && e[0] == '1' && e[1] == '6'; }();
   const int gemm_threads = (RP >= 16 && wide) ? 2 * kLrThreads : kLrThreads;
+  const bool small = lr_gemm_small();
+  const size_t smem_ns = lr_gemm_smem<RP, false, 32, 2>(), smem_ts = lr_gemm_smem<RP, true, 32, 2>();
+  if (small) {
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ns)));
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ts)));
+  }
   auto gemm_AQ = [&]() {  // part[s] (N, RP) = A Q
     dim3 grid((n + kLrBM - 1) / kLrBM, p.aq_splits);
-    k_lr_gemm<RP, false><<<grid, gemm_threads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
+    if (small)
+      k_lr_gemm<RP, false, 32, 2><<<grid, kLrThreads, smem_ns, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
+    else
+      k_lr_gemm<RP, false><<<grid, gemm_threads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
   };
   auto gemm_AtY = [&]() {  // part[s] (C, RP) = A^T Y
     dim3 grid((c + kLrBM - 1) / kLrBM, p.aty_splits);
-    k_lr_gemm<RP, true><<<grid, gemm_threads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
+    if (small)
+      k_lr_gemm<RP, true, 32, 2><<<grid, kLrThreads, smem_ts, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
+    else
+      k_lr_gemm<RP, true><<<grid, gemm_threads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
   };
   // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies).
   // One launch on one 8-CTA cluster (k_lr_orth); CF_LR_ORTH=legacy keeps round 1's five-launch chain (A/B).

@@ -86,17 +86,17 @@ __global__ void __launch_bounds__(256) k_lr_pad_split(const float* __restrict__ 
 //    TRANS: A' = A^T    (M = C, K = N)      Z = A^T Y
 // B2 = B pre-split into {hi, lo} TF32 pairs, (K, RP) row-major.   grid (ceil(M/128), splits), block 256
 // ---------------------------------------------------------------------------------------
-template <int RP, bool TRANS>
+template <int RP, bool TRANS, int BK = kLrBK, int STAGES = kLrStages>
 __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __restrict__ x, const __half* __restrict__ base,
                                                 const float2* __restrict__ B2, float* __restrict__ out, int N, int C,
                                                 int k_per_split) {
   extern __shared__ __align__(128) unsigned char lr_smem_raw[];
   constexpr int kLdB = RP + 2;                               // float2 pitch: conflict-free 64-bit fragment loads
   // fp16 tile as stored in global memory: !TRANS 128 (m) x 64 (k), pitch 72;  TRANS 64 (k) x 128 (m), pitch 136
-  constexpr int kRowsA = TRANS ? kLrBK : kLrBM, kColsA = TRANS ? kLrBM : kLrBK;
+  constexpr int kRowsA = TRANS ? BK : kLrBM, kColsA = TRANS ? kLrBM : BK;
   constexpr int kLdA = kColsA + 8;
   constexpr int kTileA = kRowsA * kLdA * 2;                  // bytes
-  constexpr int kTileB = kLrBK * kLdB * 8;
+  constexpr int kTileB = BK * kLdB * 8;
   constexpr int kStage = 2 * kTileA + kTileB;
   const int M = TRANS ? C : N, K = TRANS ? N : C;
   const int m0 = blockIdx.x * kLrBM;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
       cp_async16(xs + r * kLdA + 8 * cc, x + off, ok);
       if (has_base) cp_async16(bs + r * kLdA + 8 * cc, base + off, ok);
     }
-    constexpr int kChunksB = kLrBK * RP / 2;  // 16-byte chunks = 2 float2
+    constexpr int kChunksB = BK * RP / 2;  // 16-byte chunks = 2 float2
     for (int ch = tid; ch < kChunksB; ch += nthreads) {
       const int r = ch / (RP / 2), cc = ch % (RP / 2);
       const bool ok = k0 + r < k_end;
@@ -144,26 +144,26 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 
-  const int nchunks = (k_end - k_begin + kLrBK - 1) / kLrBK;
+  const int nchunks = (k_end - k_begin + BK - 1) / BK;
 #pragma unroll
-  for (int s0 = 0; s0 < kLrStages - 1; ++s0) {  // prologue: always commit, so group accounting stays uniform
-    if (s0 < nchunks) issue(s0, k_begin + s0 * kLrBK);
+  for (int s0 = 0; s0 < STAGES - 1; ++s0) {  // prologue: always commit, so group accounting stays uniform
+    if (s0 < nchunks) issue(s0, k_begin + s0 * BK);
     cp_async_commit();
   }
   for (int it = 0; it < nchunks; ++it) {
-    cp_async_wait<kLrStages - 2>();  // chunk `it` has landed (for this thread's copies)
+    cp_async_wait<STAGES - 2>();  // chunk `it` has landed (for this thread's copies)
     __syncthreads();                 // ... for everyone's; and everyone is done with the stage refilled below
     {
-      const int nx = it + kLrStages - 1;
-      if (nx < nchunks) issue(nx % kLrStages, k_begin + nx * kLrBK);
+      const int nx = it + STAGES - 1;
+      if (nx < nchunks) issue(nx % STAGES, k_begin + nx * BK);
       cp_async_commit();
     }
-    unsigned char* sp = stage_ptr(it % kLrStages);
+    unsigned char* sp = stage_ptr(it % STAGES);
     const __half* xs = reinterpret_cast<const __half*>(sp);
     const __half* bs = reinterpret_cast<const __half*>(sp + kTileA);
     const float2* Bs = reinterpret_cast<const float2*>(sp + 2 * kTileA);
 #pragma unroll
-    for (int kk = 0; kk < kLrBK / 16; ++kk) {
+    for (int kk = 0; kk < BK / 16; ++kk) {
       uint32_t fx[4], fb[4];
       const int mi = lane >> 3, l8 = lane & 7;
       int srow, scol;
@@ -225,10 +225,10 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
   }
 }
 
-template <int RP, bool TRANS>
+template <int RP, bool TRANS, int BK = kLrBK, int STAGES = kLrStages>
 constexpr size_t lr_gemm_smem() {
-  constexpr size_t rows = TRANS ? kLrBK : kLrBM, cols = TRANS ? kLrBM : kLrBK;
-  return kLrStages * (2 * rows * (cols + 8) * 2 + static_cast<size_t>(kLrBK) * (RP + 2) * 8);
+  constexpr size_t rows = TRANS ? BK : kLrBM, cols = TRANS ? kLrBM : BK;
+  return STAGES * (2 * rows * (cols + 8) * 2 + static_cast<size_t>(BK) * (RP + 2) * 8);
 }
 
 // ---------------------------------------------------------------------------------------

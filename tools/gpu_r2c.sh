@@ -34,6 +34,7 @@ if has lowrank; then
   echo "-- CF_LR_ORTH=legacy lowrank --rank 32" >> $OUT/${TAG}_kernel_times.md; CF_LR_ORTH=legacy timeout 120 python tools/kernel_times.py lowrank --rank 32 2>&1 | grep -v Warn >> $OUT/${TAG}_kernel_times.md
   cat $OUT/${TAG}_kernel_times.md | grep -v "^$" | head -80
 fi
+has gemmsmall && { echo "-- CF_LR_GEMM=small lowrank --rank 32" >> $OUT/${TAG}_kernel_times.md; CF_LR_GEMM=small timeout 120 python tools/kernel_times.py lowrank --rank 32 2>&1 | grep -v Warn | tee -a $OUT/${TAG}_kernel_times.md | head -8; }
 has codecs && { for args in "codec --codec int4" "codec --codec sparse"; do echo "-- $args" >> $OUT/${TAG}_kernel_times.md; timeout 120 python tools/kernel_times.py $args 2>&1 | grep -v Warn | tee -a $OUT/${TAG}_kernel_times.md; done; }
 if has sweep; then
   echo "== sweep"
