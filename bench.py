@@ -59,6 +59,10 @@ WORKLOADS = {
                                   what="PixArt-alpha 1024^2 patch parallel"),
     "sd3_patch_parallel": dict(layers=24, rows=2 * 4096, ch=1536, mode="patch", bs=2, heads=24,
                                what="SD3-medium 1024^2 patch parallel"),
+    # BASELINE configs[0]: residual compress / decompress round trip, INT4 + error feedback, one 4096 x 3072 tensor,
+    # 28 steps, world size 1 (the reference's CPU-runnable case; here on the GPU through the plugin API)
+    "config1_int4_roundtrip": dict(layers=1, rows=4096, ch=3072, mode="roundtrip", bs=1, heads=24,
+                                   what="INT4 residual round trip with error feedback, 4096x3072, 28 steps"),
 }
 
 
@@ -78,7 +82,7 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--codec", default="binary", choices=["binary", "int2", "raw", "lowrank8", "lowrank32", "lowrankq32"],
+    p.add_argument("--codec", default="binary", choices=["binary", "int2", "int4", "raw", "lowrank8", "lowrank32", "lowrankq32"],
                    help="raw = the uncompressed exchange of the same K/V (NCCL all-gather of fp16 shards, what "
                         "xDiT does without the plugin): a comparison line, none of our kernels run")
     p.add_argument("--raw-exchange", default="allgather", choices=["allgather", "ring", "async"],
@@ -265,7 +269,8 @@ class CpuSample:
             warm = lambda key, x: cm.compact_decompress(key, x, self.warm, x.shape, update_cache=True)  # noqa: E731
         else:
             from oracle.state import OracleCompact
-            oc = OracleCompact(residual=1, ef=True, fastpath=not lowrank, comp_rank=rank_r)
+            fast = codec in ("binary", "int2")
+            oc = OracleCompact(residual=1, ef=True, fastpath=fast, simulate=(codec == "int4"), comp_rank=rank_r)
             self._compress = lambda key, x: oc.compress(key, x, value, update_cache=False)
             self._decompress = lambda key, p, shape: oc.decompress(key, p, value, shape, update_cache=True)
             warm = lambda key, x: oc.decompress(key, x, "warmup", x.shape, update_cache=True)  # noqa: E731
@@ -839,6 +844,70 @@ def measure_lowrank(args, eng, ks, vs, ctype, world, layers, barrier):
             "kernels": kernels, "method": "each phase of a layer (several launches) over all layers, eager, CUDA events"}
 
 
+def run_config1(args, device):
+    """BASELINE configs[0] on one GPU: `compact_compress` (INT4, residual 1, error feedback, cache update) +
+    `compact_decompress` on the receiver's key, per step, through the plugin API (`main.py:169,322`); x_t = x_0 +
+    0.05 t randn, step 0 is WARMUP.  One "step" of the JSON line = one denoising step of this
+    one-tensor workload; the timed region is steps 1..27 of a 28-step series, repeated `--steps` times."""
+    import compactfusion_b200 as cf
+    from compactfusion_b200.quality import error_stats
+    T = cf.COMPACT_COMPRESS_TYPE
+    n, c, series = SEQ, CH, 28
+    g = torch.Generator(device=device).manual_seed(0)
+    x0 = torch.randn(n, c, generator=g, device=device)
+    xs = [(x0 + 0.05 * t * torch.randn(n, c, generator=g, device=device)).half().view(1, n, 24, c // 24) for t in range(series)]
+    cf.compact_init(cf.CompactConfig(enabled=True, residual=1, ef=True, simulate=False, comp_rank=-1,
+                                     compress_func=lambda l, s: T.INT4 if s >= 1 else T.WARMUP))
+
+    def one_series():
+        for t in range(series):
+            ct = T.INT4 if t >= 1 else T.WARMUP
+            p = cf.compact_compress("0-0-k", xs[t], ct, update_cache=True)
+            rec = cf.compact_decompress("1-0-k", p, ct, xs[t].shape, update_cache=True)
+        return rec
+
+    for _ in range(max(args.warmup, 3)):
+        one_series()
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        rec = one_series()
+    b.record()
+    torch.cuda.synchronize()
+    ms_step = a.elapsed_time(b) / (args.steps * (series - 1))   # per compressed step (27 of the 28 are compressed)
+    clock_info = clocks.stop()
+    fid = error_stats(rec.reshape(n, c), xs[-1].reshape(n, c))
+    same = bool(torch.equal(cf.compact_cache().get_base("0-0-k").reshape(n, c), cf.compact_cache().get_base("1-0-k").reshape(n, c)))
+    e = n * c
+    algo = (6 * e + e // 2 + 4 * c) + (4 * e + e // 2 + 4 * c)   # compress+EF, decompress+update (SURVEY 8d)
+    peak, peak_src = measured_hbm_peak()
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline("int4", 1, 1, 1, budget_s=8.0)
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+    print(json.dumps({
+        "metric": METRIC, "value": 2 * e / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps * (series - 1),
+        "warmup": max(args.warmup, 3) * series, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "api": "plugin (compact_compress / compact_decompress, eager launches)", "codec": "int4",
+                   "layers": 1, "seq": n, "channels": c, "world": 1, "series_steps": series, "launch_mode": "eager",
+                   "l2": "one 25 MB tensor + its two cached bases per step: L2-resident by construction of configs[0]"},
+        "roofline": {"bound": "hbm", "achieved": algo / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "cf_int4_compress (+EF) + cf_int4_decompress: the step's 5 kernels + payload cat",
+                     "algorithmic_bytes_per_launch": algo, "avg_launch_us": ms_step * 1e3},
+        "cpu_baseline": cpu, "e2e": None, "gpu_launches": args.steps * (series - 1) * 5, "clocks": clock_info,
+        "fidelity": {"rel_l2": fid["rel_l2"], "max_abs": fid["max_abs"], "psnr_db": fid["psnr_db"], "finite": True},
+        "parity_ok": bool(same and fid["rel_l2"] < 0.05),
+        "ranks_identical": {"ok": same, "what": "sender cache == receiver cache after 28 steps (bit-exact)"},
+    }))
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -848,6 +917,9 @@ def main():
         faulthandler.dump_traceback_later(args.hang_dump, exit=True)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.layers = select_workload(args.workload, args.layers)
+    if MODE == "roundtrip":
+        args.codec = "int4"   # configs[0] names its codec
+    assert args.codec != "int4" or MODE == "roundtrip", "--codec int4 is the config1_int4_roundtrip workload's codec"
     if args.impl == "reference":
         run_reference(args, max(world, args.gpus), rank)
         return
@@ -856,6 +928,13 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    if MODE == "roundtrip":
+        assert world == 1, "configs[0] is a world-size-1 workload"
+        from compactfusion_b200 import build as cf_build
+        if not os.path.exists(cf_build.OUT):
+            cf_build.build()
+        run_config1(args, device)
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     elif args.api == "dropin":

@@ -46,6 +46,8 @@ SYMBOLS = {
     "cf_topk_decompress": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_void_p]),
     "cf_lowrank_project": (c_int, [c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cf_lowrank_reconstruct": (c_int, [c_void_p] * 4 + [c_int64, c_int64, c_int, c_void_p]),
+    "cf_lowrank_q_pack": (c_int, [c_void_p] * 3 + [c_int64, c_int64, c_int, c_void_p]),
+    "cf_lowrank_q_reconstruct": (c_int, [c_void_p] * 3 + [c_int64, c_int64, c_int, c_void_p]),
     "cf_ipc_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "cf_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "cf_ipc_close": (c_int, [c_void_p]),

@@ -76,3 +76,32 @@ def lowrank_reconstruct(u: torch.Tensor, v: torch.Tensor, base: torch.Tensor | N
                                          r, nv.stream_ptr())
     nv.check(rc, "cf_lowrank_reconstruct")
     return out
+
+
+def lowrank_q_reconstruct(payload: torch.Tensor, n: int, c: int, rank: int, base: torch.Tensor | None = None,
+                          out: torch.Tensor | None = None) -> torch.Tensor:
+    """base + fp16(deq(qU) deq(qV^T)^T) straight from a LOW_RANK_Q wire payload (slowpath.py:69-75): the int4
+    decode of both factors, the transpose and the product of slowpath_decompress (slowpath.py:156-164) plus the
+    residual add, in one launch."""
+    want = (n * rank + c * rank) // 4 + 4 * rank
+    assert payload.dtype == torch.half and payload.is_contiguous() and payload.numel() >= want, "not a LOW_RANK_Q payload"
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.half, device=payload.device)
+    rc = nv.lib().cf_lowrank_q_reconstruct(nv.ptr(payload), nv.ptr(base), nv.ptr(out), n, c, rank, nv.stream_ptr())
+    nv.check(rc, "cf_lowrank_q_reconstruct")
+    return out
+
+
+def lowrank_q_pack(u: torch.Tensor, v: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """U (N, r), V (r, C) fp16 -> the LOW_RANK_Q payload [qU, sU, mU, qV^T, sV, mV] (slowpath.py:62-75) as flat fp16:
+    quantize_int4 of U and of V^T (never formed) and the concatenation, in two launches."""
+    n, r = u.shape
+    c = v.shape[1]
+    assert v.shape[0] == r and u.dtype == torch.half and v.dtype == torch.half
+    numel = (n * r + c * r) // 4 + 4 * r
+    if out is None:
+        out = torch.empty(numel, dtype=torch.half, device=u.device)
+    assert out.dtype == torch.half and out.is_contiguous() and out.numel() >= numel
+    rc = nv.lib().cf_lowrank_q_pack(nv.ptr(u.contiguous()), nv.ptr(v.contiguous()), nv.ptr(out), n, c, r, nv.stream_ptr())
+    nv.check(rc, "cf_lowrank_q_pack")
+    return out[:numel]

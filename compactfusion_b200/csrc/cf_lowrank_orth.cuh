@@ -440,4 +440,110 @@ __global__ void __launch_bounds__(128, 3) k_lr_reconstruct_v2(const __half* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// LOW_RANK_Q decode fused into the reconstruct: recon = base + fp16(deq(qU) deq(qV^T)^T) straight from the wire
+// payload [qU (N/2, r) u8 | sU (r) | mU (r) | qV^T (C/2, r) u8 | sV (r) | mV (r)] (slowpath.py:69-75, :156-164).
+// The per-call path decodes U and V^T with two int4 kernels, transposes V^T, copies it, and then reconstructs:
+// ~10 launches per tensor, 117 us each in the 2-GPU FLUX run.  Here the tile loaders of k_lr_reconstruct_v2 read
+// the packed nibbles themselves: a 64-row tile of U is 32 x r contiguous bytes, a 128-column slab of V is
+// 64 x r contiguous bytes of qV^T.  value = fp16(fp16(code * scale) + min) (compress_quantize.py:636), per column
+// of U / of V^T, i.e. per k.      grid (ceil(C / 128), ceil(N / 64)), block 128; N and C even.
+// ---------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(128, 3) k_lrq_reconstruct(const uint8_t* __restrict__ qU, const __half* __restrict__ sU,
+                                                           const __half* __restrict__ mU, const uint8_t* __restrict__ qVt,
+                                                           const __half* __restrict__ sV, const __half* __restrict__ mV,
+                                                           const __half* __restrict__ base, __half* __restrict__ recon,
+                                                           int N, int C, int r) {
+  constexpr int KP = KS * 16, BN = 128;
+  constexpr int kLdU = KP + 8, kLdV = BN + 8;
+  __shared__ __align__(16) __half Us[64 * kLdU];
+  __shared__ __align__(16) __half Vs[(KP > 64 ? KP : 64) * kLdV];   // reused as the fp16 product tile [64][kLdV]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int c0 = blockIdx.x * BN, n0 = blockIdx.y * 64;
+  const __half zero = __float2half_rn(0.f);
+  // this warp's 16 rows x 128 columns of base first: in flight while the nibbles are decoded
+  uint4 bq[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = lane + 32 * q;
+    const int n = n0 + 16 * warp + i / (BN / 8), c = c0 + 8 * (i % (BN / 8));
+    bq[q] = make_uint4(0, 0, 0, 0);
+    if (base != nullptr && n < N && c < C) bq[q] = ldg_stream(base + static_cast<size_t>(n) * C + c);
+  }
+  auto deq = [](uint32_t code, __half sc, __half mn) {
+    return __hadd_rn(__hmul_rn(__ushort2half_rn(static_cast<unsigned short>(code)), sc), mn);
+  };
+  for (int i = tid; i < 32 * KP; i += 128) {   // U: row pair rp, column k
+    const int rp = i / KP, k = i % KP;
+    const int n = n0 + 2 * rp;
+    __half lo = zero, hi = zero;
+    if (k < r && n < N) {
+      const uint32_t b = qU[(static_cast<size_t>(n) >> 1) * r + k];
+      const __half sc = sU[k], mn = mU[k];
+      lo = deq(b & 0xFu, sc, mn);
+      hi = deq(b >> 4, sc, mn);
+    }
+    Us[(2 * rp) * kLdU + k] = lo;
+    Us[(2 * rp + 1) * kLdU + k] = hi;
+  }
+  for (int i = tid; i < (BN / 2) * KP; i += 128) {   // V: column pair cp, row k
+    const int cp = i / KP, k = i % KP;
+    const int c = c0 + 2 * cp;
+    __half lo = zero, hi = zero;
+    if (k < r && c < C) {
+      const uint32_t b = qVt[(static_cast<size_t>(c) >> 1) * r + k];
+      const __half sc = sV[k], mn = mV[k];
+      lo = deq(b & 0xFu, sc, mn);
+      hi = deq(b >> 4, sc, mn);
+    }
+    *reinterpret_cast<__half2*>(Vs + k * kLdV + 2 * cp) = __halves2half2(lo, hi);
+  }
+  __syncthreads();
+  float acc[BN / 8][4];
+#pragma unroll
+  for (int j = 0; j < BN / 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const int mi = lane >> 3, l8 = lane & 7;
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    uint32_t a[4];
+    ldmatrix_x4(a, Us + (16 * warp + l8 + (mi & 1) * 8) * kLdU + 16 * kk + (mi >> 1) * 8);
+#pragma unroll
+    for (int j2 = 0; j2 < BN / 16; ++j2) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, Vs + (16 * kk + l8 + (mi & 1) * 8) * kLdV + 16 * j2 + (mi >> 1) * 8);
+      mma_f16(acc[2 * j2], a, b[0], b[1]);
+      mma_f16(acc[2 * j2 + 1], a, b[2], b[3]);
+    }
+  }
+  __syncthreads();
+  __half* Ps = Vs;
+#pragma unroll
+  for (int j = 0; j < BN / 8; ++j) {
+    const int col = 8 * j + 2 * t;
+    *reinterpret_cast<__half2*>(Ps + (16 * warp + g) * kLdV + col) = __floats2half2_rn(acc[j][0], acc[j][1]);
+    *reinterpret_cast<__half2*>(Ps + (16 * warp + g + 8) * kLdV + col) = __floats2half2_rn(acc[j][2], acc[j][3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = lane + 32 * q;
+    const int rr = 16 * warp + i / (BN / 8), cc = i % (BN / 8);
+    const int n = n0 + rr, c = c0 + 8 * cc;
+    if (n >= N || c >= C) continue;
+    const H8 pr = as_h8(*reinterpret_cast<const uint4*>(Ps + rr * kLdV + 8 * cc));
+    H8 o = pr;
+    if (base != nullptr) {
+      const H8 b = as_h8(bq[q]);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) o.w[w] = h22u(__hadd2_rn(u2h2(b.w[w]), u2h2(pr.w[w])));
+    }
+    stg_stream(recon + static_cast<size_t>(n) * C + c, as_u4(o));
+  }
+}
+
 }  // namespace cf

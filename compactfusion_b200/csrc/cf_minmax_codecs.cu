@@ -468,6 +468,66 @@ __global__ void __launch_bounds__(256) k_int4_codec_generic(const __half* __rest
   }
 }
 
+// ---- LOW_RANK_Q wire packing (slowpath.py:62-75): int4 per column of U (N, r) and per column of V^T --------
+// The per-call path runs quantize_int4(U), V.t().contiguous(), quantize_int4(V^T) and six copies into the payload
+// (~14 launches per tensor).  V^T is never formed here: column k of V^T is row k of V (r, C), and the row pairs
+// (2i, 2i + 1) of V^T that share a byte are the column pairs of V.  Same finalize / code arithmetic as above.
+__global__ void __launch_bounds__(256) k_lrq_minmax(const __half* __restrict__ U, const __half* __restrict__ V, int N, int C,
+                                                    int r, __half* __restrict__ sU, __half* __restrict__ mU,
+                                                    __half* __restrict__ sV, __half* __restrict__ mV) {
+  __shared__ __half smn[256], smx[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const bool is_u = b < r;
+  const int k = is_u ? b : b - r;
+  __half mn = __ushort_as_half(0x7C00), mx = __ushort_as_half(0xFC00);
+  if (is_u) {
+    for (int n = t; n < N; n += 256) {
+      const __half d = U[static_cast<size_t>(n) * r + k];
+      mn = __hmin(mn, d);
+      mx = __hmax(mx, d);
+    }
+  } else {
+    for (int c = t; c < C; c += 256) {
+      const __half d = V[static_cast<size_t>(k) * C + c];
+      mn = __hmin(mn, d);
+      mx = __hmax(mx, d);
+    }
+  }
+  smn[t] = mn; smx[t] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) { smn[t] = __hmin(smn[t], smn[t + o]); smx[t] = __hmax(smx[t], smx[t + o]); }
+    __syncthreads();
+  }
+  if (t == 0) finalize_column<MODE_INT4>(smn[0], smx[0], k, is_u ? sU : sV, is_u ? mU : mV, nullptr);
+}
+
+__global__ void __launch_bounds__(256) k_lrq_encode(const __half* __restrict__ U, const __half* __restrict__ V, int N, int C,
+                                                    int r, const __half* __restrict__ sU, const __half* __restrict__ mU,
+                                                    const __half* __restrict__ sV, const __half* __restrict__ mV,
+                                                    uint8_t* __restrict__ qU, uint8_t* __restrict__ qVt) {
+  const size_t nu = static_cast<size_t>(N / 2) * r, nv = static_cast<size_t>(C / 2) * r;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nu + nv;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (i < nu) {
+      const int pi = static_cast<int>(i / r), k = static_cast<int>(i % r);
+      const __half s = sU[k], mn = mU[k];
+      const uint32_t q0 = int4_code<15>(U[static_cast<size_t>(2 * pi) * r + k], mn, s);
+      const uint32_t q1 = int4_code<15>(U[static_cast<size_t>(2 * pi + 1) * r + k], mn, s);
+      qU[i] = static_cast<uint8_t>(q0 | (q1 << 4));
+    } else {
+      // consecutive threads take consecutive column pairs of V (coalesced 4-byte reads); the byte lands at
+      // qV^T[cp][k]
+      const size_t j = i - nu;
+      const int k = static_cast<int>(j / (C / 2)), cp = static_cast<int>(j % (C / 2));
+      const __half s = sV[k], mn = mV[k];
+      const uint32_t d = *reinterpret_cast<const uint32_t*>(V + static_cast<size_t>(k) * C + 2 * cp);
+      const uint32_t q0 = int4_code<15>(lo_h(d), mn, s), q1 = int4_code<15>(hi_h(d), mn, s);
+      qVt[static_cast<size_t>(cp) * r + k] = static_cast<uint8_t>(q0 | (q1 << 4));
+    }
+  }
+}
+
 template <bool ENCODE>
 __global__ void __launch_bounds__(256) k_int8_codec_generic(const __half* __restrict__ x, const __half* __restrict__ base,
                                                             const __half* __restrict__ scale, const int16_t* __restrict__ zpv,
@@ -734,6 +794,32 @@ int cf_int2mm_compress(const void* x, const void* base, void* new_base, void* pa
   return cf::minmax_compress<cf::MODE_INT2MM>(x, base, new_base, packed, scale, minv, N, C, workspace,
                                               workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+int cf_lowrank_q_pack(const void* U, const void* V, void* payload, int64_t N, int64_t C, int rank, cf_stream_t stream) {
+  using namespace cf;
+  CF_CHECK_ARG(U && V && payload, "null pointer");
+  CF_CHECK_ARG(rank >= 1 && rank <= 64, "rank %d out of range [1, 64]", rank);
+  CF_CHECK_ARG(N >= 2 && N % 2 == 0 && C >= 2 && C % 2 == 0, "N and C must be even");
+  CF_CHECK_ARG((N / 2 * rank) % 2 == 0 && (C / 2 * rank) % 2 == 0, "N * rank and C * rank must be multiples of 4 (fp16 payload)");
+  CF_CHECK_ARG(reinterpret_cast<uintptr_t>(V) % 4 == 0 && reinterpret_cast<uintptr_t>(payload) % 2 == 0, "V must be 4-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* p = static_cast<uint8_t*>(payload);
+  const size_t qu_bytes = static_cast<size_t>(N / 2) * rank, qv_bytes = static_cast<size_t>(C / 2) * rank;
+  uint8_t* qU = p;
+  __half* sU = reinterpret_cast<__half*>(p + qu_bytes);
+  __half* mU = sU + rank;
+  uint8_t* qVt = reinterpret_cast<uint8_t*>(mU + rank);
+  __half* sV = reinterpret_cast<__half*>(qVt + qv_bytes);
+  __half* mV = sV + rank;
+  const __half* u = static_cast<const __half*>(U);
+  const __half* v = static_cast<const __half*>(V);
+  k_lrq_minmax<<<2 * rank, 256, 0, st>>>(u, v, static_cast<int>(N), static_cast<int>(C), rank, sU, mU, sV, mV);
+  CF_CHECK_LAUNCH();
+  k_lrq_encode<<<generic_grid(qu_bytes + qv_bytes), 256, 0, st>>>(u, v, static_cast<int>(N), static_cast<int>(C), rank, sU, mU, sV,
+                                                                 mV, qU, qVt);
+  CF_CHECK_LAUNCH();
+  return CF_OK;
+}
+
 int cf_int4_decompress(const void* packed, const void* scale, const void* minv, const void* base, void* recon,
                        int64_t N, int64_t C, cf_stream_t stream) {
   return cf::minmax_decompress<cf::MODE_INT4>(packed, scale, minv, base, recon, N, C,

@@ -162,7 +162,11 @@ class PatchGatherEngine:
         self._publish_kernel = os.environ.get("CF_PUBLISH_MODE", "2") == "2"  # flags published by k_publish_flags
         # per-layer pointer-keyed graphs for `exchange` (the hooks' path); the whole-step graph of `capture_step`
         # does not need them
-        self._layer_graphs = os.environ.get("CF_LAYER_GRAPHS", "1") != "0"
+        # (opt-in, CF_LAYER_GRAPHS=1: measured SLOWER than eager launches on a B200 -- 3.46 vs 2.50 ms per FLUX step
+        #  through the hooks at N = 1, profiles/r2_bench_n1_dropin_layer_graphs.json: a graph per layer gives up the
+        #  programmatic-dependent-launch overlap between consecutive layers' kernels, which is worth more than the
+        #  three launches it saves)
+        self._layer_graphs = os.environ.get("CF_LAYER_GRAPHS", "0") == "1"
         self._per_layer_send = False
         self._side = None  # second stream of the overlapped step
 
@@ -524,8 +528,7 @@ class PatchGatherEngine:
     def _lowrank_compress(self, layer, k, v, ctype):
         """K and V -> [U | V] (LOW_RANK) or [qU, sU, mU, qV^T, sV, mV] (LOW_RANK_Q: int4 per column of U and of
         V^T, slowpath.py:62-75) in the send buffer; the projector subtracts the cached base on the fly."""
-        from .compress_lowrank import lowrank_project
-        from .compress_quantize import quantize_int4
+        from .compress_lowrank import lowrank_project, lowrank_q_pack
         n, c, r = self.n, self.c, self.comp_rank
         send, _ = self._buffers(ctype, layer)
         for j, (x, glob) in enumerate(((k, self.global_k[layer]), (v, self.global_v[layer]))):
@@ -535,12 +538,7 @@ class PatchGatherEngine:
                                 v_out=payload[n * r:n * r + r * c].view(r, c))
             else:
                 u, vv, _ = lowrank_project(x2, base, r, 2)
-                parts = list(quantize_int4(u)) + list(quantize_int4(vv.t().contiguous()))
-                off = 0
-                for p_ in parts:
-                    flat = p_.contiguous().view(torch.half).reshape(-1) if p_.dtype != torch.half else p_.reshape(-1)
-                    payload[off:off + flat.numel()].copy_(flat)
-                    off += flat.numel()
+                lowrank_q_pack(u, vv, out=payload)
             self.kernel_launches += 1
 
     def _lowrank_payload(self, layer, origin, ctype, kv):
@@ -550,8 +548,7 @@ class PatchGatherEngine:
     def _lowrank_decompress(self, layer, ctype, origins=None):
         """recon = base + U V for the given origins, in place in the global buffers; with the one-sided transport a
         one-warp kernel (cf_p2p_wait) first holds the stream until those origins' flags are up."""
-        from .compress_lowrank import lowrank_reconstruct
-        from .compress_quantize import dequantize_int4
+        from .compress_lowrank import lowrank_q_reconstruct, lowrank_reconstruct
         origins = tuple(range(self.world)) if origins is None else tuple(origins)
         n, c, r = self.n, self.c, self.comp_rank
         st = self._p2p.get(ctype) if (self.transport == "p2p" and self.world > 1) else None
@@ -565,14 +562,9 @@ class PatchGatherEngine:
             for j, glob in enumerate((self.global_k[layer], self.global_v[layer])):
                 payload, shard = self._lowrank_payload(layer, o, ctype, j), self._shard(glob, o)
                 if ctype == T.LOW_RANK:
-                    u, vv = payload[:n * r].view(n, r), payload[n * r:].view(r, c)
-                else:
-                    sizes = [n * r // 4, r, r, c * r // 4, r, r]
-                    qu, su, mu, qv, sv, mv = torch.split(payload, sizes)
-                    u8 = lambda t_, rows: t_.contiguous().view(torch.uint8).view(rows, r)  # noqa: E731
-                    u = dequantize_int4(u8(qu, n // 2), su.view(1, r), mu.view(1, r))
-                    vv = dequantize_int4(u8(qv, c // 2), sv.view(1, r), mv.view(1, r)).t().contiguous()
-                lowrank_reconstruct(u, vv, base=shard, out=shard)
+                    lowrank_reconstruct(payload[:n * r].view(n, r), payload[n * r:].view(r, c), base=shard, out=shard)
+                else:   # int4 decode of both factors inside the reconstruct kernel
+                    lowrank_q_reconstruct(payload, n, c, r, base=shard, out=shard)
                 self.kernel_launches += 1
 
     def send(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
@@ -662,8 +654,8 @@ class PatchGatherEngine:
         """Pointer-keyed CUDA graphs of one layer's launches.  A model hands over K / V tensors from the caching
         allocator, whose addresses repeat from step to step (or rotate among a few): when a layer sees the same pair
         of addresses a second time, its eager launch sequence is captured once for that pair and replayed from then
-        on (one launch instead of four or five: the hooks' host time per layer drops below the GPU time); an unknown
-        pair runs the eager path.  At most 8 graphs per layer; `CF_LAYER_GRAPHS=0` switches the mechanism off."""
+        on (one launch instead of four or five); an unknown pair runs the eager path.  At most 8 graphs per layer.
+        Opt-in (`CF_LAYER_GRAPHS=1`): see the measurement note in __init__."""
         seen, graphs, launches = {}, {}, {}
         state = {"ok": True}
 

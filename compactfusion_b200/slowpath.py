@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from .compress_lowrank import lowrank_reconstruct, subspace_iter
+from .compress_lowrank import lowrank_q_pack, lowrank_q_reconstruct, lowrank_reconstruct, subspace_iter
 from .compress_quantize import (dequantize_1bit, dequantize_int2, dequantize_int4, quantize_1bit, quantize_int2,
                                 quantize_int4, sim_binary, sim_int2, sim_int2_minmax, sim_int4)
 from .compress_topk import SPARSE_LAST_DIM_SIZE, sim_topk, topk_compress, topk_decompress
@@ -37,6 +37,8 @@ def slowpath_compress(x: torch.Tensor, compress_type: COMPACT_COMPRESS_TYPE, ran
     elif compress_type == T.LOW_RANK_Q:
         assert rank is not None and rank >= 1, "Rank must be provided for LOW_RANK_Q compression"
         u, v, _ = subspace_iter(x, rank, 2)
+        if n % 2 == 0 and c % 2 == 0 and rank <= 64 and (n * rank) % 4 == 0 and (c * rank) % 4 == 0:
+            return lowrank_q_pack(u, v)   # both int4 encodes and the concatenation in two launches
         qu, su, mu = quantize_int4(u)
         qv, sv, mv = quantize_int4(v.t().contiguous())
         parts = [qu, su, mu, qv, sv, mv]
@@ -79,6 +81,8 @@ def slowpath_decompress(x: torch.Tensor, shape: tuple, compress_type: COMPACT_CO
     if compress_type == T.LOW_RANK_Q:
         assert rank is not None and rank >= 1
         assert (n * rank) % 4 == 0 and (c * rank) % 4 == 0
+        if n % 2 == 0 and c % 8 == 0 and rank <= 64 and x.is_contiguous():
+            return lowrank_q_reconstruct(x, n, c, rank)   # decode + transpose + product in one launch
         qu, su, mu, qv, sv, mv = torch.split(x, [n * rank // 4, rank, rank, c * rank // 4, rank, rank])
         u = dequantize_int4(u8(qu, n // 2, rank), su.view(1, rank), mu.view(1, rank))
         v = dequantize_int4(u8(qv, c // 2, rank), sv.view(1, rank), mv.view(1, rank))

@@ -198,6 +198,19 @@ CF_API int cf_lowrank_project(const void* x, const void* base, const float* q0, 
  * residual add: recon = base + fp16(U V) (base may be NULL). */
 CF_API int cf_lowrank_reconstruct(const void* U, const void* V, const void* base, void* recon,
                            int64_t N, int64_t C, int rank, cf_stream_t stream);
+/* LOW_RANK_Q decode fused into the reconstruct: `payload` is the wire format of slowpath_compress(LOW_RANK_Q)
+ * (slowpath.py:69-75): [qU (N/2, r) u8 | scaleU (r) | minU (r) | qV^T (C/2, r) u8 | scaleV (r) | minV (r)], int4 per
+ * column of U and of V^T (rows 2i / 2i+1 share a byte, low nibble = even row).  recon = base + fp16(U V) with
+ * U, V = the dequantised factors (value = fp16(fp16(code * scale) + min)): replaces the two dequantize_int4 calls,
+ * the transpose and torch.matmul of slowpath_decompress (slowpath.py:156-164) plus the residual add.
+ * recon may alias base.  N even, C % 8 == 0. */
+/* LOW_RANK_Q wire packing: U (N, r) and V (r, C) fp16 -> payload in the layout above.  Replaces quantize_int4(u),
+ * quantize_int4(v.t().contiguous()) and the torch.cat of slowpath_compress (slowpath.py:62-75); V^T is never
+ * formed.  Bit-identical to cf_minmax_compress(CF_CODEC_INT4) on U and on V^T. */
+CF_API int cf_lowrank_q_pack(const void* U, const void* V, void* payload, int64_t N, int64_t C, int rank,
+                      cf_stream_t stream);
+CF_API int cf_lowrank_q_reconstruct(const void* payload, const void* base, void* recon, int64_t N,
+                             int64_t C, int rank, cf_stream_t stream);
 
 /* ---- one-sided NVLink transport of the payloads (replaces dist.all_gather of
  * compact_all_gather, main.py:409, and the ring's batch_isend_irecv, ring.py:268-269) -----

@@ -105,6 +105,63 @@ def test_slowpath_compress_decompress_vs_sim(ctype, tol, shape):
             assert rel_l2(rec, sim) < tol
 
 
+@pytest.mark.parametrize("n,c,rank", [(1024, 2048, 8), (290, 1536, 4), (2304, 3072, 32), (64, 128, 1), (130, 264, 20), (512, 3072, 64)])
+@pytest.mark.parametrize("with_base", [False, True])
+def test_lowrank_q_fused_decode_matches_two_step(n, c, rank, with_base):
+    """cf_lowrank_q_reconstruct (decode of both int4 factors inside the reconstruct) against the sequence of
+    slowpath.py:156-164: dequantize_int4 of U and of V^T (checked against the oracle's dequant), transpose,
+    product, residual add.  Same MMA order as the unfused kernel, so the reconstructions agree bit for bit."""
+    dev = _cuda()
+    from compactfusion_b200.compress_lowrank import lowrank_q_reconstruct, lowrank_reconstruct
+    from compactfusion_b200.compress_quantize import dequantize_int4
+    from oracle import codecs as oc
+    g = torch.Generator().manual_seed(n + c + rank)
+    qu = torch.randint(0, 256, (n // 2, rank), dtype=torch.uint8, generator=g)
+    qv = torch.randint(0, 256, (c // 2, rank), dtype=torch.uint8, generator=g)
+    su, sv = [(torch.rand(rank, generator=g) * 0.02 + 1e-3).half() for _ in range(2)]
+    mu, mv = [(-torch.rand(rank, generator=g) * 0.1).half() for _ in range(2)]
+    flat = lambda t: t.contiguous().view(-1).view(torch.half)  # noqa: E731
+    payload = torch.cat([flat(qu), su, mu, flat(qv), sv, mv]).to(dev)
+    base = torch.randn(n, c, generator=g).half().to(dev) if with_base else None
+    u = dequantize_int4(qu.to(dev), su.view(1, rank).to(dev), mu.view(1, rank).to(dev))
+    vt = dequantize_int4(qv.to(dev), sv.view(1, rank).to(dev), mv.view(1, rank).to(dev))
+    assert_bits_equal(u.cpu(), oc.int4_dequantize(qu.numpy(), su.view(1, rank), mu.view(1, rank)), "U decode vs oracle")
+    assert_bits_equal(vt.cpu(), oc.int4_dequantize(qv.numpy(), sv.view(1, rank), mv.view(1, rank)), "V^T decode vs oracle")
+    want = lowrank_reconstruct(u, vt.t().contiguous(), base)
+    got = lowrank_q_reconstruct(payload, n, c, rank, base=base)
+    assert_bits_equal(got, want, "fused LOW_RANK_Q decode")
+    if with_base:   # in place, as the engines call it
+        buf = base.clone()
+        lowrank_q_reconstruct(payload, n, c, rank, base=buf, out=buf)
+        assert_bits_equal(buf, want, "in place")
+
+
+@pytest.mark.parametrize("n,c,rank", [(1024, 2048, 8), (290, 1536, 4), (2304, 3072, 32), (64, 128, 2), (130, 264, 20), (512, 3072, 64)])
+def test_lowrank_q_pack_matches_two_quantize_calls(n, c, rank):
+    """cf_lowrank_q_pack against slowpath.py:62-75 spelled out: quantize_int4(U), quantize_int4(V^T) (each checked
+    against the oracle), concatenated.  Bit-exact, including a constant column (zero scale)."""
+    dev = _cuda()
+    from compactfusion_b200.compress_lowrank import lowrank_q_pack
+    from compactfusion_b200.compress_quantize import quantize_int4
+    from oracle import codecs as oc
+    g = torch.Generator().manual_seed(3 * n + c + rank)
+    u = (torch.randn(n, rank, generator=g) * 0.05).half()
+    v = (torch.randn(rank, c, generator=g) * 3).half()
+    u[:, 0] = 0.25   # constant column: scale 0, codes NaN -> 0
+    parts = []
+    for t in (u, v.t().contiguous()):
+        q, s, m = quantize_int4(t.to(dev))
+        oq, os_, om = oc.int4_quantize(t)
+        assert_bits_equal(s.cpu(), os_, "scale vs oracle")
+        assert_bits_equal(m.cpu(), om, "min vs oracle")
+        assert (q.cpu().numpy() == oq).all(), "codes vs oracle"
+        parts += [q.contiguous().view(-1).view(torch.half), s.view(-1), m.view(-1)]
+    want = torch.cat(parts)
+    got = lowrank_q_pack(u.to(dev), v.to(dev))
+    assert got.numel() == (n * rank + c * rank) // 4 + 4 * rank
+    assert_bits_equal(got, want, "LOW_RANK_Q payload")
+
+
 def test_lowrank_state_machine_ef_invariant():
     """residual 1 + EF with the real LOW_RANK wire codec (examples/configs.py:63-85)."""
     dev = _cuda()
