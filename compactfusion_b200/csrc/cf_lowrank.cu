@@ -715,12 +715,13 @@ int cf_lowrank_q_reconstruct(const void* payload, const void* base, void* recon,
   const __half* b = static_cast<const __half*>(base);
   __half* o = static_cast<__half*>(recon);
   const int n = static_cast<int>(N), c = static_cast<int>(C);
+  const int vec = (rank % 16 == 0 && aligned16(qU) && aligned16(qVt) && std::getenv("CF_LRQ_SCALAR") == nullptr) ? 1 : 0;
   dim3 grid(static_cast<unsigned>((C + 127) / 128), static_cast<unsigned>((N + 63) / 64));
   switch ((rank + 15) / 16) {
-    case 1: k_lrq_reconstruct<1><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank); break;
-    case 2: k_lrq_reconstruct<2><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank); break;
-    case 3: k_lrq_reconstruct<3><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank); break;
-    default: k_lrq_reconstruct<4><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank); break;
+    case 1: k_lrq_reconstruct<1><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank, vec); break;
+    case 2: k_lrq_reconstruct<2><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank, vec); break;
+    case 3: k_lrq_reconstruct<3><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank, vec); break;
+    default: k_lrq_reconstruct<4><<<grid, 128, 0, st>>>(qU, sU, mU, qVt, sV, mV, b, o, n, c, rank, vec); break;
   }
   CF_CHECK_LAUNCH();
   return CF_OK;

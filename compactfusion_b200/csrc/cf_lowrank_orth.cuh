@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128, 3) k_lrq_reconstruct(const uint8_t* __res
                                                            const __half* __restrict__ mU, const uint8_t* __restrict__ qVt,
                                                            const __half* __restrict__ sV, const __half* __restrict__ mV,
                                                            const __half* __restrict__ base, __half* __restrict__ recon,
-                                                           int N, int C, int r) {
+                                                           int N, int C, int r, int vec) {
   constexpr int KP = KS * 16, BN = 128;
   constexpr int kLdU = KP + 8, kLdV = BN + 8;
   __shared__ __align__(16) __half Us[64 * kLdU];
@@ -473,33 +473,85 @@ __global__ void __launch_bounds__(128, 3) k_lrq_reconstruct(const uint8_t* __res
     bq[q] = make_uint4(0, 0, 0, 0);
     if (base != nullptr && n < N && c < C) bq[q] = ldg_stream(base + static_cast<size_t>(n) * C + c);
   }
-  auto deq = [](uint32_t code, __half sc, __half mn) {
-    return __hadd_rn(__hmul_rn(__ushort2half_rn(static_cast<unsigned short>(code)), sc), mn);
-  };
-  for (int i = tid; i < 32 * KP; i += 128) {   // U: row pair rp, column k
-    const int rp = i / KP, k = i % KP;
-    const int n = n0 + 2 * rp;
-    __half lo = zero, hi = zero;
-    if (k < r && n < N) {
-      const uint32_t b = qU[(static_cast<size_t>(n) >> 1) * r + k];
-      const __half sc = sU[k], mn = mU[k];
-      lo = deq(b & 0xFu, sc, mn);
-      hi = deq(b >> 4, sc, mn);
-    }
-    Us[(2 * rp) * kLdU + k] = lo;
-    Us[(2 * rp + 1) * kLdU + k] = hi;
+  // the four scale vectors once per CTA: [sU | mU | sV | mV], zero beyond r
+  __shared__ __align__(16) __half sc_s[4][KP];
+  for (int i = tid; i < 4 * KP; i += 128) {
+    const int which = i / KP, k = i % KP;
+    const __half* src = which == 0 ? sU : (which == 1 ? mU : (which == 2 ? sV : mV));
+    sc_s[which][k] = k < r ? src[k] : zero;
   }
-  for (int i = tid; i < (BN / 2) * KP; i += 128) {   // V: column pair cp, row k
-    const int cp = i / KP, k = i % KP;
-    const int c = c0 + 2 * cp;
-    __half lo = zero, hi = zero;
-    if (k < r && c < C) {
-      const uint32_t b = qVt[(static_cast<size_t>(c) >> 1) * r + k];
-      const __half sc = sV[k], mn = mV[k];
-      lo = deq(b & 0xFu, sc, mn);
-      hi = deq(b >> 4, sc, mn);
+  __syncthreads();
+  // two codes -> fp16(fp16(code * scale) + min), both roundings as in compress_quantize.py:636
+  auto deq2 = [](uint32_t c0_, uint32_t c1_, __half2 sc, __half2 mn) {
+    const __half2 q = __halves2half2(__ushort2half_rn(static_cast<unsigned short>(c0_)),
+                                     __ushort2half_rn(static_cast<unsigned short>(c1_)));
+    return __hadd2_rn(__hmul2_rn(q, sc), mn);
+  };
+  if (vec) {
+    // r % 16 == 0 and both code planes 16-byte aligned: one 16-byte load = 16 consecutive k of one row pair
+    const int per = r >> 4;
+    for (int i = tid; i < 32 * per; i += 128) {
+      const int rp = i / per, k0 = (i % per) << 4;
+      const int n = n0 + 2 * rp;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (n < N) q = __ldg(reinterpret_cast<const uint4*>(qU + (static_cast<size_t>(n) >> 1) * r + k0));
+      const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+      H8 lo[2], hi[2];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = k0 + 4 * w + 2 * j;
+          const uint32_t b0 = (w4[w] >> (16 * j)) & 0xFFu, b1 = (w4[w] >> (16 * j + 8)) & 0xFFu;
+          const __half2 sc = *reinterpret_cast<const __half2*>(&sc_s[0][k]), mn = *reinterpret_cast<const __half2*>(&sc_s[1][k]);
+          lo[w >> 1].w[2 * (w & 1) + j] = h22u(deq2(b0 & 0xFu, b1 & 0xFu, sc, mn));
+          hi[w >> 1].w[2 * (w & 1) + j] = h22u(deq2(b0 >> 4, b1 >> 4, sc, mn));
+        }
+      }
+      *reinterpret_cast<uint4*>(Us + (2 * rp) * kLdU + k0) = as_u4(lo[0]);
+      *reinterpret_cast<uint4*>(Us + (2 * rp) * kLdU + k0 + 8) = as_u4(lo[1]);
+      *reinterpret_cast<uint4*>(Us + (2 * rp + 1) * kLdU + k0) = as_u4(hi[0]);
+      *reinterpret_cast<uint4*>(Us + (2 * rp + 1) * kLdU + k0 + 8) = as_u4(hi[1]);
     }
-    *reinterpret_cast<__half2*>(Vs + k * kLdV + 2 * cp) = __halves2half2(lo, hi);
+    for (int i = tid; i < (BN / 2) * per; i += 128) {
+      const int cp = i / per, k0 = (i % per) << 4;
+      const int c = c0 + 2 * cp;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (c < C) q = __ldg(reinterpret_cast<const uint4*>(qVt + (static_cast<size_t>(c) >> 1) * r + k0));
+      const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + 4 * w + j;
+          const uint32_t b = (w4[w] >> (8 * j)) & 0xFFu;
+          const __half2 sc = __half2half2(sc_s[2][k]), mn = __half2half2(sc_s[3][k]);
+          *reinterpret_cast<__half2*>(Vs + k * kLdV + 2 * cp) = deq2(b & 0xFu, b >> 4, sc, mn);
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < 32 * KP; i += 128) {   // U: row pair rp, column k
+      const int rp = i / KP, k = i % KP;
+      const int n = n0 + 2 * rp;
+      __half2 val = __halves2half2(zero, zero);
+      if (k < r && n < N) {
+        const uint32_t b = qU[(static_cast<size_t>(n) >> 1) * r + k];
+        val = deq2(b & 0xFu, b >> 4, __half2half2(sc_s[0][k]), __half2half2(sc_s[1][k]));
+      }
+      Us[(2 * rp) * kLdU + k] = __low2half(val);
+      Us[(2 * rp + 1) * kLdU + k] = __high2half(val);
+    }
+    for (int i = tid; i < (BN / 2) * KP; i += 128) {   // V: column pair cp, row k
+      const int cp = i / KP, k = i % KP;
+      const int c = c0 + 2 * cp;
+      __half2 val = __halves2half2(zero, zero);
+      if (k < r && c < C) {
+        const uint32_t b = qVt[(static_cast<size_t>(c) >> 1) * r + k];
+        val = deq2(b & 0xFu, b >> 4, __half2half2(sc_s[2][k]), __half2half2(sc_s[3][k]));
+      }
+      *reinterpret_cast<__half2*>(Vs + k * kLdV + 2 * cp) = val;
+    }
   }
   __syncthreads();
   float acc[BN / 8][4];

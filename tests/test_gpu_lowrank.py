@@ -105,7 +105,8 @@ def test_slowpath_compress_decompress_vs_sim(ctype, tol, shape):
             assert rel_l2(rec, sim) < tol
 
 
-@pytest.mark.parametrize("n,c,rank", [(1024, 2048, 8), (290, 1536, 4), (2304, 3072, 32), (64, 128, 1), (130, 264, 20), (512, 3072, 64)])
+@pytest.mark.parametrize("n,c,rank", [(1024, 2048, 8), (290, 1536, 4), (2304, 3072, 32), (64, 128, 1), (130, 264, 20), (512, 3072, 64),
+                                      (256, 1024, 16), (190, 648, 48), (4388, 3072, 32)])
 @pytest.mark.parametrize("with_base", [False, True])
 def test_lowrank_q_fused_decode_matches_two_step(n, c, rank, with_base):
     """cf_lowrank_q_reconstruct (decode of both int4 factors inside the reconstruct) against the sequence of

@@ -25,6 +25,8 @@ has tests && { echo "== tests"; (time timeout 1500 python -m pytest tests -m gpu
 has smoke && { echo "== smoke"; timeout 120 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1 ; tail -1 $OUT/${TAG}_smoke.log; }
 has bench && { echo "== bench"; timeout 500 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err ; line $OUT/${TAG}_bench.json; tail -2 $OUT/${TAG}_bench.err; }
 has dropin && { echo "== bench --api dropin"; timeout 300 python bench.py --api dropin --no-e2e --no-cpu-baseline --no-gpu-reference > $OUT/${TAG}_bench_dropin.json 2> $OUT/${TAG}_bench_dropin.err ; line $OUT/${TAG}_bench_dropin.json; tail -2 $OUT/${TAG}_bench_dropin.err; }
+has config1 && { echo "== BASELINE configs[0]: INT4 round trip"; timeout 300 python bench.py --workload config1_int4_roundtrip > $OUT/${TAG}_bench_config1.json 2> $OUT/${TAG}_bench_config1.err ; head -c 1800 $OUT/${TAG}_bench_config1.json; echo; tail -2 $OUT/${TAG}_bench_config1.err; }
+has lrq && { for w in flux1024_patch_parallel cogvideox5b_ring; do echo "== lowrankq32 $w (N=1)"; timeout 300 python bench.py --codec lowrankq32 --workload $w --no-e2e --no-cpu-baseline --no-gpu-reference --steps 5 > $OUT/${TAG}_bench_lrq_$w.json 2> $OUT/${TAG}_bench_lrq_$w.err ; line $OUT/${TAG}_bench_lrq_$w.json; tail -2 $OUT/${TAG}_bench_lrq_$w.err; done; }
 has refarm && { echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err ; head -c 500 $OUT/${TAG}_bench_ref.json; echo; }
 if has lowrank; then
   echo "== low-rank kernel times"
