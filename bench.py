@@ -139,15 +139,56 @@ def synth_activations(n_local, layers, versions, device, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons of this rank's GPU sampled DURING the timed region: in-process NVML (the
+    library behind nvidia-smi; a 20 ms polling thread, initialised before the region starts so that no process
+    start-up and no NVML attach to every GPU of the box lands inside it -- on an 8-GPU box a freshly started
+    `nvidia-smi -lms` stalled the eager launches of all ranks), falling back to `nvidia-smi -lms 200`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.handle, self.samples, self._stop = None, None, [], threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((mhz, mask))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(0.02)
 
     def start(self):
+        if self.nvml is not None:
+            self._sample()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE,
@@ -162,6 +203,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._sample()   # the timed region has just ended: still under load
+            self._stop.set()
+            self.thread.join(timeout=1)
+            n, reasons = self.nvml, set()
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            for _, mask in self.samples:
+                reasons.update(name for name, bit in bits.items() if mask & bit)
+            sm = [m for m, _ in self.samples]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -171,7 +226,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 9:
@@ -181,11 +235,11 @@ class ClockSampler:
                 mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
+            for name, val in zip(self.NAMES, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_hbm_peak():

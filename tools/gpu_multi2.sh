@@ -24,7 +24,7 @@ run() {  # run <name> <timeout> -- bench args   (env vars may be set by the call
   python - <<PY
 import json
 try:
-    d = json.load(open("$OUT/${TAG}_bench_n${N}_${name}.json"))
+    d = json.loads([l for l in open("$OUT/${TAG}_bench_n${N}_${name}.json").read().splitlines() if l.startswith("{")][-1])
     r = d.get("roofline") or {}
     print("$name: %.3f ms/step  %.0f GB/s  parity_ok=%s  rel_l2=%s  identical=%s  transport=%s  schedule=%s" % (
         d["ms_per_step"], d["value"], d.get("parity_ok"), (d.get("fidelity") or {}).get("rel_l2"),
@@ -47,6 +47,7 @@ has ring_lrq    && { echo "== CogVideoX ring, LOW_RANK_Q r=32 (the example's pre
 has lrq         && { echo "== FLUX, LOW_RANK_Q r=32"; run lrq 300 --steps 3 --warmup 3 --no-e2e --codec lowrankq32 ; }
 has nobulk      && { echo "== CF_PUT_BULK=0 (round-1 sub-word remote stores)"; CF_PUT_BULK=0 run nobulk 200 --steps 20 --warmup 3 --no-e2e ; }
 has dropin      && { echo "== drop-in hooks (compact_fwd per layer)"; run dropin 200 --steps 20 --warmup 3 --no-e2e --api dropin ; }
+has dropin_graphs && { echo "== drop-in hooks, CF_LAYER_GRAPHS=1 (pointer-keyed per-layer graphs)"; CF_LAYER_GRAPHS=1 run dropin_graphs 200 --steps 20 --warmup 3 --no-e2e --api dropin ; }
 has dropin_nccl && { echo "== drop-in hooks, NCCL transport"; run dropin_nccl 200 --steps 10 --warmup 3 --no-e2e --api dropin --transport nccl ; }
 has nccl        && { echo "== engine, NCCL all-gather"; run nccl 200 --steps 10 --warmup 3 --no-e2e --transport nccl ; }
 has int2        && { echo "== INT2"; run int2 200 --steps 20 --warmup 3 --no-e2e --codec int2 ; }

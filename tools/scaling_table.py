@@ -26,7 +26,8 @@ def fmt(v):
 
 def main():
     n1 = {"serial": "r2_bench_n1_binary_with_gpu_reference.json", "dropin": "r2_bench_n1_dropin.json",
-          "int2": "r2_bench_n1_int2.json"}
+          "int2": "r2_bench_n1_int2.json", "dropin_graphs": "r2_bench_n1_dropin_layer_graphs.json",
+          "lrq": "r2_bench_n1_lrq.json", "ring_lrq": "r2_bench_n1_ring_lrq.json"}
     print("# Round 2: per-step latency of the hot path at 1 / 2 / 4 / 8 B200 (bench.py, CUDA events, max over ranks)\n")
     print("All compressed lines: `parity_ok: true` (finite fidelity over every layer, bit-identical caches on all ranks, "
           "rank 0's payloads and reconstructions of all origins verified by the oracle).  ms per step; FLUX = 57 layers x "
@@ -36,7 +37,9 @@ def main():
         ("FLUX, BINARY, engine (one CUDA graph, one-sided fused put)", "serial"),
         ("FLUX, BINARY, round-1 flag publication (every CTA fences + W atomics)", "publish0"),
         ("FLUX, BINARY, through the hooks (`compact_fwd` per layer, eager)", "dropin"),
+        ("FLUX, BINARY, through the hooks with `CF_LAYER_GRAPHS=1` (pointer-keyed per-layer graphs)", "dropin_graphs"),
         ("FLUX, INT2, engine", "int2"),
+        ("FLUX, LOW_RANK_Q r = 32, engine (eager)", "lrq"),
         ("FLUX, uncompressed NCCL all-gather (sync patch parallel)", "raw"),
         ("FLUX, uncompressed NCCL P2P ring relay", "raw_ring"),
         ("FLUX, uncompressed stale-async all-gather (DistriFusion)", "raw_async"),
