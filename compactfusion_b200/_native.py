@@ -95,7 +95,14 @@ def check(rc: int, what: str):
         raise NativeError(f"{what} failed (status {rc}): {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw getter skips building a Stream
+    object: this runs once per hook call)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -81,6 +81,23 @@ def group_info(group):
 
 
 _fast: dict = {}       # (kind, group key, mod_idx, shape) -> (engine, layer, key view, value view)
+_hot: dict = {}        # (kind, id(group), mod_idx, shape) -> (engine, layer, views, id(config), served compress types)
+
+
+def hot(cfg, kind: str, group, k: torch.Tensor, mod_idx, ctype):
+    """`usable` + `lookup` for a layer that has been here before, in one dictionary probe: (engine, layer, views)
+    or None (per-call path).  What `usable` decides per call -- configuration, dtype, device, shape -- is fixed per
+    (configuration object, layer, shape); only the compress type changes from step to step."""
+    key = (kind, id(group), mod_idx, k.shape)
+    ent = _hot.get(key)
+    if ent is not None and ent[3] == id(cfg) and k.dtype is torch.half and k.is_cuda:
+        return ent if ctype in ent[4] else None
+    if not usable(cfg, ctype, k):
+        return None
+    eng, layer, views = lookup(kind, group, k, mod_idx, cfg.comp_rank)
+    ent = (eng, layer, views, id(cfg), _config_ok(cfg))
+    _hot[key] = ent
+    return ent
 
 
 def lookup(kind: str, group, k: torch.Tensor, mod_idx, comp_rank=None):
@@ -146,6 +163,7 @@ def shutdown():
     _cfg_ok.clear()
     _groups.clear()
     _fast.clear()
+    _hot.clear()
 
 
 def engines():

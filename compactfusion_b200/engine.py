@@ -139,6 +139,7 @@ class PatchGatherEngine:
         self._send = {}
         self._recv = {}
         self._ptr_cache = {}
+        self._plans = {}   # ctype -> [plan per layer] (bound call sequences of `exchange`, see _build_plan)
         self.kernel_launches = 0  # launches of our kernels since the last reset
         nv.lib()  # fail loudly now if the extension is missing
         assert transport in ("nccl", "p2p", "auto")
@@ -278,7 +279,7 @@ class PatchGatherEngine:
                     lib.cf_ipc_close(pp)
             lib.cf_ipc_free(st["base"])
         self._p2p.clear()
-        self._ptr_cache.clear()
+        self._drop_call_caches()
 
     def slot_bytes(self, layer: int, origin: int, ctype, kv: int = 0) -> torch.Tensor:
         """The wire payload [codes | U | V] of tensor `kv` (0: K, 1: V) that `origin` delivered for `layer`, as it
@@ -581,11 +582,16 @@ class PatchGatherEngine:
             self.compress(layer, k, v, ctype)
             self.gather(ctype, layer)
 
+    def _drop_call_caches(self):
+        self._ptr_cache.clear()
+        self._plans.clear()
+
     def exchange(self, layer: int, k: torch.Tensor, v: torch.Tensor, ctype):
         """One layer of one step; returns (global_k, global_v) ready for attention."""
-        if ctype == T.WARMUP:
+        if ctype is T.WARMUP:
             return self.warmup(layer, k, v)
-        plan = self._ptr_cache.get(("plan", layer, ctype))
+        plans = self._plans.get(ctype)
+        plan = plans[layer] if (plans is not None and layer < len(plans)) else None
         if plan is None:
             plan = self._build_plan(layer, k, v, ctype)
         plan(k, v)
@@ -647,7 +653,9 @@ class PatchGatherEngine:
                 self.decompress(layer, ctype)
         if not generic and self._layer_graphs:
             plan = self._graphed(plan)
-        self._ptr_cache[("plan", layer, ctype)] = plan
+        plans = self._plans.setdefault(ctype, [])
+        plans.extend([None] * (layer + 1 - len(plans)))
+        plans[layer] = plan
         return plan
 
     def _graphed(self, eager):
@@ -735,7 +743,7 @@ class PatchGatherEngine:
         reconstruct_t(l), as l < d <= L-1-d."""
         if self.world == 1 and not self._per_layer_send:
             self._per_layer_send = True
-            self._ptr_cache.clear()
+            self._drop_call_caches()
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -767,13 +775,13 @@ class PatchGatherEngine:
                 self.step(ks, vs, ctype, overlap)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self._ptr_cache.clear()  # workspaces are keyed by stream: rebuild inside the capture
+        self._drop_call_caches()  # workspaces are keyed by stream: rebuild inside the capture
         g = torch.cuda.CUDAGraph()
         before = self.kernel_launches
         with torch.cuda.graph(g):
             self.step(ks, vs, ctype, overlap)
         self.launches_per_graph = self.kernel_launches - before
-        self._ptr_cache.clear()
+        self._drop_call_caches()
         return g
 
 

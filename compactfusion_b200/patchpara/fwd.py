@@ -14,6 +14,18 @@ from .df_utils import PatchConfig
 
 _buffers = {}
 _main = None
+_JOINT_ALLOWED = ["front", "rear", "none"]
+
+
+def _joint_flags(joint_tensor_key, joint_tensor_value, joint_strategy, allowed):
+    """fwd.py:60-76 of the reference (same checks as ring.py's)."""
+    if joint_tensor_key is None and joint_tensor_value is None:
+        return False
+    if joint_tensor_key is not None and joint_tensor_value is not None:
+        if joint_strategy not in allowed:
+            raise ValueError(f"joint_strategy: {joint_strategy} not supprted. supported joint strategy: {allowed}")
+        return joint_strategy != "none"
+    raise ValueError("joint_tensor_key and joint_tensor_value should be None or not None simultaneously.")
 
 
 def _plugin():
@@ -30,45 +42,45 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
                      joint_tensor_key=None, joint_tensor_value=None, joint_strategy="none", mod_idx=None,
                      current_iter=None):
     m = _plugin()
-    compact_config, compact_all_gather, allgather_cache = m.compact_config, m.compact_all_gather, m.allgather_cache
-    from ..ring import _joint_flags
-
+    cfg = m.compact_config()
     assert alibi_slopes is None, "Alibi slopes not supported in this basic gather impl."
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** (-0.5)
-    assert compact_config().override_with_patch_gather_fwd, "Patch gather fwd is not enabled"
-    config: PatchConfig = compact_config().patch_gather_fwd_config
+    assert cfg.override_with_patch_gather_fwd, "Patch gather fwd is not enabled"
+    config: PatchConfig = cfg.patch_gather_fwd_config
     assert mod_idx is not None, "mod_idx is required for caching"
     assert current_iter is not None, "current_iter is required for async logic"
-    is_joint = _joint_flags(joint_tensor_key, joint_tensor_value, joint_strategy, ["front", "rear", "none"])
+    is_joint = _joint_flags(joint_tensor_key, joint_tensor_value, joint_strategy, _JOINT_ALLOWED)
 
-    world_size, rank = dropin.group_info(group)
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
 
     key_to_use = value_to_use = None
     if config.use_compact:
-        ctype = compact_config().compress_func(mod_idx, current_iter)
-        if dropin.usable(compact_config(), ctype, k):
+        ctype = cfg.compress_func(mod_idx, current_iter)
+        ent = dropin.hot(cfg, "patch", group, k, mod_idx, ctype)
+        if ent is not None:
             # K and V of the layer through the persistent-buffer engine: one compress(+put) launch pair, one
             # reconstruct launch for all W origins, straight into the buffer attention reads (no cat for bs == 1)
-            eng, layer, views = dropin.lookup("patch", group, k, mod_idx, compact_config().comp_rank)
+            eng, layer, views = ent[0], ent[1], ent[2]
             gk, gv = eng.exchange(layer, k, v, ctype)
             if views is not None:
                 key_to_use, value_to_use = views
             else:
-                key_to_use = dropin.as_sequence(gk, world_size, k.shape)
-                value_to_use = dropin.as_sequence(gv, world_size, v.shape)
+                key_to_use = dropin.as_sequence(gk, eng.world, k.shape)
+                value_to_use = dropin.as_sequence(gv, eng.world, v.shape)
         else:
-            k_list = compact_all_gather(f"{mod_idx}-k", k, comp_type=ctype, group=group)
-            v_list = compact_all_gather(f"{mod_idx}-v", v, comp_type=ctype, group=group)
+            k_list = m.compact_all_gather(f"{mod_idx}-k", k, comp_type=ctype, group=group)
+            v_list = m.compact_all_gather(f"{mod_idx}-v", v, comp_type=ctype, group=group)
     elif not config.async_comm:
+        world_size, rank = dropin.group_info(group)
         k_list = [torch.empty_like(k) for _ in range(world_size)]
         v_list = [torch.empty_like(v) for _ in range(world_size)]
         with Profiler.scope("compact.gather.all_gather_sync"):
             dist.all_gather(k_list, k, group=group)
             dist.all_gather(v_list, v, group=group)
     else:
-        cache = allgather_cache()
+        world_size, rank = dropin.group_info(group)
+        cache = m.allgather_cache()
         kk, vk = f"{mod_idx}-k", f"{mod_idx}-v"
         with Profiler.scope("df.all_gather"):
             if current_iter < config.async_warmup:
@@ -109,4 +121,4 @@ def patch_gather_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, wind
                             window_size=window_size)
     # (b, h, s) like the flash-attn LSE the reference post-processes (fwd.py:234-235 is a no-op reshape
     # chain on that layout); callers of the patch path only use `out`
-    return out.to(q.dtype), lse, None
+    return (out if out.dtype == q.dtype else out.to(q.dtype)), lse, None

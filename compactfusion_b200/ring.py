@@ -58,6 +58,9 @@ class RingComm:
         self._ops = []
 
 
+_patch_fwd = None
+
+
 def compact_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, window_size=(-1, -1), alibi_slopes=None,
                 return_attn_probs=None, deterministic=False, attn_layer=None, group=None, joint_tensor_key=None,
                 joint_tensor_value=None, joint_strategy="none", mod_idx=None, current_iter=None):
@@ -66,8 +69,11 @@ def compact_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, window_si
     args = (q, k, v, dropout_p, softmax_scale, causal, window_size, alibi_slopes, return_attn_probs, deterministic,
             attn_layer, group, joint_tensor_key, joint_tensor_value, joint_strategy, mod_idx, current_iter)
     if compact_config().override_with_patch_gather_fwd:
-        from .patchpara.fwd import patch_gather_fwd
-        return patch_gather_fwd(*args)
+        global _patch_fwd
+        if _patch_fwd is None:
+            from .patchpara.fwd import patch_gather_fwd   # (that module imports this one's package: first call)
+            _patch_fwd = patch_gather_fwd
+        return _patch_fwd(*args)
     return _compact_ring_fwd(*args)
 
 
@@ -108,11 +114,13 @@ def _compact_ring_fwd(q, k, v, dropout_p=0, softmax_scale=None, causal=True, win
     assert v.shape == shape
 
     from . import dropin
-    if (dropin.usable(compact_config(), ctype, k) and not causal and dropout_p == 0
-            and tuple(window_size) == (-1, -1)):
+    ent = None
+    if not causal and dropout_p == 0 and tuple(window_size) == (-1, -1):
+        ent = dropin.hot(compact_config(), "ring", group, k, mod_idx, ctype)
+    if ent is not None:
         # the ring on the persistent-buffer engine: the payload goes to every rank's slot at once, hop s consumes
         # origin (rank - s) mod W with one flag-waiting launch for K and V, the LSE merge is one fused kernel
-        eng, layer = dropin.get("ring", group, k, mod_idx, compact_config().comp_rank)
+        eng, layer = ent[0], ent[1]
         out, lse = eng.ring_forward(layer, q, k, v, ctype, softmax_scale, joint_tensor_key, joint_tensor_value,
                                     joint_strategy)
         return out, lse, None
