@@ -1124,19 +1124,26 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    host_t0 = time.perf_counter()
+    host_first = None
     for i in range(args.steps):
         run_step(i)
+        if i == 1:   # two steps fit the launch queue: how long the HOST needs to enqueue a step (eager modes)
+            host_first = (time.perf_counter() - host_t0) / 2
     if raw:
         stepper.finish()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    note(rank, f"timed region done: {ms / args.steps:.3f} ms/step")
+    note(rank, f"timed region done: {ms / args.steps:.3f} ms/step"
+         + (f"; host enqueue of a step {host_first * 1e3:.3f} ms" if host_first else ""))
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clock_info = clocks.stop() if rank == 0 else None
+    if getattr(eng, "plan_host_s", None) and eng.plan_host_s[1]:
+        note(rank, f"CF_PLAN_TIMING: {eng.plan_host_s[0] / eng.plan_host_s[1] * 1e6:.1f} us of host time per layer inside the C calls")
     launches = (eng.launches_per_graph * args.steps) if graphs is not None else eng.kernel_launches
     ms_per_step = ms / args.steps
     value = job_bytes(layers, world) / (ms_per_step * 1e-3) / 1e9
@@ -1190,6 +1197,7 @@ def main():
                                                      if dropin_api else "engine (whole-step runtime)"),
                        "exchange": MODE, "codec": args.codec, "layers": layers, "seq": SEQ,
                        "channels": CH, "world": world, "shard_rows": n_local, "launch_mode": mode,
+                       "host_enqueue_ms_per_step": (round(host_first * 1e3, 4) if (host_first and graphs is None) else None),
                        "schedule": "two chains (compress | reconstruct)" if (args.overlap and not raw and eng.can_overlap(ctype)) else "serial",
                        "transport": transport + (" (fused into the codec kernels)" if world > 1 and eng.fused(ctype) else ""),
                        **({"transport_note": probe_note} if probe_note else {}),

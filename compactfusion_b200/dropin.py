@@ -125,7 +125,11 @@ def get(kind: str, group, k: torch.Tensor, mod_idx, comp_rank=None):
     if ent is None:
         cls = RingExchangeEngine if kind == "ring" else PatchGatherEngine
         transport = os.environ.get("CF_DROPIN_TRANSPORT", "auto")
+        # CF_DROPIN_INPUTS_STABLE=1 (A/B only): lets the stats kernel fill its pipeline before the previous kernel
+        # has finished -- legitimate for static input buffers (bench.py's engine lines), NOT in a model, where
+        # the kernel right before the hook is the one that writes K and V
         ent = (cls(0, n, c, group=group, device=k.device, transport=transport,
+                   inputs_stable=os.environ.get("CF_DROPIN_INPUTS_STABLE") == "1",
                    comp_rank=comp_rank if (isinstance(comp_rank, int) and comp_rank > 0) else None), {})
         _engines[key] = ent
     eng, index = ent
