@@ -512,7 +512,7 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
         cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
         cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)) == cudaSuccess) {
       cudaLaunchConfig_t q{};
-      q.gridDim = dim3(16); q.blockDim = dim3(256); q.dynamicSmemBytes = smem_o;
+      q.gridDim = dim3(16); q.blockDim = dim3(kOrthThreads); q.dynamicSmemBytes = smem_o;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
       qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -529,14 +529,16 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
       CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_orth<RP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_o)));
     }
   }
-  auto orth = [&](int S, int M, int ctas, int rows, float2* out2, __half* out16, float* out32c) -> int {
+  static const bool light_ok = [] { const char* e = getenv("CF_LR_LIGHT"); return !(e && e[0] == '0'); }();
+  auto orth = [&](int S, int M, int ctas, int rows, float2* out2, __half* out16, float* out32c, bool light = false) -> int {
     if (!legacy_orth) {
       OrthParams o{};
+      o.light = (light && light_ok) ? 1 : 0;
       o.part = part; o.S = S; o.part_stride = static_cast<size_t>(M) * RP; o.X = Xsum; o.M = M; o.r = r;
       o.out2 = out2; o.out16 = out16; o.out32c = out32c;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(orth_nc);
-      cfg.blockDim = dim3(256);
+      cfg.blockDim = dim3(kOrthThreads);
       cfg.dynamicSmemBytes = smem_o;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
@@ -581,7 +583,10 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
     gemm_AtY();
     CF_CHECK_LAUNCH();
     const bool last = it == iters - 1;
-    if (int rc = orth(p.aty_splits, c, p.gram_ctas_c, p.gram_rows_c, Q2, nullptr, (last && q_out) ? q_out : nullptr))
+    // the bases between iterations only seed the next product; the one handed back to the caller (q_out) and U are
+    // orthonormalised in full
+    if (int rc = orth(p.aty_splits, c, p.gram_ctas_c, p.gram_rows_c, Q2, nullptr, (last && q_out) ? q_out : nullptr,
+                      !(last && q_out)))
       return rc;
     q_written = q_written || (last && q_out);
   }

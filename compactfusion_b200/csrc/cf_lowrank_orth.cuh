@@ -28,8 +28,11 @@ namespace cf {
 // ---------------------------------------------------------------------------------------
 constexpr int kClusterCtas = 8;    // portable cluster size; 16 (non-portable, opt-in attribute) halves the rows per CTA
 // rows staged per step: one row per thread in the substitution passes (RP = 64: half, to fit shared memory)
+// 512 threads per CTA: the Gram blocks are dealt to the first 256 thread slots and the rows of a chunk to two row
+// groups (slot, group), so the substitution has one row per thread for up to 512 rows and twice the loads in flight
+constexpr int kOrthThreads = 512;
 template <int RP>
-constexpr int orth_chunk() { return RP <= 32 ? 256 : 128; }
+constexpr int orth_chunk() { return RP <= 32 ? 512 : 256; }
 
 struct OrthParams {
   const float* part;     // S partial copies of X, `part_stride` floats apart
@@ -40,12 +43,15 @@ struct OrthParams {
   float2* out2;          // optional (M, RP) {hi, lo} TF32 pairs (the next product's skinny operand)
   __half* out16;         // optional (M, r) fp16
   float* out32c;         // optional (M, r) compact fp32
+  int light;             // 1: X only seeds the next product (an intermediate basis of the subspace iteration): any
+                         // well-conditioned basis of span(X) gives the same next subspace, so ONE factorisation is
+                         // enough when X is well conditioned (orthogonality error ~cond^2 u ~ 2e-4), two otherwise
 };
 
 template <int RP>
 constexpr size_t lr_orth_smem() {
   return sizeof(float) * orth_chunk<RP>() * (RP + 2)      // row chunk
-         + sizeof(float) * RP * RP                        // this CTA's partial Gram (read by the cluster)
+         + sizeof(float) * 2 * RP * RP                    // this CTA's partial Gram (read by the cluster) + row group 1's
          + sizeof(float) * (2 * RP * (RP + 1) + RP)       // G, its copy (+ pivots) for the factorisation
          + sizeof(float) * (RP * RP + RP) + 64;           // R (upper), 1 / diag, scalars
 }
@@ -76,6 +82,7 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank)
 template <int RP>
 __device__ void cholesky_upper_f32(float (*G)[RP + 1], float* piv, int r, int t, float floor_piv) {
   const int ti = t >> 4, tj = t & 15;
+  const bool active = t < 256;   // (threads beyond the 16 x 16 grid only keep the barriers company)
   for (int k = 0; k < r; ++k) {
     float d = G[k][k];
     if (!(d > floor_piv)) d = floor_piv;
@@ -84,7 +91,7 @@ __device__ void cholesky_upper_f32(float (*G)[RP + 1], float* piv, int r, int t,
 #pragma unroll
     for (int a = 0; a < (RP + 15) / 16; ++a) {
       const int i = ti + 16 * a;
-      if (i > k && i < r) {
+      if (active && i > k && i < r) {
         const float gki = G[k][i] * inv_d;
 #pragma unroll
         for (int b = 0; b < (RP + 15) / 16; ++b) {
@@ -98,12 +105,13 @@ __device__ void cholesky_upper_f32(float (*G)[RP + 1], float* piv, int r, int t,
 }
 
 template <int RP, int NC>
-__global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
+__global__ void __launch_bounds__(kOrthThreads, 1) k_lr_orth(const OrthParams p) {
   extern __shared__ __align__(16) unsigned char orth_raw[];
   constexpr int kLdX = RP + 2, kOrthChunk = orth_chunk<RP>();
   float* Xd = reinterpret_cast<float*>(orth_raw);                         // [kOrthChunk][kLdX]
   float* Gp = Xd + kOrthChunk * kLdX;                                     // [RP][RP] partial Gram of this CTA
-  float (*G)[RP + 1] = reinterpret_cast<float (*)[RP + 1]>(Gp + RP * RP);
+  float* Gp2 = Gp + RP * RP;                                              // [RP][RP] row group 1's share of it
+  float (*G)[RP + 1] = reinterpret_cast<float (*)[RP + 1]>(Gp2 + RP * RP);
   float (*Gc)[RP + 1] = reinterpret_cast<float (*)[RP + 1]>(reinterpret_cast<float*>(G) + RP * (RP + 1));
   float* piv = reinterpret_cast<float*>(Gc) + RP * (RP + 1);
   float* Rs = piv + RP;                                                   // [RP][RP]
@@ -121,13 +129,14 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   int bi[KB], bj[KB];
 #pragma unroll
   for (int q = 0; q < KB; ++q) {
-    int id = t + 256 * q, i = 0;
+    int id = (t & 255) + 256 * q, i = 0;
     if (id >= kBlocks) id = -1;
     if (id >= 0)
       while (id >= NB - i) { id -= NB - i; ++i; }   // row i of the block triangle holds NB - i blocks
     bi[q] = id >= 0 ? i : -1;
     bj[q] = id >= 0 ? i + id : -1;
   }
+  const int rg = t >> 8;             // row group: 32-row blocks rg, rg + 2, ... of a chunk
   float acc[KB][4], comp[KB][4];   // Kahan sum of the 32-row block sums
 
   auto zero_acc = [&]() {
@@ -143,7 +152,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
     sum = tsum;
   };
   auto gram_chunk = [&](int rows) {   // acc += Xd[0..rows)^T Xd[0..rows) on this thread's blocks
-    for (int rb = 0; rb < rows; rb += 32) {
+    for (int rb = 32 * rg; rb < rows; rb += 32 * (kOrthThreads / 256)) {
       const int re = min(rows, rb + 32);
 #pragma unroll
       for (int q = 0; q < KB; ++q) {
@@ -171,17 +180,27 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   auto reduce_and_factor = [&](float shift_rel, bool adaptive) {
 #pragma unroll
     for (int q = 0; q < KB; ++q)
-      if (bi[q] >= 0) {
+      if (bi[q] >= 0 && rg == 1) {
         const int i = 2 * bi[q], j = 2 * bj[q];
-        Gp[i * RP + j] = acc[q][0];
-        Gp[i * RP + j + 1] = acc[q][1];
-        Gp[(i + 1) * RP + j] = acc[q][2];
-        Gp[(i + 1) * RP + j + 1] = acc[q][3];
+        Gp2[i * RP + j] = acc[q][0];
+        Gp2[i * RP + j + 1] = acc[q][1];
+        Gp2[(i + 1) * RP + j] = acc[q][2];
+        Gp2[(i + 1) * RP + j + 1] = acc[q][3];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < KB; ++q)
+      if (bi[q] >= 0 && rg == 0) {   // group 0 + group 1, always in this order
+        const int i = 2 * bi[q], j = 2 * bj[q];
+        Gp[i * RP + j] = acc[q][0] + Gp2[i * RP + j];
+        Gp[i * RP + j + 1] = acc[q][1] + Gp2[i * RP + j + 1];
+        Gp[(i + 1) * RP + j] = acc[q][2] + Gp2[(i + 1) * RP + j];
+        Gp[(i + 1) * RP + j + 1] = acc[q][3] + Gp2[(i + 1) * RP + j + 1];
       }
     cluster_sync_all();   // every CTA's Gp is complete and visible cluster-wide
 #pragma unroll
     for (int q = 0; q < KB; ++q)
-      if (bi[q] >= 0) {
+      if (bi[q] >= 0 && rg == 0) {
         const int i = 2 * bi[q], j = 2 * bj[q];
         float v[NC][4];
 #pragma unroll
@@ -223,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
       // first try the plain factorisation on a copy: if every pivot stays above 1 % of the largest diagonal entry,
       // X is well conditioned (cond^2 <~ 100 r) and CholeskyQR2 is enough -- the caller then runs one pass less.
       // Every CTA holds the same bits of G, so every CTA takes the same decision.
-      for (int e = t; e < RP * (RP + 1); e += 256) (&Gc[0][0])[e] = (&G[0][0])[e];
+      for (int e = t; e < RP * (RP + 1); e += kOrthThreads) (&Gc[0][0])[e] = (&G[0][0])[e];
       __syncthreads();
       cholesky_upper_f32<RP>(G, piv, r, t, floor_piv);
       if (t == 0) {
@@ -234,7 +253,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
       __syncthreads();
       well = scal[1] != 0.f;
       if (!well) {   // ill conditioned: restore G, shift, factor again
-        for (int e = t; e < RP * (RP + 1); e += 256) (&G[0][0])[e] = (&Gc[0][0])[e];
+        for (int e = t; e < RP * (RP + 1); e += kOrthThreads) (&G[0][0])[e] = (&Gc[0][0])[e];
         __syncthreads();
         shifted = true;
       }
@@ -246,11 +265,11 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
       __syncthreads();
     }
     if (!adaptive || shifted) cholesky_upper_f32<RP>(G, piv, r, t, floor_piv);
-    for (int e = t; e < RP * RP; e += 256) {
+    for (int e = t; e < RP * RP; e += kOrthThreads) {
       const int i = e / RP, j = e % RP;
       Rs[e] = (i < r && j < r && j >= i) ? G[i][j] * piv[i] : 0.f;
     }
-    for (int j = t; j < RP; j += 256) Ds[j] = (j < r) ? piv[j] : 0.f;
+    for (int j = t; j < RP; j += kOrthThreads) Ds[j] = (j < r) ? piv[j] : 0.f;
     __syncthreads();
   };
   // X[m] <- X[m] R^-1 for one row held in registers (right-looking forward substitution)
@@ -287,7 +306,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   for (int mc = m_begin; mc < m_end; mc += kOrthChunk) {
     const int rows = min(kOrthChunk, m_end - mc);
     __syncthreads();
-    for (int i = t; i < rows * (RP / 4); i += 256) {
+    for (int i = t; i < rows * (RP / 4); i += kOrthThreads) {
       const int rr = i / (RP / 4), c4 = i % (RP / 4);
       const size_t o = static_cast<size_t>(mc + rr) * RP + 4 * c4;
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -311,7 +330,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   // well-conditioned X (the common case): plain factorisation, CholeskyQR2; otherwise the shifted factorisation,
   // which always succeeds and leaves cond(X R1^-1) <= ~100, and one more pass (CholeskyQR3)
   reduce_and_factor(1e-4f, true);
-  const int more_passes = well ? 1 : 2;
+  const int more_passes = (well ? 1 : 2) - (p.light ? 1 : 0);
 
   // ---- passes 1 (second half) and 2: X <- X R^-1, Gram of the new X, plain Cholesky ----
   for (int pass = 0; pass < more_passes; ++pass) {
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(256, 1) k_lr_orth(const OrthParams p) {
   }
 
   // ---- last pass (second half): X <- X R^-1, outputs ----
-  for (int m = m_begin + t; m < m_end; m += 256) {
+  for (int m = m_begin + t; m < m_end; m += kOrthThreads) {
     float xr[RP];
     load_row(xr, m);
     solve_row(xr);
