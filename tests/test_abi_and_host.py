@@ -692,3 +692,45 @@ def test_quantized_cache_host_logic(monkeypatch):
     plain = utils.CompactCache()
     plain.put("k", x, None)
     assert plain.get_base("k") is x
+
+
+# ---------------- dropin.hot: the hooks' one-probe path (dropin.py) ----------------
+def test_dropin_hot_caches_per_layer_and_respects_type_and_config(monkeypatch):
+    """`hot` = `usable` + `lookup` once per (hook, group, layer, shape); afterwards one dictionary probe that still
+    refuses a compress type the engines do not serve and re-decides for a new configuration object."""
+    from compactfusion_b200 import dropin
+    from compactfusion_b200.utils import COMPACT_COMPRESS_TYPE as T
+    dropin.shutdown()
+    calls = {"usable": 0, "lookup": 0}
+
+    class Cfg:
+        comp_rank = -1
+
+    def usable(cfg, ctype, k):
+        calls["usable"] += 1
+        return ctype in dropin._ENGINE_TYPES
+
+    def lookup(kind, group, k, mod_idx, comp_rank=None):
+        calls["lookup"] += 1
+        return ("engine", 7, None)
+
+    class K:   # what `hot` reads of a tensor
+        shape, dtype, is_cuda = (1, 576, 24, 128), torch.half, True
+
+    monkeypatch.setattr(dropin, "usable", usable)
+    monkeypatch.setattr(dropin, "lookup", lookup)
+    monkeypatch.setattr(dropin, "_config_ok", lambda cfg: dropin._ENGINE_TYPES)
+    cfg = Cfg()
+    assert dropin.hot(cfg, "patch", None, K, 3, T.SPARSE) is None and calls == {"usable": 1, "lookup": 0}
+    ent = dropin.hot(cfg, "patch", None, K, 3, T.BINARY)
+    assert ent[:3] == ("engine", 7, None) and calls == {"usable": 2, "lookup": 1}
+    for ct in (T.BINARY, T.INT2, T.WARMUP):
+        assert dropin.hot(cfg, "patch", None, K, 3, ct) is ent
+    assert dropin.hot(cfg, "patch", None, K, 3, T.SPARSE) is None   # served types are checked on the cached entry too
+    assert calls == {"usable": 2, "lookup": 1}
+    assert dropin.hot(cfg, "patch", None, K, 4, T.BINARY)[1] == 7 and calls["lookup"] == 2   # another layer: its own entry
+    other = Cfg()
+    dropin.hot(other, "patch", None, K, 3, T.BINARY)                                          # new configuration object
+    assert calls["usable"] == 4 and calls["lookup"] == 3
+    dropin.shutdown()
+    assert not dropin._hot and not dropin._fast

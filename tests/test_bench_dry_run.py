@@ -196,6 +196,18 @@ def test_bench_gpu_arm_single_gpu_dry_run(monkeypatch, capsys, argv):
         assert line["oracle_parity"]["ok"] is False and line["parity_ok"] is False
 
 
+def test_bench_config1_int4_roundtrip_dry_run(monkeypatch, capsys):
+    """BASELINE configs[0] (one 4096 x 3072 tensor, INT4 + error feedback, 28-step series) through the plugin API:
+    the line keeps the contract's keys, names the workload and counts the launches of the per-call path."""
+    line = _run_bench(monkeypatch, capsys, ["--workload", "config1_int4_roundtrip", "--steps", "2", "--no-cpu-baseline"])
+    assert BASE_KEYS <= set(line) and line["n_gpus"] == 1 and line["unit"] == "GB/s"
+    cfg = line["config"]
+    assert cfg["workload"] == "config1_int4_roundtrip" and cfg["codec"] == "int4" and cfg["series_steps"] == 28
+    assert cfg["seq"] == 4096 and cfg["channels"] == 3072 and "model" not in cfg
+    assert line["gpu_launches"] > 0 and line["roofline"]["bound"] == "hbm" and line["roofline"]["algorithmic_bytes_per_launch"] > 0
+    assert line["e2e"] is None and line["cpu_baseline"] is None
+
+
 @pytest.mark.parametrize("argv", [
     ["--gpus", "2", "--layers", "3", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference"],
     ["--gpus", "2", "--layers", "6", "--steps", "3", "--no-cpu-baseline", "--no-gpu-reference", "--no-e2e", "--overlap", "--no-parity"],
