@@ -449,7 +449,7 @@ static LrMmaPlan make_lr_mma_plan(int64_t N, int64_t C, int r) {
   p.part_off = take(part_aq > part_aty ? part_aq : part_aty);
   p.gpart_off = take(static_cast<size_t>(16) * r * r * 8);
   p.rinv_off = take(static_cast<size_t>(p.RP) * p.RP * 4 + static_cast<size_t>(p.RP) * 4);
-  p.ticket_off = take(256);
+  p.ticket_off = take(4096);   // [0]: the legacy Gram kernels' ticket; [1 + it]: max |partial| of iteration it's A Q
   p.total = off;
   return p;
 }
@@ -469,8 +469,14 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   const size_t smem_n = lr_gemm_smem<RP, false>(), smem_t = lr_gemm_smem<RP, true>();
   CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_n)));
   CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t)));
-  CF_CHECK_CUDA(cudaMemsetAsync(ticket, 0, 256, st));
-  k_lr_pad_split<<<small_grid, 256, 0, st>>>(q0, Q2, c, r, RP);
+  CF_CHECK_CUDA(cudaMemsetAsync(ticket, 0, 4096, st));
+  // fp16 planes (hi | lo * 2^11) instead of TF32 pairs for the skinny operands of modest size -- the bases Q (the
+  // N(0, 1) start, then orthonormal) and the orthonormal U of the last product: two fp16 MMAs per term instead of
+  // four TF32 ones and no conversion of the streamed delta fragments.  The raw Y of the intermediate A^T Y products
+  // has no such bound and keeps the TF32 pairs.  CF_LR_HALF=0: TF32 everywhere (A/B).
+  static const bool half_env = [] { const char* e = getenv("CF_LR_HALF"); return !(e && e[0] == '0'); }();
+  const bool hb = half_env && RP >= 16 && lr_gemm_small();
+  k_lr_pad_split<<<small_grid, 256, 0, st>>>(q0, Q2, c, r, RP, hb ? 1 : 0);
   CF_CHECK_LAUNCH();
 
   // 16 warps per CTA split the column tiles between two warp groups
@@ -480,23 +486,33 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   const int gemm_threads = (RP >= 16 && wide) ? 2 * kLrThreads : kLrThreads;
   const bool small = lr_gemm_small();
   const size_t smem_ns = lr_gemm_smem<RP, false, 32, 2>(), smem_ts = lr_gemm_smem<RP, true, 32, 2>();
+  constexpr bool kHalfOk = RP >= 16;   // (one ldmatrix.trans covers two 8-column tiles)
+  const size_t smem_nh = lr_gemm_smem<RP, false, 32, 2, kHalfOk>(), smem_th = lr_gemm_smem<RP, true, 32, 2, kHalfOk>();
   if (small) {
     CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ns)));
     CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ts)));
   }
-  auto gemm_AQ = [&]() {  // part[s] (N, RP) = A Q
+  if (hb) {
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false, 32, 2, kHalfOk>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_nh)));
+    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true, 32, 2, kHalfOk>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_th)));
+  }
+  auto gemm_AQ = [&](unsigned* absmax = nullptr) {  // part[s] (N, RP) = A Q
     dim3 grid((n + kLrBM - 1) / kLrBM, p.aq_splits);
-    if (small)
-      k_lr_gemm<RP, false, 32, 2><<<grid, kLrThreads, smem_ns, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
+    if (hb)
+      k_lr_gemm<RP, false, 32, 2, kHalfOk><<<grid, kLrThreads, smem_nh, st>>>(xh, bh, Q2, part, n, c, p.aq_kper, absmax);
+    else if (small)
+      k_lr_gemm<RP, false, 32, 2><<<grid, kLrThreads, smem_ns, st>>>(xh, bh, Q2, part, n, c, p.aq_kper, nullptr);
     else
-      k_lr_gemm<RP, false><<<grid, gemm_threads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper);
+      k_lr_gemm<RP, false><<<grid, gemm_threads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper, nullptr);
   };
-  auto gemm_AtY = [&]() {  // part[s] (C, RP) = A^T Y
+  auto gemm_AtY = [&](bool planes = false) {  // part[s] (C, RP) = A^T Y; planes: Y2 holds fp16 planes (the orthonormal U)
     dim3 grid((c + kLrBM - 1) / kLrBM, p.aty_splits);
-    if (small)
-      k_lr_gemm<RP, true, 32, 2><<<grid, kLrThreads, smem_ts, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
+    if (planes)
+      k_lr_gemm<RP, true, 32, 2, kHalfOk><<<grid, kLrThreads, smem_th, st>>>(xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
+    else if (small)
+      k_lr_gemm<RP, true, 32, 2><<<grid, kLrThreads, smem_ts, st>>>(xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
     else
-      k_lr_gemm<RP, true><<<grid, gemm_threads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper);
+      k_lr_gemm<RP, true><<<grid, gemm_threads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
   };
   // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies).
   // One launch on one 8-CTA cluster (k_lr_orth); CF_LR_ORTH=legacy keeps round 1's five-launch chain (A/B).
@@ -534,6 +550,7 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
     if (!legacy_orth) {
       OrthParams o{};
       o.light = (light && light_ok) ? 1 : 0;
+      o.half_planes = (hb && out2 != nullptr) ? 1 : 0;
       o.part = part; o.S = S; o.part_stride = static_cast<size_t>(M) * RP; o.X = Xsum; o.M = M; o.r = r;
       o.out2 = out2; o.out16 = out16; o.out32c = out32c;
       cudaLaunchConfig_t cfg{};
@@ -556,31 +573,34 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
     }
     // the S split-K partials are added by a wide kernel (all SMs); the 16 Gram CTAs then read one copy
     k_lr_sum_split<<<small_grid, 256, 0, st>>>(part, S, static_cast<size_t>(M) * RP, nullptr, Xsum,
-                                               static_cast<size_t>(M) * RP);
+                                               static_cast<size_t>(M) * RP, nullptr);
     CF_CHECK_LAUNCH();
     GramParams g{};
     g.xpart = Xsum; g.S = 1; g.part_stride = static_cast<size_t>(M) * RP; g.X = Xsum;
     g.M = M; g.r = r; g.rows_per_cta = rows; g.gpart = gpart; g.ticket = ticket; g.r_out = rfac; g.rdinv_out = rdinv;
     k_lr_gram_chol<RP><<<ctas, 256, 0, st>>>(g);
     CF_CHECK_LAUNCH();
-    k_lr_solve_out<RP><<<(M + 127) / 128, 128, 0, st>>>(Xsum, rfac, rdinv, M, r, nullptr, nullptr, nullptr);
+    k_lr_solve_out<RP><<<(M + 127) / 128, 128, 0, st>>>(Xsum, rfac, rdinv, M, r, nullptr, nullptr, nullptr, 0);
     CF_CHECK_LAUNCH();
     g.xpart = Xsum; g.S = 1;
     k_lr_gram_chol<RP><<<ctas, 256, 0, st>>>(g);
     CF_CHECK_LAUNCH();
-    k_lr_solve_out<RP><<<(M + 127) / 128, 128, 0, st>>>(Xsum, rfac, rdinv, M, r, out2, out16, out32c);
+    k_lr_solve_out<RP><<<(M + 127) / 128, 128, 0, st>>>(Xsum, rfac, rdinv, M, r, out2, out16, out32c, hb ? 1 : 0);
     CF_CHECK_LAUNCH();
     return CF_OK;
   };
 
   bool q_written = false;
   for (int it = 0; it < iters; ++it) {
-    gemm_AQ();
+    // the raw Y = A Q of an iteration has no a-priori bound: the product kernel records max |partial| and the sum
+    // kernel scales Y by a power of two before splitting it into fp16 planes (span(A^T Y) is unchanged)
+    unsigned* amax = (hb && it < 1000) ? ticket + 1 + it : nullptr;
+    gemm_AQ(amax);
     CF_CHECK_LAUNCH();
     k_lr_sum_split<<<small_grid, 256, 0, st>>>(part, p.aq_splits, static_cast<size_t>(n) * RP, Y2, nullptr,
-                                               static_cast<size_t>(n) * RP);
+                                               static_cast<size_t>(n) * RP, amax);
     CF_CHECK_LAUNCH();
-    gemm_AtY();
+    gemm_AtY(amax != nullptr);
     CF_CHECK_LAUNCH();
     const bool last = it == iters - 1;
     // the bases between iterations only seed the next product; the one handed back to the caller (q_out) and U are
@@ -595,7 +615,7 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   gemm_AQ();  // U_temp = A Q
   CF_CHECK_LAUNCH();
   if (int rc = orth(p.aq_splits, n, p.gram_ctas_n, p.gram_rows_n, Y2, U, nullptr)) return rc;  // U = orth(A Q)
-  gemm_AtY();  // V^T = A^T U
+  gemm_AtY(hb);  // V^T = A^T U
   CF_CHECK_LAUNCH();
   k_lr_store_v_sum<<<small_grid, 256, 0, st>>>(part, p.aty_splits, static_cast<size_t>(c) * RP, V, c, RP, r);
   CF_CHECK_LAUNCH();

@@ -49,6 +49,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float2 split_tf32(float v) {
   uint32_t hi, lo;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
@@ -57,26 +63,73 @@ __device__ __forceinline__ float2 split_tf32(float v) {
   return make_float2(__uint_as_float(hi), __uint_as_float(lo));
 }
 
-// out2[i] = split(sum_s part[s][i]);  optionally the fp32 sum as well
+// fp16 image of a skinny operand with entries of modest size (an orthonormal basis, the N(0, 1) start, or a Y scaled
+// by a power of two, below): v ~= hi + lo * 2^-11 with hi = fp16(v), lo = fp16((v - hi) * 2^11): 22 bits, two fp16
+// MMAs per term instead of four TF32 ones and no conversion of the streamed operand (k_lr_gemm<.., HB = true>).
+// Stored as two planes, hi at [i] and lo at [count + i], in the buffer that otherwise holds the TF32 pairs.
+__device__ __forceinline__ void split_h16_store(float v, __half* planes, size_t i, size_t count) {
+  const __half hi = __float2half_rn(v);
+  planes[i] = hi;
+  planes[count + i] = __float2half_rn((v - __half2float(hi)) * 2048.f);
+}
+
+// out2[i] = split(sum_s part[s][i]);  optionally the fp32 sum as well.
+// absmax != nullptr: out2 receives fp16 planes of the sum times 2^-e, e chosen from the bound
+// S * max |partial| <= 2^14 * 2^e that the product kernel left in *absmax (fp32 bits of a non-negative number).
+// A power of two common to the whole matrix is exact and changes neither span(A^T Y) nor what the
+// orthonormalisation (scale-invariant: its shift is relative to the trace) returns.
 __global__ void __launch_bounds__(256) k_lr_sum_split(const float* __restrict__ part, int S, size_t stride,
-                                                     float2* __restrict__ out2, float* __restrict__ out32, size_t count) {
+                                                     float2* __restrict__ out2, float* __restrict__ out32, size_t count,
+                                                     const unsigned* __restrict__ absmax) {
+  float scale = 1.f;
+  if (absmax != nullptr) {
+    const float bound = static_cast<float>(S) * __uint_as_float(*absmax);
+    if (bound > 0.f && bound < 3.0e38f) scale = ldexpf(1.f, 13 - ilogbf(bound));   // bound * scale in [2^13, 2^14)
+  }
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < count;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float s = 0.f;
     for (int p = 0; p < S; ++p) s += part[static_cast<size_t>(p) * stride + i];
-    if (out2) out2[i] = split_tf32(s);
+    if (out2 && absmax != nullptr)
+      split_h16_store(s * scale, reinterpret_cast<__half*>(out2), i, count);
+    else if (out2)
+      out2[i] = split_tf32(s);
     if (out32) out32[i] = s;
   }
 }
 
-// (rows, r) compact fp32 -> (rows, RP) {hi, lo} pairs, zero padded
+// one row of RP values held in registers -> both planes, 16 bytes per store (2-byte stores cost the orthonormalisation
+// 6 us per call: 2 x RP store instructions per thread on 16 SMs)
+template <int RP>
+__device__ __forceinline__ void split_h16_store_row(const float (&xr)[RP], __half* planes, size_t row_off, size_t count) {
+#pragma unroll
+  for (int q = 0; q < RP / 8; ++q) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float v0 = xr[8 * q + 2 * w], v1 = xr[8 * q + 2 * w + 1];
+      const __half2 hi = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hi);
+      h[w] = h22u(hi);
+      l[w] = h22u(__floats2half2_rn((v0 - hf.x) * 2048.f, (v1 - hf.y) * 2048.f));
+    }
+    *reinterpret_cast<uint4*>(planes + row_off + 8 * q) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(planes + count + row_off + 8 * q) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// (rows, r) compact fp32 -> (rows, RP) {hi, lo} pairs (or fp16 planes), zero padded
 __global__ void __launch_bounds__(256) k_lr_pad_split(const float* __restrict__ src, float2* __restrict__ dst, int rows,
-                                                     int r, int RP) {
+                                                     int r, int RP, int half_planes) {
   const size_t total = static_cast<size_t>(rows) * RP;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int row = static_cast<int>(i / RP), j = static_cast<int>(i % RP);
-    dst[i] = (j < r) ? split_tf32(src[static_cast<size_t>(row) * r + j]) : make_float2(0.f, 0.f);
+    const float v = (j < r) ? src[static_cast<size_t>(row) * r + j] : 0.f;
+    if (half_planes)
+      split_h16_store(v, reinterpret_cast<__half*>(dst), i, total);
+    else
+      dst[i] = split_tf32(v);
   }
 }
 
@@ -86,17 +139,18 @@ __global__ void __launch_bounds__(256) k_lr_pad_split(const float* __restrict__ 
 //    TRANS: A' = A^T    (M = C, K = N)      Z = A^T Y
 // B2 = B pre-split into {hi, lo} TF32 pairs, (K, RP) row-major.   grid (ceil(M/128), splits), block 256
 // ---------------------------------------------------------------------------------------
-template <int RP, bool TRANS, int BK = kLrBK, int STAGES = kLrStages>
+template <int RP, bool TRANS, int BK = kLrBK, int STAGES = kLrStages, bool HB = false>
 __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __restrict__ x, const __half* __restrict__ base,
                                                 const float2* __restrict__ B2, float* __restrict__ out, int N, int C,
-                                                int k_per_split) {
+                                                int k_per_split, unsigned* __restrict__ absmax) {
   extern __shared__ __align__(128) unsigned char lr_smem_raw[];
   constexpr int kLdB = RP + 2;                               // float2 pitch: conflict-free 64-bit fragment loads
   // fp16 tile as stored in global memory: !TRANS 128 (m) x 64 (k), pitch 72;  TRANS 64 (k) x 128 (m), pitch 136
   constexpr int kRowsA = TRANS ? BK : kLrBM, kColsA = TRANS ? kLrBM : BK;
   constexpr int kLdA = kColsA + 8;
   constexpr int kTileA = kRowsA * kLdA * 2;                  // bytes
-  constexpr int kTileB = BK * kLdB * 8;
+  constexpr int kLdH = RP + 8;                               // HB: fp16 pitch of a B plane (16-byte rows, conflict-free ldmatrix)
+  constexpr int kTileB = HB ? 2 * BK * kLdH * 2 : BK * kLdB * 8;
   constexpr int kStage = 2 * kTileA + kTileB;
   const int M = TRANS ? C : N, K = TRANS ? N : C;
   const int m0 = blockIdx.x * kLrBM;
@@ -129,6 +183,19 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
       cp_async16(xs + r * kLdA + 8 * cc, x + off, ok);
       if (has_base) cp_async16(bs + r * kLdA + 8 * cc, base + off, ok);
     }
+    if (HB) {   // two fp16 planes (hi | lo) of the (K, RP) operand, `K * RP` halves apart
+      constexpr int kChunksH = BK * (RP / 8);
+      const __half* Bg = reinterpret_cast<const __half*>(B2);
+      __half* Bh = reinterpret_cast<__half*>(sp + 2 * kTileA);
+      for (int ch = tid; ch < 2 * kChunksH; ch += nthreads) {
+        const int plane = ch / kChunksH, rem = ch % kChunksH;
+        const int r = rem / (RP / 8), cc = rem % (RP / 8);
+        const bool ok = k0 + r < k_end;
+        const size_t off = ok ? (static_cast<size_t>(plane) * K * RP + static_cast<size_t>(k0 + r) * RP + 8 * cc) : 0;
+        cp_async16(Bh + (plane * BK + r) * kLdH + 8 * cc, Bg + off, ok);
+      }
+      return;
+    }
     constexpr int kChunksB = BK * RP / 2;  // 16-byte chunks = 2 float2
     for (int ch = tid; ch < kChunksB; ch += nthreads) {
       const int r = ch / (RP / 2), cc = ch % (RP / 2);
@@ -139,10 +206,14 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
   };
 
   float acc[RP / 8][4];
+  float accl[HB ? RP / 8 : 1][4];   // HB: the lo plane's products, scaled by 2^11
 #pragma unroll
   for (int j = 0; j < RP / 8; ++j)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    for (int e = 0; e < 4; ++e) {
+      acc[j][e] = 0.f;
+      if (HB) accl[HB ? j : 0][e] = 0.f;
+    }
 
   const int nchunks = (k_end - k_begin + BK - 1) / BK;
 #pragma unroll
@@ -177,6 +248,26 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
         scol = 16 * warp + (mi & 1) * 8;
         ldmatrix_x4_trans(fx, xs + srow * kLdA + scol);
         if (has_base) ldmatrix_x4_trans(fb, bs + srow * kLdA + scol);
+      }
+      if (HB) {
+        // fp16 m16n8k16: the delta fragment is the A operand as it is; B fragments of two adjacent column tiles
+        // per ldmatrix.trans from the [k][n] planes
+        uint32_t a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = has_base ? h22u(__hsub2_rn(u2h2(fx[q]), u2h2(fb[q]))) : fx[q];
+        const __half* Bh = reinterpret_cast<const __half*>(sp + 2 * kTileA);
+        const __half* brow_h = Bh + (16 * kk + l8 + (mi & 1) * 8) * kLdH + (mi >> 1) * 8;
+#pragma unroll
+        for (int j2 = 0; j2 < RP / 16; ++j2) {
+          uint32_t bh[4], bl[4];
+          ldmatrix_x4_trans(bh, brow_h + 16 * j2);
+          ldmatrix_x4_trans(bl, brow_h + BK * kLdH + 16 * j2);
+          mma_f16(acc[2 * j2], a, bh[0], bh[1]);
+          mma_f16(acc[2 * j2 + 1], a, bh[2], bh[3]);
+          mma_f16(accl[HB ? 2 * j2 : 0], a, bl[0], bl[1]);
+          mma_f16(accl[HB ? 2 * j2 + 1 : 0], a, bl[2], bl[3]);
+        }
+        continue;
       }
       uint32_t a_even[4], a_odd[4];
 #pragma unroll
@@ -213,6 +304,29 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
         if (j >= j_begin && j < j_end) mma_tf32(acc[j], a_odd, __float_as_uint(bo0[j].y), __float_as_uint(bo1[j].y));
     }
   }
+  if (HB) {
+#pragma unroll
+    for (int j = 0; j < RP / 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = fmaf(accl[HB ? j : 0][e], 1.0f / 2048.f, acc[j][e]);
+  }
+  if (absmax != nullptr) {
+    // largest |partial| of the launch (fp32 bits of non-negative numbers order like unsigned integers): the bound
+    // k_lr_sum_split scales the sum by before it splits it into fp16 planes
+    __shared__ unsigned cta_max;
+    if (tid == 0) cta_max = 0u;
+    __syncthreads();
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < RP / 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mx = fmaxf(mx, fabsf(acc[j][e]));
+#pragma unroll
+    for (int o_ = 16; o_ > 0; o_ >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o_));
+    if (lane == 0) atomicMax(&cta_max, __float_as_uint(mx));
+    __syncthreads();
+    if (tid == 0) atomicMax(absmax, cta_max);
+  }
   float* o = out + static_cast<size_t>(blockIdx.y) * M * RP;
   const int r0 = m0 + 16 * warp + g;
 #pragma unroll
@@ -225,10 +339,11 @@ __global__ void __launch_bounds__(2 * kLrThreads) k_lr_gemm(const __half* __rest
   }
 }
 
-template <int RP, bool TRANS, int BK = kLrBK, int STAGES = kLrStages>
+template <int RP, bool TRANS, int BK = kLrBK, int STAGES = kLrStages, bool HB = false>
 constexpr size_t lr_gemm_smem() {
   constexpr size_t rows = TRANS ? BK : kLrBM, cols = TRANS ? kLrBM : BK;
-  return STAGES * (2 * rows * (cols + 8) * 2 + static_cast<size_t>(BK) * (RP + 2) * 8);
+  constexpr size_t tile_b = HB ? 2 * static_cast<size_t>(BK) * (RP + 8) * 2 : static_cast<size_t>(BK) * (RP + 2) * 8;
+  return STAGES * (2 * rows * (cols + 8) * 2 + tile_b);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -394,7 +509,7 @@ template <int RP>
 __global__ void __launch_bounds__(128) k_lr_solve_out(float* __restrict__ X, const float* __restrict__ R,
                                                      const float* __restrict__ rdinv, int M, int r,
                                                      float2* __restrict__ out2, __half* __restrict__ out16,
-                                                     float* __restrict__ out32c) {
+                                                     float* __restrict__ out32c, int half_planes) {
   __shared__ __align__(16) float Rs[RP * RP];
   __shared__ float Ds[RP];
   for (int e = threadIdx.x; e < RP * RP; e += 128) Rs[e] = R[e];
@@ -418,7 +533,9 @@ __global__ void __launch_bounds__(128) k_lr_solve_out(float* __restrict__ X, con
   }
 #pragma unroll
   for (int q = 0; q < RP / 4; ++q) xrow[q] = make_float4(xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]);
-  if (out2) {
+  if (out2 && half_planes) {
+    split_h16_store_row<RP>(xr, reinterpret_cast<__half*>(out2), static_cast<size_t>(m) * RP, static_cast<size_t>(M) * RP);
+  } else if (out2) {
 #pragma unroll
     for (int j = 0; j < RP; ++j) out2[static_cast<size_t>(m) * RP + j] = split_tf32(xr[j]);
   }
@@ -437,12 +554,6 @@ __global__ void __launch_bounds__(128) k_lr_solve_out(float* __restrict__ X, con
 // staged through shared memory so that base is read and recon written in 16-byte row segments.
 // grid (ceil(C/256), ceil(N/64)), block 128
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 template <int KS>
 __global__ void __launch_bounds__(128) k_lr_reconstruct_mma(const __half* __restrict__ U, const __half* __restrict__ V,

@@ -43,6 +43,7 @@ struct OrthParams {
   float2* out2;          // optional (M, RP) {hi, lo} TF32 pairs (the next product's skinny operand)
   __half* out16;         // optional (M, r) fp16
   float* out32c;         // optional (M, r) compact fp32
+  int half_planes;       // out2 as two fp16 planes (hi | lo * 2^11) instead of TF32 pairs (split_h16_store)
   int light;             // 1: X only seeds the next product (an intermediate basis of the subspace iteration): any
                          // well-conditioned basis of span(X) gives the same next subspace, so ONE factorisation is
                          // enough when X is well conditioned (orthogonality error ~cond^2 u ~ 2e-4), two otherwise
@@ -359,7 +360,9 @@ __global__ void __launch_bounds__(kOrthThreads, 1) k_lr_orth(const OrthParams p)
     float xr[RP];
     load_row(xr, m);
     solve_row(xr);
-    if (p.out2) {
+    if (p.out2 && p.half_planes) {
+      split_h16_store_row<RP>(xr, reinterpret_cast<__half*>(p.out2), static_cast<size_t>(m) * RP, static_cast<size_t>(M) * RP);
+    } else if (p.out2) {
 #pragma unroll
       for (int j = 0; j < RP; ++j) p.out2[static_cast<size_t>(m) * RP + j] = split_tf32(xr[j]);
     }
