@@ -416,7 +416,9 @@ static bool lr_gemm_small() {
 }
 static void lr_split_cfg(int64_t M, int64_t K, int* splits, int* kper) {
   const int64_t m_tiles = (M + kLrBM - 1) / kLrBM;
-  const int64_t ctas = static_cast<int64_t>(sm_count()) * (lr_gemm_small() ? 2 : 1);
+  // CF_LR_CTAS_PER_SM (A/B): CTAs per SM the split-K factor aims at (default 2 with the small tiles, else 1)
+  static const int per_sm_env = [] { const char* e = getenv("CF_LR_CTAS_PER_SM"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 0; }();
+  const int64_t ctas = static_cast<int64_t>(sm_count()) * (per_sm_env ? per_sm_env : (lr_gemm_small() ? 2 : 1));
   int64_t s = (ctas + m_tiles / 2) / m_tiles;  // ~one CTA per SM (two with the small tiles), one wave
   if (s < 1) s = 1;
   if (s > 16) s = 16;
@@ -454,6 +456,29 @@ static LrMmaPlan make_lr_mma_plan(int64_t N, int64_t C, int r) {
   return p;
 }
 
+// one instantiation of the product kernel: opt-in shared memory size set once, then the launch
+template <int RP, bool TRANS, int BK, int ST, bool HB>
+static cudaError_t launch_lr_gemm(dim3 grid, cudaStream_t st, const __half* xh, const __half* bh, const float2* B2, float* part,
+                                  int n, int c, int kper, unsigned* absmax) {
+  constexpr size_t smem = lr_gemm_smem<RP, TRANS, BK, ST, HB>();
+  static bool ready = false;   // (per instantiation; one device per process)
+  if (!ready) {
+    cudaError_t e = cudaFuncSetAttribute(k_lr_gemm<RP, TRANS, BK, ST, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    ready = true;
+  }
+  k_lr_gemm<RP, TRANS, BK, ST, HB><<<grid, kLrThreads, smem, st>>>(xh, bh, B2, part, n, c, kper, absmax);
+  return cudaGetLastError();
+}
+// CF_LR_HB_TILE (A/B of the fp16-plane products): 0 = 32-wide K chunks x 2 stages, 1 = 32 x 3, 2 = 64 x 2 (default),
+// 3 = 64 x 3.  Measured at 4608 x 3072, r = 32 (A Q / A^T Y, us): 16.3 / 14.6, 15.0 / 14.6, 14.8 / 14.2, 16.4 / 16.4 --
+// a plateau at ~0.6 of the HBM roofline whatever the tile.
+static int lr_hb_tile() {
+  static const int v = [] { const char* e = getenv("CF_LR_HB_TILE"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2; }();
+  return v;
+}
+
 template <int RP>
 static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, __half* U, __half* V, float* q_out,
                           int n, int c, int r, int iters, char* ws, const LrMmaPlan& p, cudaStream_t st) {
@@ -487,32 +512,41 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   const bool small = lr_gemm_small();
   const size_t smem_ns = lr_gemm_smem<RP, false, 32, 2>(), smem_ts = lr_gemm_smem<RP, true, 32, 2>();
   constexpr bool kHalfOk = RP >= 16;   // (one ldmatrix.trans covers two 8-column tiles)
-  const size_t smem_nh = lr_gemm_smem<RP, false, 32, 2, kHalfOk>(), smem_th = lr_gemm_smem<RP, true, 32, 2, kHalfOk>();
   if (small) {
     CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ns)));
     CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ts)));
   }
-  if (hb) {
-    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, false, 32, 2, kHalfOk>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_nh)));
-    CF_CHECK_CUDA(cudaFuncSetAttribute(k_lr_gemm<RP, true, 32, 2, kHalfOk>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_th)));
-  }
-  auto gemm_AQ = [&](unsigned* absmax = nullptr) {  // part[s] (N, RP) = A Q
+  auto gemm_AQ = [&](unsigned* absmax = nullptr) -> cudaError_t {  // part[s] (N, RP) = A Q
     dim3 grid((n + kLrBM - 1) / kLrBM, p.aq_splits);
-    if (hb)
-      k_lr_gemm<RP, false, 32, 2, kHalfOk><<<grid, kLrThreads, smem_nh, st>>>(xh, bh, Q2, part, n, c, p.aq_kper, absmax);
-    else if (small)
+    if (hb) {
+      switch (lr_hb_tile()) {
+        case 1: return launch_lr_gemm<RP, false, 32, 3, kHalfOk>(grid, st, xh, bh, Q2, part, n, c, p.aq_kper, absmax);
+        case 2: return launch_lr_gemm<RP, false, 64, 2, kHalfOk>(grid, st, xh, bh, Q2, part, n, c, p.aq_kper, absmax);
+        case 3: return launch_lr_gemm<RP, false, 64, 3, kHalfOk>(grid, st, xh, bh, Q2, part, n, c, p.aq_kper, absmax);
+        default: return launch_lr_gemm<RP, false, 32, 2, kHalfOk>(grid, st, xh, bh, Q2, part, n, c, p.aq_kper, absmax);
+      }
+    }
+    if (small)
       k_lr_gemm<RP, false, 32, 2><<<grid, kLrThreads, smem_ns, st>>>(xh, bh, Q2, part, n, c, p.aq_kper, nullptr);
     else
       k_lr_gemm<RP, false><<<grid, gemm_threads, smem_n, st>>>(xh, bh, Q2, part, n, c, p.aq_kper, nullptr);
+    return cudaGetLastError();
   };
-  auto gemm_AtY = [&](bool planes = false) {  // part[s] (C, RP) = A^T Y; planes: Y2 holds fp16 planes (the orthonormal U)
+  auto gemm_AtY = [&](bool planes = false) -> cudaError_t {  // part[s] (C, RP) = A^T Y; planes: Y2 holds fp16 planes
     dim3 grid((c + kLrBM - 1) / kLrBM, p.aty_splits);
-    if (planes)
-      k_lr_gemm<RP, true, 32, 2, kHalfOk><<<grid, kLrThreads, smem_th, st>>>(xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
-    else if (small)
+    if (planes) {
+      switch (lr_hb_tile()) {
+        case 1: return launch_lr_gemm<RP, true, 32, 3, kHalfOk>(grid, st, xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
+        case 2: return launch_lr_gemm<RP, true, 64, 2, kHalfOk>(grid, st, xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
+        case 3: return launch_lr_gemm<RP, true, 64, 3, kHalfOk>(grid, st, xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
+        default: return launch_lr_gemm<RP, true, 32, 2, kHalfOk>(grid, st, xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
+      }
+    }
+    if (small)
       k_lr_gemm<RP, true, 32, 2><<<grid, kLrThreads, smem_ts, st>>>(xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
     else
       k_lr_gemm<RP, true><<<grid, gemm_threads, smem_t, st>>>(xh, bh, Y2, part, n, c, p.aty_kper, nullptr);
+    return cudaGetLastError();
   };
   // CholeskyQR2 of (sum of `S` partials, M x RP): result as TF32 pairs in out2 (+ fp16 / compact fp32 copies).
   // One launch on one 8-CTA cluster (k_lr_orth); CF_LR_ORTH=legacy keeps round 1's five-launch chain (A/B).
@@ -595,13 +629,11 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
     // the raw Y = A Q of an iteration has no a-priori bound: the product kernel records max |partial| and the sum
     // kernel scales Y by a power of two before splitting it into fp16 planes (span(A^T Y) is unchanged)
     unsigned* amax = (hb && it < 1000) ? ticket + 1 + it : nullptr;
-    gemm_AQ(amax);
-    CF_CHECK_LAUNCH();
+    CF_CHECK_CUDA(gemm_AQ(amax));
     k_lr_sum_split<<<small_grid, 256, 0, st>>>(part, p.aq_splits, static_cast<size_t>(n) * RP, Y2, nullptr,
                                                static_cast<size_t>(n) * RP, amax);
     CF_CHECK_LAUNCH();
-    gemm_AtY(amax != nullptr);
-    CF_CHECK_LAUNCH();
+    CF_CHECK_CUDA(gemm_AtY(amax != nullptr));
     const bool last = it == iters - 1;
     // the bases between iterations only seed the next product; the one handed back to the caller (q_out) and U are
     // orthonormalised in full
@@ -612,11 +644,9 @@ static int lr_mma_project(const __half* xh, const __half* bh, const float* q0, _
   }
   if (q_out != nullptr && !q_written)
     CF_CHECK_CUDA(cudaMemcpyAsync(q_out, q0, static_cast<size_t>(c) * r * 4, cudaMemcpyDeviceToDevice, st));
-  gemm_AQ();  // U_temp = A Q
-  CF_CHECK_LAUNCH();
+  CF_CHECK_CUDA(gemm_AQ());  // U_temp = A Q
   if (int rc = orth(p.aq_splits, n, p.gram_ctas_n, p.gram_rows_n, Y2, U, nullptr)) return rc;  // U = orth(A Q)
-  gemm_AtY(hb);  // V^T = A^T U
-  CF_CHECK_LAUNCH();
+  CF_CHECK_CUDA(gemm_AtY(hb));  // V^T = A^T U
   k_lr_store_v_sum<<<small_grid, 256, 0, st>>>(part, p.aty_splits, static_cast<size_t>(c) * RP, V, c, RP, r);
   CF_CHECK_LAUNCH();
   return CF_OK;
