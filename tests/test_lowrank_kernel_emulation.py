@@ -110,7 +110,7 @@ using namespace cf;
 template <int RP, bool HB = false>
 static int project(const __half* x, const __half* base, const float* q0, int n, int c, int r, int iters,
                    std::vector<__half>& U, std::vector<__half>& V) {
-  // HB: the bases Q and the orthonormal U as fp16 planes, k_lr_gemm<.., 32, 2, true> (lr_mma_project's default for RP >= 16)
+  // HB: the bases Q and the orthonormal U as fp16 planes, k_lr_gemm<.., 64, 2, true> (lr_mma_project's default for RP >= 16)
   const int aq_splits = 2, aty_splits = 3;
   const int aq_kper = ((c + aq_splits - 1) / aq_splits + kLrBK - 1) / kLrBK * kLrBK;
   const int aty_kper = ((n + aty_splits - 1) / aty_splits + kLrBK - 1) / kLrBK * kLrBK;
@@ -125,13 +125,13 @@ static int project(const __half* x, const __half* base, const float* q0, int n, 
   unsigned amax_slots[64] = {0};
   auto gemm_AQ = [&](unsigned* amax = nullptr) {
     launch((n + kLrBM - 1) / kLrBM, aq_s, kLrThreads, 1, [&] {
-      if (HB) k_lr_gemm<RP, false, 32, 2, HB>(x, base, Q2.data(), part.data(), n, c, aq_kper, amax);
+      if (HB) k_lr_gemm<RP, false, 64, 2, HB>(x, base, Q2.data(), part.data(), n, c, aq_kper, amax);
       else k_lr_gemm<RP, false>(x, base, Q2.data(), part.data(), n, c, aq_kper, nullptr);
     });
   };
   auto gemm_AtY = [&](bool planes = false) {
     launch((c + kLrBM - 1) / kLrBM, aty_s, kLrThreads, 1, [&] {
-      if (planes) k_lr_gemm<RP, true, 32, 2, HB>(x, base, Y2.data(), part.data(), n, c, aty_kper, nullptr);
+      if (planes) k_lr_gemm<RP, true, 64, 2, HB>(x, base, Y2.data(), part.data(), n, c, aty_kper, nullptr);
       else k_lr_gemm<RP, true>(x, base, Y2.data(), part.data(), n, c, aty_kper, nullptr);
     });
   };
