@@ -25,7 +25,7 @@ def fmt(v):
 
 
 def main():
-    n1 = {"serial": "r2_bench_n1_binary_with_gpu_reference.json", "dropin": "r2_bench_n1_dropin.json",
+    n1 = {"serial": "r2_final_bench.json", "dropin": "r2_bench_n1_dropin.json",
           "int2": "r2_bench_n1_int2.json", "dropin_graphs": "r2_bench_n1_dropin_layer_graphs.json",
           "lrq": "r2_bench_n1_lrq.json", "ring_lrq": "r2_bench_n1_ring_lrq.json"}
     print("# Round 2: per-step latency of the hot path at 1 / 2 / 4 / 8 B200 (bench.py, CUDA events, max over ranks)\n")
@@ -39,12 +39,12 @@ def main():
         ("FLUX, BINARY, through the hooks (`compact_fwd` per layer, eager)", "dropin"),
         ("FLUX, BINARY, through the hooks with `CF_LAYER_GRAPHS=1` (pointer-keyed per-layer graphs)", "dropin_graphs"),
         ("FLUX, INT2, engine", "int2"),
-        ("FLUX, LOW_RANK_Q r = 32, engine (eager)", "lrq"),
+        ("FLUX, LOW_RANK_Q r = 32, engine (eager; N = 8 measured before the fp16-plane products)", "lrq"),
         ("FLUX, uncompressed NCCL all-gather (sync patch parallel)", "raw"),
         ("FLUX, uncompressed NCCL P2P ring relay", "raw_ring"),
         ("FLUX, uncompressed stale-async all-gather (DistriFusion)", "raw_async"),
         ("CogVideoX-5b ring (42 layers, 2 x 17552 tokens), BINARY", "ring"),
-        ("CogVideoX-5b ring, LOW_RANK_Q r = 32 (the example's preset)", "ring_lrq"),
+        ("CogVideoX-5b ring, LOW_RANK_Q r = 32 (the example's preset; N = 8 measured before the fp16-plane products)", "ring_lrq"),
         ("CogVideoX-5b ring, uncompressed NCCL P2P ring", "ring_raw"),
         ("PixArt-alpha (28 layers, 2 x 4096 tokens, C = 1152), BINARY", "pixart"),
         ("PixArt-alpha, uncompressed all-gather", "pixart_raw"),
