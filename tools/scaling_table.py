@@ -44,7 +44,7 @@ def main():
         ("FLUX, uncompressed NCCL P2P ring relay", "raw_ring"),
         ("FLUX, uncompressed stale-async all-gather (DistriFusion)", "raw_async"),
         ("CogVideoX-5b ring (42 layers, 2 x 17552 tokens), BINARY", "ring"),
-        ("CogVideoX-5b ring, LOW_RANK_Q r = 32 (the example's preset; N = 8 measured before the fp16-plane products)", "ring_lrq"),
+        ("CogVideoX-5b ring, LOW_RANK_Q r = 32 (the example's preset; N = 1 and 8 measured before the fp16-plane products)", "ring_lrq"),
         ("CogVideoX-5b ring, uncompressed NCCL P2P ring", "ring_raw"),
         ("PixArt-alpha (28 layers, 2 x 4096 tokens, C = 1152), BINARY", "pixart"),
         ("PixArt-alpha, uncompressed all-gather", "pixart_raw"),
