@@ -172,10 +172,38 @@ def state_machine_goldens(ref):
     print("state_machine.npz:", len(out), "arrays")
 
 
+def lowrank_q_wire_goldens(ref):
+    """The LOW_RANK_Q wire codec on FIXED factors: the payload the reference assembles from U (N, r) and V (r, C)
+    (its own quantize_int4 on U and on V^T, concatenated as in slowpath.py:69-75) and what its slowpath_decompress
+    makes of that payload (slowpath.py:156-164).  Pins cf_lowrank_q_pack / cf_lowrank_q_reconstruct (and the oracle's
+    int4) against the reference itself, without the random start of subspace_iter in the way."""
+    from xfuser.compact import compress_quantize as cq
+    from xfuser.compact import slowpath as sp
+    from xfuser.compact.utils import COMPACT_COMPRESS_TYPE as T
+
+    out = {}
+    for name, seed, n, c, r in (("n64_c256_r4", 7, 64, 256, 4), ("n130_c264_r20", 8, 130, 264, 20), ("n96_c512_r32", 9, 96, 512, 32)):
+        g = torch.Generator().manual_seed(seed)
+        u = (torch.randn(n, r, generator=g) * 0.05).half()
+        v = (torch.randn(r, c, generator=g) * 3).half()
+        qu, su, mu = cq.quantize_int4(u)
+        qv, sv, mv = cq.quantize_int4(v.t())   # (slowpath.py:70: the transposed view)
+        parts = [qu.view(torch.half).reshape(-1), su.reshape(-1), mu.reshape(-1),
+                 qv.view(torch.half).reshape(-1), sv.reshape(-1), mv.reshape(-1)]
+        payload = torch.cat([p_.contiguous() for p_ in parts])
+        out[f"{name}/u"], out[f"{name}/v"] = bits(u), bits(v)
+        out[f"{name}/payload"] = bits(payload)
+        out[f"{name}/recon"] = bits(sp.slowpath_decompress(payload, (n, c), T.LOW_RANK_Q, rank=r))
+    np.savez_compressed(os.path.join(OUT, "lowrank_q_wire.npz"), **out)
+    print("lowrank_q_wire.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # reduction order independent of the host's core count
     ref = load_reference()
-    codec_goldens(ref)
-    slowpath_goldens(ref)
-    state_machine_goldens(ref)
+    only = sys.argv[1:]   # e.g. `python oracle/make_goldens.py lowrank_q_wire`: just that file
+    for name, fn in (("codecs", codec_goldens), ("slowpath", slowpath_goldens), ("state_machine", state_machine_goldens),
+                     ("lowrank_q_wire", lowrank_q_wire_goldens)):
+        if not only or name in only:
+            fn(ref)

@@ -81,6 +81,16 @@ def golden_slowpath():
 
 
 @pytest.fixture(scope="session")
+def golden_lowrank_q_wire():
+    """LOW_RANK_Q payloads the reference assembled from fixed factors, and its reconstructions of them
+    (oracle/make_goldens.py lowrank_q_wire_goldens)."""
+    return np.load(os.path.join(GOLDEN, "lowrank_q_wire.npz"))
+
+
+LRQ_WIRE_CASES = [("n64_c256_r4", 64, 256, 4), ("n130_c264_r20", 130, 264, 20), ("n96_c512_r32", 96, 512, 32)]
+
+
+@pytest.fixture(scope="session")
 def golden_state():
     return np.load(os.path.join(GOLDEN, "state_machine.npz"))
 

@@ -4,7 +4,7 @@ and basis conventions are arbitrary); tolerances are the 
 import pytest
 import torch
 
-from conftest import assert_bits_equal, h16, rel_l2
+from conftest import LRQ_WIRE_CASES, assert_bits_equal, h16, rel_l2
 from oracle import codecs as oc
 
 pytestmark = pytest.mark.gpu
@@ -161,6 +161,24 @@ def test_lowrank_q_pack_matches_two_quantize_calls(n, c, rank):
     got = lowrank_q_pack(u.to(dev), v.to(dev))
     assert got.numel() == (n * rank + c * rank) // 4 + 4 * rank
     assert_bits_equal(got, want, "LOW_RANK_Q payload")
+
+
+@pytest.mark.parametrize("name,n,c,r", LRQ_WIRE_CASES)
+def test_lowrank_q_wire_codec_vs_reference_goldens(golden_lowrank_q_wire, name, n, c, r):
+    """Fixed factors U, V through the reference's own quantize_int4 + concatenation (slowpath.py:69-75) and its
+    slowpath_decompress (slowpath.py:156-164), recorded by oracle/make_goldens.py: cf_lowrank_q_pack reproduces the
+    reference's payload bit for bit; cf_lowrank_q_reconstruct decodes the reference's payload to the reference's
+    reconstruction up to the rounding of the fp16 product (summation order is the only freedom)."""
+    dev = _cuda()
+    from compactfusion_b200.compress_lowrank import lowrank_q_pack, lowrank_q_reconstruct
+    g = golden_lowrank_q_wire
+    u, v = h16(g[f"{name}/u"]), h16(g[f"{name}/v"])
+    want, ref = h16(g[f"{name}/payload"]), h16(g[f"{name}/recon"])
+    got = lowrank_q_pack(u.to(dev), v.to(dev)).cpu()
+    assert_bits_equal(got, want, "LOW_RANK_Q payload vs the reference's")
+    rec = lowrank_q_reconstruct(want.to(dev), n, c, r).cpu()
+    assert rel_l2(rec, ref) < 1e-3, rel_l2(rec, ref)
+    assert float((rec.float() - ref.float()).abs().max()) <= 2e-2
 
 
 def test_lowrank_state_machine_ef_invariant():

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import CODEC_CASES, assert_bits_equal, h16, rel_l2
+from conftest import LRQ_WIRE_CASES, CODEC_CASES, assert_bits_equal, h16, rel_l2
 from oracle import codecs
 from oracle.state import OracleCompact
 
@@ -122,6 +122,24 @@ def test_slowpath_payloads(golden_slowpath, name, ctype, kw):
     assert_bits_equal(codecs.slowpath_decompress(p, x.shape, ctype, **kw), h16(g[f"{name}/recon"]), "recon")
     torch.manual_seed(123)
     assert_bits_equal(codecs.sim_compress(x, ctype, **kw), h16(g[f"{name}/sim"]), "sim")
+
+
+@pytest.mark.parametrize("name,n,c,r", LRQ_WIRE_CASES)
+def test_lowrank_q_wire_codec_on_fixed_factors(golden_lowrank_q_wire, name, n, c, r):
+    """slowpath.py:69-75 / :156-164 on fixed U, V: the oracle's int4 assembles the reference's payload bit for bit
+    and decodes it to the reference's reconstruction (fp16 matmul: fp32 accumulation, one rounding)."""
+    g = golden_lowrank_q_wire
+    u, v = h16(g[f"{name}/u"]), h16(g[f"{name}/v"])
+    parts = []
+    for t in (u, v.t().contiguous()):
+        q, s, m = codecs.int4_quantize(t)
+        parts += [torch.from_numpy(q.copy()).contiguous().view(-1).view(torch.half), s.reshape(-1), m.reshape(-1)]
+    payload = torch.cat(parts)
+    want = h16(g[f"{name}/payload"])
+    assert_bits_equal(payload, want, "LOW_RANK_Q payload from fixed factors")
+    rec = codecs.slowpath_decompress(want, (n, c), "low-rank-int4", rank=r)
+    ref = h16(g[f"{name}/recon"])
+    assert rel_l2(rec, ref) < 1e-3 and float((rec.float() - ref.float()).abs().max()) <= 2e-2
 
 
 STATE_FLAVOURS = {
