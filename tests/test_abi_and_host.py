@@ -734,3 +734,28 @@ def test_dropin_hot_caches_per_layer_and_respects_type_and_config(monkeypatch):
     assert calls["usable"] == 4 and calls["lookup"] == 3
     dropin.shutdown()
     assert not dropin._hot and not dropin._fast
+
+
+# ---------------- the INT4 encode's exact-quotient shortcut (csrc/cf_minmax_codecs.cu, int4_codes2) ----------------
+def test_int4_bracketed_quotient_never_accepts_a_wrong_fp16_value():
+    """RN16 of both ends of [t (1 - 2^-21), t (1 + 2^-21)], t = RN32(a * RN32(1 / s)): whenever they agree they equal
+    the reference's fp16(a / s) -- every finite fp16 numerator against 60 scales here (tools/check_int4_bracket.py runs
+    3000), and the division is needed for well under 1 % of the elements."""
+    import numpy as np
+    a = np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16).astype(np.float32)
+    rng = np.random.default_rng(1)
+    s_bits = rng.integers(1, 0x7C00, size=60, dtype=np.uint16)
+    s_bits[:6] = [1, 0x03FF, 0x0400, 0x3C00, 0x7BFF, 0x2E66]
+    k_lo, k_hi = np.float32(1.0) - np.float32(2.0 ** -21), np.float32(1.0) + np.float32(2.0 ** -21)
+    wrong = fallback = 0
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for sb in s_bits:
+            s = np.array([sb], dtype=np.uint16).view(np.float16).astype(np.float32)[0]
+            ref = (a / s).astype(np.float16).view(np.uint16)
+            t = a * (np.float32(1.0) / s)
+            lo, hi = (t * k_lo).astype(np.float16).view(np.uint16), (t * k_hi).astype(np.float16).view(np.uint16)
+            same = lo == hi
+            wrong += int((lo[same] != ref[same]).sum())
+            fallback += int((~same).sum())
+    assert wrong == 0
+    assert fallback < 0.01 * a.size * len(s_bits)
